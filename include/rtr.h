@@ -1,0 +1,247 @@
+/*
+ * rtr.h -- C ABI of librtr_b200.so: the B200-native (sm_100a) replacement for the
+ * acceleration-structure + ray-cast path of MrBigoudi/RealTimeRaytracing.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout).  Conventions:
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - every call returns int: 0 = RTR_OK, negative = RTR_E_*; rtr_last_error() gives text;
+ *     nothing exits or throws across the ABI (the reference prints and exit()s,
+ *     srcCommon/core/errorHandler.cpp:13-29 -- the C++ shim in rtr_scene.hpp restores that);
+ *   - inputs are borrowed for the duration of the call; outputs go to caller-owned buffers;
+ *     opaque rtr_ctx / rtr_bvh own device memory, destroyed explicitly;
+ *   - one rtr_ctx per (host thread, GPU); calls on one ctx are not re-entrant;
+ *   - names ending in _dev take DEVICE pointers and are asynchronous on the ctx stream;
+ *     the others take HOST pointers, copy in/out and return after completion;
+ *   - there is NO CPU fallback: without a usable CUDA device rtr_ctx_create fails with
+ *     RTR_E_NODEVICE and nothing else can be called.
+ */
+#ifndef RTR_H
+#define RTR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTR_OK 0
+#define RTR_E_INVALID (-1)     /* bad argument */
+#define RTR_E_CUDA (-2)        /* CUDA runtime error, see rtr_last_error */
+#define RTR_E_NOMEM (-3)       /* device or pinned-host allocation failed */
+#define RTR_E_NODEVICE (-4)    /* no CUDA device / wrong architecture */
+#define RTR_E_UNSUPPORTED (-5) /* size outside the supported range */
+#define RTR_E_STATE (-6)       /* object not in the state the call needs */
+#define RTR_E_COMM (-7)        /* NCCL error / libnccl not loadable */
+
+#define RTR_DEFAULT_SEARCH_RADIUS 16u /* PlocParams::_SEARCH_RADIUS, bvh.hpp:66 */
+#define RTR_MAX_SEARCH_RADIUS 16u
+#define RTR_NONE 0xFFFFFFFFu
+
+/* ---- reference record layouts (SURVEY.md App. A rule 10) ---- */
+
+/* cr::TriangleGPU, srcCommon/scene/geometry/triangle.hpp:9-14 (64 B, _ModelId at 48) */
+typedef struct rtr_triangle {
+    float p0[4];
+    float p1[4];
+    float p2[4];
+    uint32_t model_id;
+    uint32_t pad[3];
+} rtr_triangle;
+
+/* cr::MeshModelGPU, srcCommon/scene/geometry/mesh.hpp:12-15 (68 B host layout, Q7) */
+typedef struct rtr_mesh {
+    float model[16]; /* column-major */
+    uint32_t material_id;
+} rtr_mesh;
+
+/* cr::BVH_NodeGPU, srcCommon/scene/geometry/bvh.hpp:22-42 (48 B); leaf <=> left==0 && right==0 */
+typedef struct rtr_node {
+    float bmin[3];
+    uint32_t pad0;
+    float bmax[3];
+    uint32_t pad1;
+    uint32_t triangle_id;
+    uint32_t left;
+    uint32_t right;
+    uint32_t pad2;
+} rtr_node;
+
+/* cr::CameraGPU, srcCommon/scene/camera.hpp:21-30 */
+typedef struct rtr_camera {
+    float view[16];
+    float proj[16];
+    float inv_view[16];
+    float inv_proj[16];
+    float eye[4];
+    float plane_width;
+    float plane_height;
+    float plane_near;
+} rtr_camera;
+
+/* Ray, srcCommon/shaders/raytracer.glsl:14-17 */
+typedef struct rtr_ray {
+    float origin[4];
+    float direction[4];
+} rtr_ray;
+
+/* Hit, srcCommon/shaders/raytracer.glsl:36-40 ; (b0,b1,b2,t), DidHit, TriangleId */
+typedef struct rtr_hit {
+    float b0, b1, b2, t;
+    uint32_t did_hit;
+    uint32_t triangle_id;
+} rtr_hit;
+
+typedef struct rtr_ctx rtr_ctx;
+typedef struct rtr_bvh rtr_bvh;
+
+/* ---- context ---- */
+const char* rtr_version(void);
+/* replaces glr::Application::dummyApplication() (srcOpenGL/application.cpp:416-423) as the
+ * "give me a device context" step of the tests and of Application::init (:281-295) */
+int rtr_ctx_create(int device, rtr_ctx** out);
+int rtr_ctx_destroy(rtr_ctx* ctx);
+/* ctx may be NULL: returns the last error of a failed rtr_ctx_create on this thread */
+const char* rtr_last_error(const rtr_ctx* ctx);
+int rtr_ctx_sync(rtr_ctx* ctx);
+void* rtr_ctx_stream(rtr_ctx* ctx);                 /* cudaStream_t the ctx launches on */
+int rtr_ctx_set_stream(rtr_ctx* ctx, void* stream); /* adopt a caller-owned cudaStream_t */
+int rtr_ctx_device(const rtr_ctx* ctx);
+int rtr_ctx_sm_count(const rtr_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
+uint64_t rtr_ctx_launch_count(const rtr_ctx* ctx);
+
+/* pinned host buffers for the host-pointer entry points (plain malloc'd memory also works) */
+int rtr_host_alloc(size_t bytes, void** out);
+int rtr_host_free(void* p);
+/* device buffers for C/C++ hosts (replace glCreateBuffers/glNamedBufferStorage,
+ * tests/testsSortGPU/testHistogramCreation.cpp:75-85, and glGetNamedBufferSubData :131) */
+int rtr_dev_alloc(rtr_ctx* ctx, size_t bytes, void** out);
+int rtr_dev_free(rtr_ctx* ctx, void* p);
+int rtr_dev_upload(rtr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int rtr_dev_download(rtr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int rtr_dev_zero(rtr_ctx* ctx, void* dst_dev, size_t bytes);
+
+/* ---- sort pre-passes pinned by tests/testsSortGPU ---- */
+/* srcCommon/shaders/ploc/preprocessing/sort/histogramOfGlobalDigitCounts.glsl:31-59 :
+ * out[b] = number of keys with bit b set.  The _dev form ADDS into out_dev (the shader
+ * atomically accumulates into a pre-zeroed SSBO, testHistogramCreation.cpp:113-116). */
+int rtr_bit_histogram32(rtr_ctx* ctx, const uint32_t* keys, uint32_t n, uint32_t out[32]);
+int rtr_bit_histogram32_dev(rtr_ctx* ctx, const uint32_t* keys_dev, uint32_t n, uint32_t* out_dev);
+/* .../sort/prefixSumOfGlobalDigitCounts.glsl:24-69 : exclusive scan inside each group of 4 bins */
+int rtr_digitplace_exclusive_scan(rtr_ctx* ctx, const uint32_t in[32], uint32_t out[32]);
+int rtr_digitplace_exclusive_scan_dev(rtr_ctx* ctx, const uint32_t* in_dev, uint32_t* out_dev);
+
+/* ---- LSD radix sort (Onesweep).  Replaces the std::sort of (code,index) pairs at
+ * srcCommon/scene/geometry/bvh.cpp:223-231 and the unfinished chainedScanDigitBinning.glsl.
+ * Stable; ascending; in place from the caller's point of view.  n < 2^30. ---- */
+int rtr_sort_keys_u32(rtr_ctx* ctx, uint32_t* keys, uint32_t n);
+int rtr_sort_pairs_u32(rtr_ctx* ctx, uint32_t* keys, uint32_t* values, uint32_t n);
+int rtr_sort_keys_u64(rtr_ctx* ctx, uint64_t* keys, uint32_t n);
+int rtr_sort_pairs_u64(rtr_ctx* ctx, uint64_t* keys, uint32_t* values, uint32_t n);
+/* device forms: values_dev may be NULL (keys only); bits [begin_bit, end_bit) take part */
+int rtr_sort_pairs_u32_dev(rtr_ctx* ctx, uint32_t* keys_dev, uint32_t* values_dev, uint32_t n,
+                           int begin_bit, int end_bit);
+int rtr_sort_pairs_u64_dev(rtr_ctx* ctx, uint64_t* keys_dev, uint32_t* values_dev, uint32_t n,
+                           int begin_bit, int end_bit);
+
+/* ---- Morton codes: BVH::getMortonCodes, bvh.cpp:330-348 (:235-328, :350-372) and the
+ * stub shader ploc/preprocessing/preprocessing.glsl.  tris_array_len is the length of the
+ * vector the reference computes the scene box over (Q2); codes are in input order. ---- */
+int rtr_morton_codes(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t tris_array_len,
+                     const rtr_mesh* meshes, uint32_t nb_meshes, uint32_t* codes_out);
+int rtr_morton_codes_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uint32_t tris_array_len,
+                         const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t* codes_dev);
+/* 21-bit-per-axis extension (no reference definition) */
+int rtr_morton_codes64(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t tris_array_len,
+                       const rtr_mesh* meshes, uint32_t nb_meshes, uint64_t* codes_out);
+/* out[0..5] = scene AABB min,max (bvh.cpp:235-251); out[6..11] = "circumscribed cube" (bvh.cpp:253-303) */
+int rtr_scene_bounds(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t tris_array_len,
+                     const rtr_mesh* meshes, uint32_t nb_meshes, float out[12]);
+
+/* ---- BVH build: replaces cr::BVH::BVH(nbTriangles, unsortedTriangles, meshesInTheScene)
+ * (bvh.hpp:89-91, bvh.cpp:11-24) as called from glr::Scene::bindSSBO (scene.cpp:148) plus the
+ * flatten glr::Scene::getBVH_NodesToGPUData (scene.cpp:189-208). ---- */
+/* host inputs: copies them to the device (as the reference ctor copies its vectors) and
+ * returns after the build finished.  *out must be NULL or a BVH from this ctx to reuse. */
+int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t nb_triangles, uint32_t tris_array_len,
+                  const rtr_mesh* meshes, uint32_t nb_meshes, uint32_t search_radius, rtr_bvh** out);
+/* device inputs, borrowed (must stay alive while the BVH is traced); asynchronous */
+int rtr_bvh_build_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t nb_triangles, uint32_t tris_array_len,
+                      const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t search_radius, rtr_bvh** out);
+int rtr_bvh_destroy(rtr_bvh* bvh);
+uint32_t rtr_bvh_nb_triangles(const rtr_bvh* bvh);
+uint32_t rtr_bvh_nb_nodes(const rtr_bvh* bvh); /* 2n-1 */
+/* PLOC iterations of the last build and its trace (n_i active clusters, m_i merges) */
+int rtr_bvh_iteration_trace(rtr_bvh* bvh, uint32_t* active, uint32_t* merges, uint32_t capacity, uint32_t* count);
+/* per-stage device times of the last build in ms: [0] scene box + Morton, [1] sort, [2] leaf init,
+ * [3] PLOC loop, [4] flatten, [5] total.  Only measured when enabled. */
+int rtr_bvh_enable_stage_timing(rtr_bvh* bvh, int enable);
+int rtr_bvh_stage_ms(rtr_bvh* bvh, float out[6]);
+/* sorted Morton codes (PlocParams::_MortonCodes) and BVH_Params::_TriangleIndices (bvh.hpp:55) */
+int rtr_bvh_morton_codes(rtr_bvh* bvh, uint32_t* out);
+int rtr_bvh_triangle_indices(rtr_bvh* bvh, uint32_t* out);
+/* BVH_Params::_Clusters/_Parent/_LeftChild/_RightChild/_IsLeaf (bvh.hpp:50-54) by cluster id,
+ * ids in serial-merge order (Q3); absent links are RTR_NONE; any pointer may be NULL */
+int rtr_bvh_clusters(rtr_bvh* bvh, rtr_node* clusters, uint32_t* parent, uint32_t* left, uint32_t* right,
+                     uint8_t* is_leaf);
+/* DFS pre-order array of scene.cpp:203-208 */
+int rtr_bvh_flat_nodes(rtr_bvh* bvh, rtr_node* out);
+const rtr_node* rtr_bvh_device_nodes(const rtr_bvh* bvh);
+const rtr_triangle* rtr_bvh_device_triangles(const rtr_bvh* bvh);
+const rtr_mesh* rtr_bvh_device_meshes(const rtr_bvh* bvh);
+/* wrap device arrays produced elsewhere (e.g. received by a broadcast) as a traceable BVH; borrowed */
+int rtr_bvh_adopt_dev(rtr_ctx* ctx, const rtr_node* nodes_dev, uint32_t nb_triangles,
+                      const rtr_triangle* tris_dev, const rtr_mesh* meshes_dev, uint32_t nb_meshes,
+                      rtr_bvh** out);
+
+/* ---- traversal: replaces glDispatchCompute on raytracer.glsl (srcOpenGL/application.cpp:245).
+ * denom_w/denom_h are the pixel-position divisors numGroups*16 of raytracer.glsl:304-305 (Q5);
+ * pass 0 for the reference formula floor(W/16)*16.  Pixels at or beyond the divisors are not
+ * traced (their records are zero).  Rows [row0,row1) are produced (row1 = 0 means height). ---- */
+#define RTR_TRACE_DEFAULT 0u
+/* visit nodes exactly as getClosestHitBVH does (raytracer.glsl:246-295): no pruning, right child
+ * first.  The default order prunes by the closest hit found so far with a conservative margin
+ * and returns identical results. */
+#define RTR_TRACE_REFERENCE_ORDER 1u
+
+int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+                      uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+                      uint32_t flags, rtr_hit* hits_out /* [height*width] */);
+int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+                          uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+                          uint32_t row0, uint32_t row1, uint32_t flags, rtr_hit* hits_dev /* [(row1-row0)*width] */);
+/* explicit ray batches (getClosestHitBVH semantics); any_hit != 0: did_hit = 1 iff a hit with
+ * t < t_max[i] exists (t_max NULL = +inf), other fields zero */
+int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays, uint64_t n_rays, int any_hit,
+                   const float* t_max, uint32_t flags, rtr_hit* hits_out);
+int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays_dev, uint64_t n_rays, int any_hit,
+                       const float* t_max_dev, uint32_t flags, rtr_hit* hits_dev);
+/* multi-bounce frame (definition in DESIGN.md "secondary rays"): rgba32f like the reference's
+ * image unit 0 (srcOpenGL/application.cpp:335,341).  rgba / primary_hits / rays_traced may be NULL. */
+int rtr_render(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+               uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+               uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
+               uint32_t flags, float* rgba_out, rtr_hit* primary_hits_out, uint64_t* rays_traced);
+int rtr_render_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+                   uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+                   uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
+                   uint32_t flags, float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
+
+/* ---- multi-GPU (one process per GPU; NCCL resolved at run time with dlopen("libnccl.so.2"),
+ * so inside a torch process it is the very library torch.distributed already loaded) ---- */
+#define RTR_NCCL_UNIQUE_ID_BYTES 128
+int rtr_comm_unique_id(void* id_out /* 128 B */);
+int rtr_comm_init(rtr_ctx* ctx, const void* unique_id, int rank, int nranks);
+int rtr_comm_destroy(rtr_ctx* ctx);
+/* root: sends flat nodes + triangles + meshes of *bvh; others: receive into a BVH they own */
+int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root);
+/* rows of the image are dealt to ranks in blocks of `rows_per_block`, block b -> rank b % nranks */
+int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                       uint32_t rows_per_block);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTR_H */

@@ -1,0 +1,466 @@
+"""ctypes binding of librtr_b200.so (include/rtr.h).  No fallback: if the CUDA library is
+missing or no B200 is present the constructors raise -- nothing here computes on the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .layouts import CAMERA, HIT, MESH, NODE, RAY, TRIANGLE
+
+RTR_OK = 0
+ERROR_NAMES = {0: "RTR_OK", -1: "RTR_E_INVALID", -2: "RTR_E_CUDA", -3: "RTR_E_NOMEM", -4: "RTR_E_NODEVICE",
+               -5: "RTR_E_UNSUPPORTED", -6: "RTR_E_STATE", -7: "RTR_E_COMM"}
+TRACE_DEFAULT = 0
+TRACE_REFERENCE_ORDER = 1
+NCCL_UNIQUE_ID_BYTES = 128
+
+# every symbol include/rtr.h declares (tests/test_abi.py checks the header against this list and the .so)
+SYMBOLS = [
+    "rtr_version", "rtr_ctx_create", "rtr_ctx_destroy", "rtr_last_error", "rtr_ctx_sync", "rtr_ctx_stream",
+    "rtr_ctx_set_stream", "rtr_ctx_device", "rtr_ctx_sm_count", "rtr_ctx_launch_count",
+    "rtr_host_alloc", "rtr_host_free", "rtr_dev_alloc", "rtr_dev_free", "rtr_dev_upload", "rtr_dev_download",
+    "rtr_dev_zero",
+    "rtr_bit_histogram32", "rtr_bit_histogram32_dev", "rtr_digitplace_exclusive_scan",
+    "rtr_digitplace_exclusive_scan_dev",
+    "rtr_sort_keys_u32", "rtr_sort_pairs_u32", "rtr_sort_keys_u64", "rtr_sort_pairs_u64",
+    "rtr_sort_pairs_u32_dev", "rtr_sort_pairs_u64_dev",
+    "rtr_morton_codes", "rtr_morton_codes_dev", "rtr_morton_codes64", "rtr_scene_bounds",
+    "rtr_bvh_build", "rtr_bvh_build_dev", "rtr_bvh_destroy", "rtr_bvh_nb_triangles", "rtr_bvh_nb_nodes",
+    "rtr_bvh_iteration_trace", "rtr_bvh_enable_stage_timing", "rtr_bvh_stage_ms", "rtr_bvh_morton_codes",
+    "rtr_bvh_triangle_indices", "rtr_bvh_clusters", "rtr_bvh_flat_nodes", "rtr_bvh_device_nodes",
+    "rtr_bvh_device_triangles", "rtr_bvh_device_meshes", "rtr_bvh_adopt_dev",
+    "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
+    "rtr_render_dev",
+    "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
+]
+
+
+class RtrError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s (%d): %s" % (ERROR_NAMES.get(code, "RTR_E_?"), code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library():
+    """dlopen librtr_b200.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s is missing: run `python -m realtimeraytracing_b200.build` (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
+    pp = C.POINTER(C.c_void_p)
+    L.rtr_version.restype = C.c_char_p
+    L.rtr_ctx_create.argtypes = [i32, pp]
+    L.rtr_ctx_destroy.argtypes = [vp]
+    L.rtr_last_error.argtypes = [vp]
+    L.rtr_last_error.restype = C.c_char_p
+    L.rtr_ctx_sync.argtypes = [vp]
+    L.rtr_ctx_stream.argtypes = [vp]
+    L.rtr_ctx_stream.restype = vp
+    L.rtr_ctx_set_stream.argtypes = [vp, vp]
+    L.rtr_ctx_device.argtypes = [vp]
+    L.rtr_ctx_sm_count.argtypes = [vp]
+    L.rtr_ctx_launch_count.argtypes = [vp]
+    L.rtr_ctx_launch_count.restype = u64
+    L.rtr_host_alloc.argtypes = [sz, pp]
+    L.rtr_host_free.argtypes = [vp]
+    L.rtr_dev_alloc.argtypes = [vp, sz, pp]
+    L.rtr_dev_free.argtypes = [vp, vp]
+    L.rtr_dev_upload.argtypes = [vp, vp, vp, sz]
+    L.rtr_dev_download.argtypes = [vp, vp, vp, sz]
+    L.rtr_dev_zero.argtypes = [vp, vp, sz]
+    L.rtr_bit_histogram32.argtypes = [vp, vp, u32, vp]
+    L.rtr_bit_histogram32_dev.argtypes = [vp, vp, u32, vp]
+    L.rtr_digitplace_exclusive_scan.argtypes = [vp, vp, vp]
+    L.rtr_digitplace_exclusive_scan_dev.argtypes = [vp, vp, vp]
+    L.rtr_sort_keys_u32.argtypes = [vp, vp, u32]
+    L.rtr_sort_pairs_u32.argtypes = [vp, vp, vp, u32]
+    L.rtr_sort_keys_u64.argtypes = [vp, vp, u32]
+    L.rtr_sort_pairs_u64.argtypes = [vp, vp, vp, u32]
+    L.rtr_sort_pairs_u32_dev.argtypes = [vp, vp, vp, u32, i32, i32]
+    L.rtr_sort_pairs_u64_dev.argtypes = [vp, vp, vp, u32, i32, i32]
+    L.rtr_morton_codes.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+    L.rtr_morton_codes_dev.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+    L.rtr_morton_codes64.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+    L.rtr_scene_bounds.argtypes = [vp, vp, u32, vp, u32, vp]
+    L.rtr_bvh_build.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
+    L.rtr_bvh_build_dev.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
+    L.rtr_bvh_destroy.argtypes = [vp]
+    L.rtr_bvh_nb_triangles.argtypes = [vp]
+    L.rtr_bvh_nb_triangles.restype = u32
+    L.rtr_bvh_nb_nodes.argtypes = [vp]
+    L.rtr_bvh_nb_nodes.restype = u32
+    L.rtr_bvh_iteration_trace.argtypes = [vp, vp, vp, u32, vp]
+    L.rtr_bvh_enable_stage_timing.argtypes = [vp, i32]
+    L.rtr_bvh_stage_ms.argtypes = [vp, vp]
+    L.rtr_bvh_morton_codes.argtypes = [vp, vp]
+    L.rtr_bvh_triangle_indices.argtypes = [vp, vp]
+    L.rtr_bvh_clusters.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rtr_bvh_flat_nodes.argtypes = [vp, vp]
+    for name in ("rtr_bvh_device_nodes", "rtr_bvh_device_triangles", "rtr_bvh_device_meshes"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.rtr_bvh_adopt_dev.argtypes = [vp, vp, u32, vp, vp, u32, pp]
+    L.rtr_trace_primary.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp]
+    L.rtr_trace_primary_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, vp]
+    L.rtr_trace_rays.argtypes = [vp, vp, vp, u64, i32, vp, u32, vp]
+    L.rtr_trace_rays_dev.argtypes = [vp, vp, vp, u64, i32, vp, u32, vp]
+    L.rtr_render.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, u32, vp, vp, vp]
+    L.rtr_render_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, u32, vp, vp, vp]
+    L.rtr_comm_unique_id.argtypes = [vp]
+    L.rtr_comm_init.argtypes = [vp, vp, i32, i32]
+    L.rtr_comm_destroy.argtypes = [vp]
+    L.rtr_bvh_broadcast.argtypes = [vp, pp, i32]
+    L.rtr_allgather_rows.argtypes = [vp, vp, u32, u32, u32, u32]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """Host numpy array, raw device address (int) or None -> c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def _as(a, dtype):
+    a = np.ascontiguousarray(a)
+    if a.dtype != dtype:
+        if dtype.fields is not None:
+            raise TypeError("expected an array of dtype %s" % (dtype,))
+        a = a.astype(dtype)
+    return a
+
+
+class Context:
+    """rtr_ctx: one per (host thread, GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.rtr_ctx_create(device, C.byref(h))
+        if rc != RTR_OK:
+            raise RtrError(rc, (self.lib.rtr_last_error(None) or b"").decode())
+        self.handle = h
+
+    def check(self, rc):
+        if rc != RTR_OK:
+            raise RtrError(rc, (self.lib.rtr_last_error(self.handle) or b"").decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.rtr_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def sync(self):
+        self.check(self.lib.rtr_ctx_sync(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.rtr_ctx_stream(self.handle) or 0)
+
+    def set_stream(self, stream: int):
+        self.check(self.lib.rtr_ctx_set_stream(self.handle, C.c_void_p(stream)))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.rtr_ctx_sm_count(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rtr_ctx_launch_count(self.handle))
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.lib.rtr_dev_alloc(self.handle, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def dev_free(self, ptr: int):
+        self.check(self.lib.rtr_dev_free(self.handle, C.c_void_p(ptr)))
+
+    def upload(self, dst_dev: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self.check(self.lib.rtr_dev_upload(self.handle, C.c_void_p(dst_dev), _ptr(src), src.nbytes))
+
+    def download(self, dst: np.ndarray, src_dev: int):
+        self.check(self.lib.rtr_dev_download(self.handle, _ptr(dst), C.c_void_p(src_dev), dst.nbytes))
+
+    def zero(self, dst_dev: int, nbytes: int):
+        self.check(self.lib.rtr_dev_zero(self.handle, C.c_void_p(dst_dev), nbytes))
+
+    # ---- testsSortGPU stage entries ----
+    def bit_histogram32(self, keys) -> np.ndarray:
+        keys = _as(keys, np.dtype(np.uint32))
+        out = np.zeros(32, dtype=np.uint32)
+        self.check(self.lib.rtr_bit_histogram32(self.handle, _ptr(keys), keys.size, _ptr(out)))
+        return out
+
+    def bit_histogram32_dev(self, keys_dev: int, n: int, out_dev: int):
+        self.check(self.lib.rtr_bit_histogram32_dev(self.handle, C.c_void_p(keys_dev), n, C.c_void_p(out_dev)))
+
+    def digitplace_exclusive_scan(self, hist) -> np.ndarray:
+        hist = _as(hist, np.dtype(np.uint32))
+        if hist.size != 32:
+            raise ValueError("expects the 32-bin histogram")
+        out = np.zeros(32, dtype=np.uint32)
+        self.check(self.lib.rtr_digitplace_exclusive_scan(self.handle, _ptr(hist), _ptr(out)))
+        return out
+
+    def digitplace_exclusive_scan_dev(self, in_dev: int, out_dev: int):
+        self.check(self.lib.rtr_digitplace_exclusive_scan_dev(self.handle, C.c_void_p(in_dev), C.c_void_p(out_dev)))
+
+    # ---- sort ----
+    def sort_keys_u32(self, keys) -> np.ndarray:
+        keys = np.array(keys, dtype=np.uint32)
+        self.check(self.lib.rtr_sort_keys_u32(self.handle, _ptr(keys), keys.size))
+        return keys
+
+    def sort_pairs_u32(self, keys, values):
+        keys = np.array(keys, dtype=np.uint32)
+        values = np.array(values, dtype=np.uint32)
+        if keys.size != values.size:
+            raise ValueError("keys/values length mismatch")
+        self.check(self.lib.rtr_sort_pairs_u32(self.handle, _ptr(keys), _ptr(values), keys.size))
+        return keys, values
+
+    def sort_keys_u64(self, keys) -> np.ndarray:
+        keys = np.array(keys, dtype=np.uint64)
+        self.check(self.lib.rtr_sort_keys_u64(self.handle, _ptr(keys), keys.size))
+        return keys
+
+    def sort_pairs_u64(self, keys, values):
+        keys = np.array(keys, dtype=np.uint64)
+        values = np.array(values, dtype=np.uint32)
+        if keys.size != values.size:
+            raise ValueError("keys/values length mismatch")
+        self.check(self.lib.rtr_sort_pairs_u64(self.handle, _ptr(keys), _ptr(values), keys.size))
+        return keys, values
+
+    def sort_pairs_u32_dev(self, keys_dev: int, values_dev, n: int, begin_bit: int = 0, end_bit: int = 32):
+        self.check(self.lib.rtr_sort_pairs_u32_dev(self.handle, C.c_void_p(keys_dev), _ptr(values_dev), n, begin_bit, end_bit))
+
+    def sort_pairs_u64_dev(self, keys_dev: int, values_dev, n: int, begin_bit: int = 0, end_bit: int = 64):
+        self.check(self.lib.rtr_sort_pairs_u64_dev(self.handle, C.c_void_p(keys_dev), _ptr(values_dev), n, begin_bit, end_bit))
+
+    # ---- Morton ----
+    def morton_codes(self, tris, meshes, n=None) -> np.ndarray:
+        tris, meshes = _as(tris, TRIANGLE), _as(meshes, MESH)
+        n = tris.size if n is None else n
+        out = np.zeros(n, dtype=np.uint32)
+        self.check(self.lib.rtr_morton_codes(self.handle, _ptr(tris), n, tris.size, _ptr(meshes), meshes.size, _ptr(out)))
+        return out
+
+    def morton_codes64(self, tris, meshes, n=None) -> np.ndarray:
+        tris, meshes = _as(tris, TRIANGLE), _as(meshes, MESH)
+        n = tris.size if n is None else n
+        out = np.zeros(n, dtype=np.uint64)
+        self.check(self.lib.rtr_morton_codes64(self.handle, _ptr(tris), n, tris.size, _ptr(meshes), meshes.size, _ptr(out)))
+        return out
+
+    def morton_codes_dev(self, tris_dev: int, n: int, array_len: int, meshes_dev: int, nb_meshes: int, codes_dev: int):
+        self.check(self.lib.rtr_morton_codes_dev(self.handle, C.c_void_p(tris_dev), n, array_len, C.c_void_p(meshes_dev),
+                                                 nb_meshes, C.c_void_p(codes_dev)))
+
+    def scene_bounds(self, tris, meshes) -> np.ndarray:
+        tris, meshes = _as(tris, TRIANGLE), _as(meshes, MESH)
+        out = np.zeros(12, dtype=np.float32)
+        self.check(self.lib.rtr_scene_bounds(self.handle, _ptr(tris), tris.size, _ptr(meshes), meshes.size, _ptr(out)))
+        return out
+
+    # ---- NCCL plumbing of the C ABI ----
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(NCCL_UNIQUE_ID_BYTES)
+        rc = self.lib.rtr_comm_unique_id(buf)
+        if rc != RTR_OK:
+            raise RtrError(rc, (self.lib.rtr_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(bytes(unique_id), NCCL_UNIQUE_ID_BYTES)
+        self.check(self.lib.rtr_comm_init(self.handle, buf, rank, nranks))
+
+    def comm_destroy(self):
+        self.check(self.lib.rtr_comm_destroy(self.handle))
+
+    def allgather_rows(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int):
+        self.check(self.lib.rtr_allgather_rows(self.handle, C.c_void_p(image_dev), width, height, bytes_per_pixel, rows_per_block))
+
+
+class Bvh:
+    """rtr_bvh handle.  Build with Bvh.build / Bvh.build_dev, wrap received arrays with Bvh.adopt_dev."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.handle = C.c_void_p()
+
+    # -- construction --
+    def build(self, tris, meshes, n=None, search_radius: int = 16):
+        tris, meshes = _as(tris, TRIANGLE), _as(meshes, MESH)
+        n = tris.size if n is None else n
+        self.ctx.check(self.lib.rtr_bvh_build(self.ctx.handle, _ptr(tris), n, tris.size, _ptr(meshes), meshes.size,
+                                              search_radius, C.byref(self.handle)))
+        return self
+
+    def build_dev(self, tris_dev: int, n: int, array_len: int, meshes_dev: int, nb_meshes: int, search_radius: int = 16):
+        self.ctx.check(self.lib.rtr_bvh_build_dev(self.ctx.handle, C.c_void_p(tris_dev), n, array_len,
+                                                  C.c_void_p(meshes_dev), nb_meshes, search_radius, C.byref(self.handle)))
+        return self
+
+    def adopt_dev(self, nodes_dev: int, n: int, tris_dev: int, meshes_dev: int, nb_meshes: int):
+        self.ctx.check(self.lib.rtr_bvh_adopt_dev(self.ctx.handle, C.c_void_p(nodes_dev), n, C.c_void_p(tris_dev),
+                                                  C.c_void_p(meshes_dev), nb_meshes, C.byref(self.handle)))
+        return self
+
+    def broadcast(self, root: int = 0):
+        self.ctx.check(self.lib.rtr_bvh_broadcast(self.ctx.handle, C.byref(self.handle), root))
+        return self
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value and self.ctx.handle:
+            self.lib.rtr_bvh_destroy(self.handle)
+        self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- results --
+    @property
+    def nb_triangles(self) -> int:
+        return int(self.lib.rtr_bvh_nb_triangles(self.handle))
+
+    @property
+    def nb_nodes(self) -> int:
+        return int(self.lib.rtr_bvh_nb_nodes(self.handle))
+
+    def enable_stage_timing(self, enable: bool = True):
+        self.ctx.check(self.lib.rtr_bvh_enable_stage_timing(self.handle, 1 if enable else 0))
+
+    def stage_ms(self) -> np.ndarray:
+        out = np.zeros(6, dtype=np.float32)
+        self.ctx.check(self.lib.rtr_bvh_stage_ms(self.handle, _ptr(out)))
+        return out
+
+    def iteration_trace(self):
+        cap = 1 << 16
+        active = np.zeros(cap, dtype=np.uint32)
+        merges = np.zeros(cap, dtype=np.uint32)
+        count = C.c_uint32(0)
+        self.ctx.check(self.lib.rtr_bvh_iteration_trace(self.handle, _ptr(active), _ptr(merges), cap, C.byref(count)))
+        k = min(cap, count.value)
+        return active[:k].copy(), merges[:k].copy()
+
+    def morton_codes(self) -> np.ndarray:
+        out = np.zeros(self.nb_triangles, dtype=np.uint32)
+        self.ctx.check(self.lib.rtr_bvh_morton_codes(self.handle, _ptr(out)))
+        return out
+
+    def triangle_indices(self) -> np.ndarray:
+        out = np.zeros(self.nb_triangles, dtype=np.uint32)
+        self.ctx.check(self.lib.rtr_bvh_triangle_indices(self.handle, _ptr(out)))
+        return out
+
+    def clusters(self):
+        nc = self.nb_nodes
+        clusters = np.zeros(nc, dtype=NODE)
+        parent = np.zeros(nc, dtype=np.uint32)
+        left = np.zeros(nc, dtype=np.uint32)
+        right = np.zeros(nc, dtype=np.uint32)
+        is_leaf = np.zeros(nc, dtype=np.uint8)
+        self.ctx.check(self.lib.rtr_bvh_clusters(self.handle, _ptr(clusters), _ptr(parent), _ptr(left), _ptr(right), _ptr(is_leaf)))
+        return clusters, parent, left, right, is_leaf
+
+    def flat_nodes(self) -> np.ndarray:
+        out = np.zeros(self.nb_nodes, dtype=NODE)
+        self.ctx.check(self.lib.rtr_bvh_flat_nodes(self.handle, _ptr(out)))
+        return out
+
+    @property
+    def device_nodes(self) -> int:
+        return int(self.lib.rtr_bvh_device_nodes(self.handle) or 0)
+
+    @property
+    def device_triangles(self) -> int:
+        return int(self.lib.rtr_bvh_device_triangles(self.handle) or 0)
+
+    @property
+    def device_meshes(self) -> int:
+        return int(self.lib.rtr_bvh_device_meshes(self.handle) or 0)
+
+    # -- traversal --
+    def trace_primary(self, camera, width: int, height: int, denom_w: int = 0, denom_h: int = 0, flags: int = 0) -> np.ndarray:
+        camera = _as(camera, CAMERA)
+        hits = np.zeros(width * height, dtype=HIT)
+        self.ctx.check(self.lib.rtr_trace_primary(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w,
+                                                  denom_h, flags, _ptr(hits)))
+        return hits
+
+    def trace_primary_dev(self, camera, width, height, hits_dev: int, denom_w=0, denom_h=0, row0=0, row1=0, flags=0):
+        camera = _as(camera, CAMERA)
+        self.ctx.check(self.lib.rtr_trace_primary_dev(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w,
+                                                      denom_h, row0, row1, flags, C.c_void_p(hits_dev)))
+
+    def trace_rays(self, rays, any_hit: bool = False, t_max=None, flags: int = 0) -> np.ndarray:
+        rays = _as(rays, RAY)
+        hits = np.zeros(rays.size, dtype=HIT)
+        tm = None if t_max is None else _as(t_max, np.dtype(np.float32))
+        self.ctx.check(self.lib.rtr_trace_rays(self.ctx.handle, self.handle, _ptr(rays), rays.size, 1 if any_hit else 0,
+                                               _ptr(tm), flags, _ptr(hits)))
+        return hits
+
+    def trace_rays_dev(self, rays_dev: int, n_rays: int, hits_dev: int, any_hit=False, t_max_dev=None, flags=0):
+        self.ctx.check(self.lib.rtr_trace_rays_dev(self.ctx.handle, self.handle, C.c_void_p(rays_dev), n_rays,
+                                                   1 if any_hit else 0, _ptr(t_max_dev), flags, C.c_void_p(hits_dev)))
+
+    def render(self, camera, width, height, denom_w=0, denom_h=0, row0=0, row1=0, bounces=0, shadow=False,
+               light=(0.0, 0.0, 0.0), flags=0, want_hits=True):
+        camera = _as(camera, CAMERA)
+        rows = (height if row1 == 0 else row1) - row0
+        rgba = np.zeros((rows, width, 4), dtype=np.float32)
+        hits = np.zeros(rows * width, dtype=HIT) if want_hits else None
+        nrays = np.zeros(1, dtype=np.uint64)
+        light = np.asarray(light, dtype=np.float32)
+        self.ctx.check(self.lib.rtr_render(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w, denom_h,
+                                           row0, row1, bounces, 1 if shadow else 0, _ptr(light), flags, _ptr(rgba),
+                                           _ptr(hits), _ptr(nrays)))
+        return rgba, hits, int(nrays[0])
+
+    def render_dev(self, camera, width, height, rgba_dev, hits_dev=None, rays_dev=None, denom_w=0, denom_h=0, row0=0,
+                   row1=0, bounces=0, shadow=False, light=(0.0, 0.0, 0.0), flags=0):
+        camera = _as(camera, CAMERA)
+        light = np.asarray(light, dtype=np.float32)
+        self.ctx.check(self.lib.rtr_render_dev(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w, denom_h,
+                                               row0, row1, bounces, 1 if shadow else 0, _ptr(light), flags,
+                                               _ptr(rgba_dev), _ptr(hits_dev), _ptr(rays_dev)))

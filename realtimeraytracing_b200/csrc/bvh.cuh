@@ -1,0 +1,81 @@
+// bvh.cuh -- device-side layout of a BVH under construction and of a built BVH.
+#pragma once
+#include "common.cuh"
+
+// PLOC loop state, double buffered by launch parity (see ploc.cu)
+struct PlocState {
+    uint32_t n_active;      // clusters alive at the start of the iteration
+    uint32_t total;         // clusters created so far (next new id)
+    uint32_t iter;          // iterations completed
+    uint32_t tile_counter;  // dynamic tile ids of the launch that reads this slot
+};
+
+// scene constants the traversal kernels need (device resident so an adopted BVH can carry them)
+struct TraceParams {
+    uint32_t emax2_ordered;  // max squared edge length over all triangles, ordered-uint encoded
+    uint32_t stack_overflows;
+    uint32_t pad0, pad1;
+};
+
+constexpr uint32_t kMaxPlocIterations = 1u << 16;
+
+struct rtr_bvh {
+    rtr_ctx* ctx = nullptr;
+    uint32_t n = 0;          // triangles
+    uint32_t capacity = 0;   // triangles the arrays below were sized for
+    uint32_t array_len = 0;
+    uint32_t nb_meshes = 0;
+    uint32_t radius = RTR_DEFAULT_SEARCH_RADIUS;
+    bool adopted = false;    // flat/tris/meshes are borrowed, no build arrays
+    bool built = false;
+
+    // inputs (device)
+    const rtr_triangle* tris = nullptr;
+    const rtr_mesh* meshes = nullptr;
+    rtr_triangle* tris_own = nullptr;  size_t tris_own_cap = 0;   // triangles
+    rtr_mesh* meshes_own = nullptr;    size_t meshes_own_cap = 0; // meshes
+
+    // build arrays (device), sized by capacity
+    uint32_t* codes = nullptr;     // [cap]  sorted Morton codes
+    uint32_t* tri_idx = nullptr;   // [cap]  BVH_Params::_TriangleIndices
+    float4* node_lo = nullptr;     // [2cap-1] by cluster id: min.xyz, max.x
+    float4* node_hi = nullptr;     // [2cap-1] max.y, max.z, bits(left | triangle id), bits(right | NONE)
+    uint32_t* isize = nullptr;     // [cap] nodes in the subtree of internal cluster (id - n)
+    uint32_t* ipos = nullptr;      // [cap] DFS pre-order position of internal cluster (id - n)
+    uint32_t* cin = nullptr;       // [cap] active list, ping
+    uint32_t* cout = nullptr;      // [cap] active list, pong
+    uint64_t* tile_status = nullptr;  // [ceil(cap/tile)] decoupled look-back words
+    PlocState* state = nullptr;    // [2]
+    uint32_t* trace_active = nullptr;   // [kMaxPlocIterations]
+    uint32_t* trace_merges = nullptr;   // [kMaxPlocIterations]
+    uint32_t* iter_first_id = nullptr;  // [kMaxPlocIterations + 1] first cluster id created by iteration i
+    float* bounds12 = nullptr;     // scene box + cube
+    uint32_t* ordered6 = nullptr;
+    rtr_node* flat = nullptr;      // [2cap-1] DFS pre-order, the reference's SSBO 5
+    const rtr_node* flat_view = nullptr;  // what traversal reads (== flat, flat_recv, or an adopted pointer)
+    rtr_node* flat_recv = nullptr; // receive buffer of rtr_bvh_broadcast on non-root ranks
+    size_t recv_cap = 0;           // triangles flat_recv/tris_own were sized for by a broadcast
+    TraceParams* tparams = nullptr;
+
+    // host mirrors of the last build
+    uint32_t iterations = 0;
+    std::vector<uint32_t> h_first_id;  // [iterations + 1]
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// ploc.cu
+int rtr_bvh_run_build(rtr_bvh* b);
+int rtr_bvh_export_clusters(rtr_bvh* b, rtr_node* clusters_dev, uint32_t* parent_dev, uint32_t* left_dev,
+                            uint32_t* right_dev, uint8_t* is_leaf_dev);
+int rtr_bvh_compute_trace_params(rtr_bvh* b);
+// trace.cu
+int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                             uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t flags,
+                             rtr_hit* hits_dev);
+int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays_dev, uint64_t n_rays, int any_hit,
+                          const float* t_max_dev, uint32_t flags, rtr_hit* hits_dev);
+int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                      uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
+                      const float light[3], uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev);

@@ -1,0 +1,203 @@
+// comm.cu -- multi-GPU plumbing of the C ABI: one process per GPU, the BVH is built on one rank and
+// broadcast over NVLink, image rows are dealt to ranks in blocks and all-gathered.
+//
+// The reference has no multi-GPU path at all; this is new surface.
+// PLOC iterations are globally dependent, so the build itself is NOT sharded -- only its result is
+// replicated -- while rays are independent and shard without any data-path collective.
+//
+// NCCL is resolved at run time with dlopen("libnccl.so.2"): inside a torch process that is the
+// library torch.distributed already loaded (same soname), in a plain C++ host it is the system one.
+#include <dlfcn.h>
+
+#include "bvh.cuh"
+
+namespace {
+
+typedef struct { char internal[RTR_NCCL_UNIQUE_ID_BYTES]; } NcclUniqueId;
+typedef void* NcclComm;
+constexpr int kNcclUint8 = 1;
+
+struct NcclApi {
+    int (*GetUniqueId)(NcclUniqueId*);
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int);
+    int (*CommDestroy)(NcclComm);
+    int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char* (*GetErrorString)(int);
+    void* lib;
+};
+
+NcclApi g_nccl = {};
+
+int load_nccl(rtr_ctx* ctx) {
+    if (g_nccl.lib) return RTR_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) {
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return rtr_set_error(ctx, RTR_E_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+    NcclApi api = {};
+    api.lib = lib;
+#define RTR_SYM(field, name)                                                              \
+    *reinterpret_cast<void**>(&api.field) = dlsym(lib, name);                             \
+    if (!api.field) return rtr_set_error(ctx, RTR_E_COMM, "libnccl lacks symbol %s", name)
+    RTR_SYM(GetUniqueId, "ncclGetUniqueId");
+    RTR_SYM(CommInitRank, "ncclCommInitRank");
+    RTR_SYM(CommDestroy, "ncclCommDestroy");
+    RTR_SYM(Broadcast, "ncclBroadcast");
+    RTR_SYM(GroupStart, "ncclGroupStart");
+    RTR_SYM(GroupEnd, "ncclGroupEnd");
+    RTR_SYM(GetErrorString, "ncclGetErrorString");
+#undef RTR_SYM
+    g_nccl = api;
+    return RTR_OK;
+}
+
+#define RTR_NCCL(ctx, call)                                                                          \
+    do {                                                                                             \
+        int _e = (call);                                                                             \
+        if (_e != 0)                                                                                 \
+            return rtr_set_error((ctx), RTR_E_COMM, "%s:%d %s -> %s", __FILE__, __LINE__, #call,     \
+                                 g_nccl.GetErrorString ? g_nccl.GetErrorString(_e) : "nccl error"); \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int rtr_comm_unique_id(void* id_out) {
+    if (!id_out) return RTR_E_INVALID;
+    RTR_CHECK(load_nccl(nullptr));
+    NcclUniqueId id;
+    const int e = g_nccl.GetUniqueId(&id);
+    if (e != 0) return rtr_set_error(nullptr, RTR_E_COMM, "ncclGetUniqueId -> %s", g_nccl.GetErrorString(e));
+    memcpy(id_out, &id, sizeof(id));
+    return RTR_OK;
+}
+
+int rtr_comm_init(rtr_ctx* ctx, const void* unique_id, int rank, int nranks) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!unique_id || nranks < 1 || rank < 0 || rank >= nranks)
+        return rtr_set_error(ctx, RTR_E_INVALID, "comm_init: bad rank %d / nranks %d", rank, nranks);
+    if (ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "comm_init: communicator already initialised");
+    RTR_CHECK(load_nccl(ctx));
+    RTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    NcclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    NcclComm comm = nullptr;
+    RTR_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return RTR_OK;
+}
+
+int rtr_comm_destroy(rtr_ctx* ctx) {
+    if (!ctx) return RTR_E_INVALID;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->rank = 0;
+    ctx->nranks = 1;
+    return RTR_OK;
+}
+
+int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
+    if (!ctx || !bvh) return RTR_E_INVALID;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: rtr_comm_init has not been called");
+    if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: bad root %d", root);
+    const bool is_root = ctx->rank == root;
+    if (is_root && (!*bvh || !(*bvh)->built)) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
+    NcclComm comm = ctx->nccl_comm;
+
+    // 1. header: triangle and mesh counts
+    RTR_CHECK(rtr_ws_reserve(ctx, 256));
+    uint32_t* h_hdr = static_cast<uint32_t*>(ctx->pinned) + 64;
+    uint32_t* d_hdr = static_cast<uint32_t*>(ctx->ws);
+    if (is_root) {
+        h_hdr[0] = (*bvh)->n; h_hdr[1] = (*bvh)->nb_meshes; h_hdr[2] = 0; h_hdr[3] = 0;
+        RTR_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr, 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RTR_NCCL(ctx, g_nccl.Broadcast(d_hdr, d_hdr, 16, kNcclUint8, root, comm, ctx->stream));
+    RTR_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t n = h_hdr[0], nb_meshes = h_hdr[1];
+    if (n == 0 || nb_meshes == 0) return rtr_set_error(ctx, RTR_E_COMM, "bvh_broadcast: empty header from root");
+    const size_t nc = 2 * (size_t)n - 1;
+
+    // 2. receivers own their copies
+    rtr_bvh* b = *bvh;
+    if (!is_root) {
+        if (!b) {
+            b = new (std::nothrow) rtr_bvh();
+            if (!b) return rtr_set_error(ctx, RTR_E_NOMEM, "bvh_broadcast: host allocation failed");
+            b->ctx = ctx;
+            *bvh = b;
+        }
+        b->built = false;
+        if (b->recv_cap < n) {
+            RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (b->flat_recv) cudaFree(b->flat_recv);
+            if (b->tris_own) cudaFree(b->tris_own);
+            b->flat_recv = nullptr; b->tris_own = nullptr; b->tris_own_cap = 0; b->recv_cap = 0;
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->flat_recv), nc * sizeof(rtr_node)));
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->tris_own), (size_t)n * sizeof(rtr_triangle)));
+            b->tris_own_cap = n; b->recv_cap = n;
+        }
+        if (b->meshes_own_cap < nb_meshes) {
+            RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (b->meshes_own) cudaFree(b->meshes_own);
+            b->meshes_own = nullptr; b->meshes_own_cap = 0;
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->meshes_own), (size_t)nb_meshes * sizeof(rtr_mesh)));
+            b->meshes_own_cap = nb_meshes;
+        }
+        if (!b->tparams) RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->tparams), sizeof(TraceParams)));
+    }
+    void* nodes = is_root ? const_cast<rtr_node*>(b->flat_view) : b->flat_recv;
+    void* tris = is_root ? const_cast<rtr_triangle*>(b->tris) : b->tris_own;
+    void* meshes = is_root ? const_cast<rtr_mesh*>(b->meshes) : b->meshes_own;
+
+    // 3. one grouped broadcast: flat nodes (48 B*(2n-1)) + triangles (64 B*n) + meshes + trace constants
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    RTR_NCCL(ctx, g_nccl.Broadcast(nodes, nodes, nc * sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(tris, tris, (size_t)n * sizeof(rtr_triangle), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(meshes, meshes, (size_t)nb_meshes * sizeof(rtr_mesh), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.GroupEnd());
+
+    if (!is_root) {
+        b->n = n; b->array_len = n; b->nb_meshes = nb_meshes;
+        b->tris = b->tris_own; b->meshes = b->meshes_own; b->flat_view = b->flat_recv;
+        b->adopted = true;
+        b->built = true;
+    }
+    return RTR_OK;
+}
+
+int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                       uint32_t rows_per_block) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!image_dev || width == 0 || height == 0 || bytes_per_pixel == 0 || rows_per_block == 0)
+        return rtr_set_error(ctx, RTR_E_INVALID, "allgather_rows: bad argument");
+    if (ctx->nranks == 1) return RTR_OK;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "allgather_rows: rtr_comm_init has not been called");
+    const size_t row_bytes = (size_t)width * bytes_per_pixel;
+    const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    for (uint32_t blk = 0; blk < blocks; ++blk) {
+        const uint32_t r0 = blk * rows_per_block;
+        const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
+        char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
+        RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, (int)(blk % (uint32_t)ctx->nranks),
+                                       ctx->nccl_comm, ctx->stream));
+    }
+    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    return RTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+// sort.cu -- Onesweep least-significant-digit radix sort (8-bit digits) for 32/64-bit
+// Morton keys with optional 32-bit payload, plus the two pre-pass kernels the reference's
+// tests/testsSortGPU pin.
+//
+// Replaces std::sort over pair<code,index> (bvh.cpp:223-231) -- whose result equals a stable
+// sort by code because the indices are an iota -- and the reference's unfinished GPU sort
+// (ploc/preprocessing/sort/*.glsl; chainedScanDigitBinning.glsl:31-33 is an empty main).
+//
+// Kernels
+//   radix_histogram_kernel : one read of the keys, all digit places at once (shared atomics)
+//   radix_scan_kernel      : exclusive scan of each 256-bin histogram (one warp-scan CTA)
+//   onesweep_kernel        : per pass; tile = BLOCK*IPT keys staged into shared memory by one
+//                            TMA bulk copy (cp.async.bulk + mbarrier), warp-level match ranking,
+//                            shuffle scans, decoupled look-back over per-tile digit counts,
+//                            shared-memory reorder, coalesced scatter
+// Algorithmic HBM bytes: n*(s_k + P*2*s_e)  (SURVEY.md 8d): 36 B/key u32 keys, 68 B/pair.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr uint32_t kFlagAgg = 1u << 30;   // tile aggregate available
+constexpr uint32_t kFlagIncl = 2u << 30;  // inclusive prefix available
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- TMA (bulk async copy) + mbarrier, raw PTX ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, uint32_t mask) {
+    return static_cast<uint32_t>(k >> shift) & mask;
+}
+
+// ---------------------------------------------------------------------------------------
+// up-front histogram of every digit place (one pass over the keys)
+// ---------------------------------------------------------------------------------------
+template <typename KeyT, int MAX_PASSES>
+__global__ void __launch_bounds__(512)
+radix_histogram_kernel(const KeyT* __restrict__ keys, uint32_t n, int begin_bit, int end_bit, int passes,
+                       uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t s_hist[MAX_PASSES][kRadix];
+    for (int i = threadIdx.x; i < MAX_PASSES * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    constexpr int VEC = 16 / sizeof(KeyT);
+    const uint32_t nvec = n / VEC;
+    const uint4* kv = reinterpret_cast<const uint4*>(keys);
+    const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
+    auto add_key = [&](KeyT k) {
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p) {
+            if (p < passes) {
+                const int shift = begin_bit + p * kRadixBits;
+                const int bits = min(kRadixBits, end_bit - shift);
+                atomicAdd(&s_hist[p][digit_of<KeyT>(k, shift, (1u << bits) - 1u)], 1u);
+            }
+        }
+    };
+    if (aligned) {
+        for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+            const uint4 q = __ldg(kv + v);
+            if constexpr (sizeof(KeyT) == 4) {
+                add_key(q.x); add_key(q.y); add_key(q.z); add_key(q.w);
+            } else {
+                add_key((KeyT)q.x | ((KeyT)q.y << 32));
+                add_key((KeyT)q.z | ((KeyT)q.w << 32));
+            }
+        }
+        for (uint32_t i = nvec * VEC + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            add_key(keys[i]);
+    } else {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            add_key(keys[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// exclusive scan of each pass's 256 bins: gbase[p][d] = #keys with digit < d at place p
+__global__ void __launch_bounds__(kRadix)
+radix_scan_kernel(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ gbase) {
+    __shared__ uint32_t s_warp[kRadix / 32];
+    const uint32_t p = blockIdx.x, d = threadIdx.x, l = lane_id(), w = d >> 5;
+    const uint32_t v = ghist[p * kRadix + d];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (l >= (uint32_t)o) x += y;
+    }
+    if (l == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t i = 0; i < w; ++i) base += s_warp[i];
+    gbase[p * kRadix + d] = base + x - v;
+}
+
+// ---------------------------------------------------------------------------------------
+// one Onesweep digit pass
+// ---------------------------------------------------------------------------------------
+template <typename KeyT, bool PAIRS, int BLOCK, int IPT>
+struct OnesweepSmem {
+    static constexpr int TILE = BLOCK * IPT;
+    static constexpr int WARPS = BLOCK / 32;
+    alignas(128) KeyT keys[TILE];
+    uint32_t vals[PAIRS ? TILE : 1];
+    uint32_t whist[WARPS][kRadix];  // per-warp digit counts, then warp-exclusive offsets
+    uint32_t cta_ofs[kRadix];       // first tile-local slot of each digit
+    uint32_t gofs[kRadix];          // global slot of digit's first key of this tile, minus cta_ofs
+    uint32_t scan_warp[kRadix / 32];
+    alignas(8) uint64_t mbar;
+    uint32_t tile;
+};
+
+template <typename KeyT, bool PAIRS, int BLOCK, int IPT, bool TMA>
+__global__ void __launch_bounds__(BLOCK)
+onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
+                const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                uint32_t n, uint32_t num_tiles, int shift, uint32_t mask,
+                const uint32_t* __restrict__ gbase,   // [256] for this pass
+                uint32_t* __restrict__ status,        // [num_tiles][256] zero-initialised
+                uint32_t* __restrict__ tile_counter) {
+    using Smem = OnesweepSmem<KeyT, PAIRS, BLOCK, IPT>;
+    constexpr int TILE = Smem::TILE;
+    constexpr int WARPS = Smem::WARPS;
+    static_assert(BLOCK >= kRadix, "one look-back thread per digit");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    // dynamic tile id: tiles start in issue order, so look-back never waits on an unscheduled CTA
+    if (tid == 0) {
+        s.tile = atomicAdd(tile_counter, 1u);
+        if (TMA) { mbar_init(&s.mbar, 1); mbar_fence_init(); }
+    }
+    for (uint32_t i = lane; i < kRadix; i += 32) s.whist[warp][i] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t valid = min((uint32_t)TILE, n - tile_base);
+    const bool full = (valid == (uint32_t)TILE);
+
+    // ---- load: warp-striped so that (item, lane) order == memory order (stability) ----
+    KeyT key[IPT];
+    const uint32_t warp_base = warp * 32u * IPT;
+    if (TMA && full) {
+        if (tid == 0) {
+            mbar_expect_tx(&s.mbar, TILE * sizeof(KeyT));
+            tma_bulk_g2s(s.keys, keys_in + tile_base, TILE * sizeof(KeyT), &s.mbar);
+        }
+        mbar_wait(&s.mbar, 0);
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) key[k] = s.keys[warp_base + k * 32 + lane];
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t i = warp_base + k * 32 + lane;
+            key[k] = (i < valid) ? keys_in[tile_base + i] : ~KeyT(0);  // pad sorts last, never written
+        }
+    }
+
+    // ---- rank inside the warp with match.any (ballot of equal digits) ----
+    uint32_t rank[IPT];
+    uint32_t* wh = s.whist[warp];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t leader = 31u - __clz(peers);
+        uint32_t prev = 0;
+        if (lane == leader) { prev = wh[d]; wh[d] = prev + __popc(peers); }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[k] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
+
+    // ---- per digit: exclusive offsets across warps, tile total, publish aggregate ----
+    uint32_t total = 0, incl = 0;
+    if (tid < kRadix) {
+#pragma unroll 4
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s.whist[w][tid];
+            s.whist[w][tid] = total;
+            total += c;
+        }
+        st_relaxed_u32(&status[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagIncl : kFlagAgg) | total);
+        // scan of the 256 totals -> first tile-local slot of each digit (warp level here)
+        incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        if (lane == 31) s.scan_warp[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < kRadix) {
+        uint32_t base = 0;
+        for (uint32_t i = 0; i < warp; ++i) base += s.scan_warp[i];
+        s.cta_ofs[tid] = base + incl - total;
+    }
+    __syncthreads();
+
+    // ---- reorder keys inside the tile through shared memory ----
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
+        const uint32_t pos = s.cta_ofs[d] + wh[d] + rank[k];
+        s.keys[pos] = key[k];
+        rank[k] = pos;
+    }
+    if (PAIRS) {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t i = warp_base + k * 32 + lane;
+            if (i < valid) s.vals[rank[k]] = __ldg(vals_in + tile_base + i);
+        }
+    }
+
+    // ---- decoupled look-back: one thread per digit ----
+    if (tid < kRadix) {
+        uint32_t prev = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                const uint32_t v = ld_relaxed_u32(&status[(size_t)t * kRadix + tid]);
+                const uint32_t flag = v & ~kValueMask;
+                if (flag == 0) continue;  // predecessor has not published yet
+                prev += v & kValueMask;
+                if (flag == kFlagIncl) break;
+                --t;
+            }
+            st_relaxed_u32(&status[(size_t)tile * kRadix + tid], kFlagIncl | (prev + total));
+        }
+        s.gofs[tid] = gbase[tid] + prev - s.cta_ofs[tid];
+    }
+    __syncthreads();
+
+    // ---- coalesced scatter: consecutive threads write runs of equal digits ----
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t i = k * BLOCK + tid;
+        if (i < valid) {
+            const KeyT kk = s.keys[i];
+            const uint32_t dst = s.gofs[digit_of<KeyT>(kk, shift, mask)] + i;
+            keys_out[dst] = kk;
+            if (PAIRS) vals_out[dst] = s.vals[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// testsSortGPU pre-passes
+// ---------------------------------------------------------------------------------------
+// histogramOfGlobalDigitCounts.glsl:31-59 : per-bit popcount histogram.  Lane b of every warp
+// owns bit b: 32 ballots per 32 keys, no shared atomics in the loop.
+__global__ void __launch_bounds__(256)
+bit_histogram32_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_hist[32];
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    uint32_t acc = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (n + stride - 1) / stride;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t k = (i < n) ? __ldg(keys + i) : 0u;
+#pragma unroll
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (k >> b) & 1u);
+            if (lane == b) acc += __popc(bal);
+        }
+    }
+    if (acc) atomicAdd(&s_hist[lane], acc);
+    __syncthreads();
+    if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&out[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// prefixSumOfGlobalDigitCounts.glsl:24-69 : exclusive scan inside each group of 4 bins (one warp)
+__global__ void digitplace_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+    const uint32_t l = threadIdx.x;
+    const uint32_t v = in[l];
+    uint32_t x = v;
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, 1, 4);
+    if ((l & 3u) >= 1u) x += y;
+    y = __shfl_up_sync(0xffffffffu, x, 2, 4);
+    if ((l & 3u) >= 2u) x += y;
+    out[l] = x - v;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <typename KeyT> struct SortCfg;
+template <> struct SortCfg<uint32_t> { static constexpr int BLOCK = 512, IPT = 16, MAX_PASSES = 4; };
+template <> struct SortCfg<uint64_t> { static constexpr int BLOCK = 512, IPT = 8, MAX_PASSES = 8; };
+
+struct SortWs {
+    void* keys_tmp;
+    uint32_t* vals_tmp;
+    uint32_t* ghist;     // [MAX_PASSES][256]
+    uint32_t* gbase;     // [MAX_PASSES][256]
+    uint32_t* counters;  // [MAX_PASSES]
+    uint32_t* status;    // [passes][tiles][256]
+    size_t zero_bytes;   // ghist..status are contiguous and zeroed together
+    void* zero_begin;
+};
+
+template <typename KeyT>
+size_t sort_ws_layout(void* base, uint32_t n, bool pairs, SortWs* out) {
+    using Cfg = SortCfg<KeyT>;
+    const uint32_t tile = Cfg::BLOCK * Cfg::IPT;
+    const uint32_t tiles = (n + tile - 1) / tile;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = rtr_align_up(off + bytes, 256); return o; };
+    const size_t o_keys = take((size_t)n * sizeof(KeyT));
+    const size_t o_vals = take(pairs ? (size_t)n * 4 : 0);
+    const size_t o_hist = take((size_t)Cfg::MAX_PASSES * kRadix * 4);
+    const size_t o_base = take((size_t)Cfg::MAX_PASSES * kRadix * 4);
+    const size_t o_cnt = take((size_t)Cfg::MAX_PASSES * 4);
+    const size_t o_status = take((size_t)Cfg::MAX_PASSES * tiles * kRadix * 4);
+    if (out) {
+        char* b = static_cast<char*>(base);
+        out->keys_tmp = b + o_keys;
+        out->vals_tmp = reinterpret_cast<uint32_t*>(b + o_vals);
+        out->ghist = reinterpret_cast<uint32_t*>(b + o_hist);
+        out->gbase = reinterpret_cast<uint32_t*>(b + o_base);
+        out->counters = reinterpret_cast<uint32_t*>(b + o_cnt);
+        out->status = reinterpret_cast<uint32_t*>(b + o_status);
+        out->zero_begin = b + o_hist;
+        out->zero_bytes = off - o_hist;
+    }
+    return off;
+}
+
+template <typename KeyT, bool PAIRS, bool TMA>
+int launch_pass(rtr_ctx* ctx, const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, uint32_t n,
+                uint32_t tiles, int shift, uint32_t mask, const uint32_t* gbase, uint32_t* status, uint32_t* counter) {
+    using Cfg = SortCfg<KeyT>;
+    auto kern = onesweep_kernel<KeyT, PAIRS, Cfg::BLOCK, Cfg::IPT, TMA>;
+    const size_t smem = sizeof(OnesweepSmem<KeyT, PAIRS, Cfg::BLOCK, Cfg::IPT>);
+    static bool configured = false;  // per template instantiation
+    if (!configured) {
+        RTR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<tiles, Cfg::BLOCK, smem, ctx->stream>>>(kin, kout, vin, vout, n, tiles, shift, mask, gbase, status, counter);
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}
+
+template <typename KeyT>
+int sort_impl(rtr_ctx* ctx, KeyT* keys, uint32_t* vals, uint32_t n, int begin_bit, int end_bit) {
+    using Cfg = SortCfg<KeyT>;
+    const int key_bits = (int)sizeof(KeyT) * 8;
+    if (begin_bit < 0 || end_bit > key_bits || begin_bit >= end_bit)
+        return rtr_set_error(ctx, RTR_E_INVALID, "sort: bad bit range [%d,%d)", begin_bit, end_bit);
+    if (n >= (1u << 30)) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "sort: n=%u >= 2^30", n);
+    if (n <= 1) return RTR_OK;
+    const bool pairs = vals != nullptr;
+    const int passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    const uint32_t tile = Cfg::BLOCK * Cfg::IPT;
+    const uint32_t tiles = (n + tile - 1) / tile;
+
+    const size_t need = sort_ws_layout<KeyT>(nullptr, n, pairs, nullptr);
+    RTR_CHECK(rtr_ws_reserve(ctx, need));
+    SortWs ws;
+    sort_ws_layout<KeyT>(ctx->ws, n, pairs, &ws);
+
+    RTR_CUDA(ctx, cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, ctx->stream));
+    {
+        uint32_t blocks = (n / 4 + 511) / 512;
+        const uint32_t cap = (uint32_t)ctx->sm_count * 4;
+        blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+        radix_histogram_kernel<KeyT, Cfg::MAX_PASSES><<<blocks, 512, 0, ctx->stream>>>(keys, n, begin_bit, end_bit, passes, ws.ghist);
+        RTR_LAUNCH_CHECK(ctx);
+        radix_scan_kernel<<<passes, kRadix, 0, ctx->stream>>>(ws.ghist, ws.gbase);
+        RTR_LAUNCH_CHECK(ctx);
+    }
+    KeyT* kin = keys;
+    KeyT* kout = static_cast<KeyT*>(ws.keys_tmp);
+    uint32_t* vin = vals;
+    uint32_t* vout = pairs ? ws.vals_tmp : nullptr;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = begin_bit + p * kRadixBits;
+        const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
+        const uint32_t mask = (1u << bits) - 1u;
+        const bool tma = (reinterpret_cast<uintptr_t>(kin) & 15u) == 0;
+        uint32_t* status = ws.status + (size_t)p * tiles * kRadix;
+        int r;
+        if (pairs) r = tma ? launch_pass<KeyT, true, true>(ctx, kin, kout, vin, vout, n, tiles, shift, mask, ws.gbase + p * kRadix, status, ws.counters + p)
+                           : launch_pass<KeyT, true, false>(ctx, kin, kout, vin, vout, n, tiles, shift, mask, ws.gbase + p * kRadix, status, ws.counters + p);
+        else r = tma ? launch_pass<KeyT, false, true>(ctx, kin, kout, vin, vout, n, tiles, shift, mask, ws.gbase + p * kRadix, status, ws.counters + p)
+                     : launch_pass<KeyT, false, false>(ctx, kin, kout, vin, vout, n, tiles, shift, mask, ws.gbase + p * kRadix, status, ws.counters + p);
+        RTR_CHECK(r);
+        KeyT* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    if (kin != keys) {  // odd number of passes: result sits in the workspace
+        RTR_CUDA(ctx, cudaMemcpyAsync(keys, kin, (size_t)n * sizeof(KeyT), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (pairs) RTR_CUDA(ctx, cudaMemcpyAsync(vals, vin, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return RTR_OK;
+}
+
+}  // namespace
+
+size_t rtr_sort_ws_bytes(uint32_t n, int key_bytes, bool pairs) {
+    return key_bytes == 8 ? sort_ws_layout<uint64_t>(nullptr, n, pairs, nullptr)
+                          : sort_ws_layout<uint32_t>(nullptr, n, pairs, nullptr);
+}
+
+int rtr_sort_impl_u32(rtr_ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, int begin_bit, int end_bit) {
+    return sort_impl<uint32_t>(ctx, keys, vals, n, begin_bit, end_bit);
+}
+int rtr_sort_impl_u64(rtr_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n, int begin_bit, int end_bit) {
+    return sort_impl<uint64_t>(ctx, keys, vals, n, begin_bit, end_bit);
+}
+
+int rtr_bit_histogram32_launch(rtr_ctx* ctx, const uint32_t* keys, uint32_t n, uint32_t* out) {
+    uint32_t blocks = (n + 2047) / 2048;  // the reference dispatches n/2048 work-groups of 2048 keys
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+    blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+    bit_histogram32_kernel<<<blocks, 256, 0, ctx->stream>>>(keys, n, out);
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}
+
+int rtr_digitplace_scan_launch(rtr_ctx* ctx, const uint32_t* in, uint32_t* out) {
+    digitplace_scan_kernel<<<1, 32, 0, ctx->stream>>>(in, out);
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}

@@ -1,0 +1,447 @@
+// trace.cu -- stack-based BVH traversal + ray/triangle intersection over the reference's
+// 48-byte DFS pre-order node array.
+//
+// Replaces the compute shader srcCommon/shaders/raytracer.glsl: getRay (:92-100), pixel mapping
+// (:303-305), intersectBVH (:182-237), isLeafBVH (:239-244), rayTriangleIntersection (:102-147),
+// getClosestHitBVH (:246-295) with the guarded-miss semantics of getAllHits (:149-157) (Q6).
+// Every fp32 expression is evaluated in the order of oracle/rtr_oracle.c (library built with
+// -fmad=false), so hit records are bit-identical to the CPU restatement.
+//
+// Two visiting orders produce the same records:
+//   RTR_TRACE_REFERENCE_ORDER  exactly the shader's loop: pop, box test, leaf -> triangle test,
+//                              else push Left then Right; no pruning.
+//   default                    same loop, but a node is skipped when its slab entry distance is
+//                              beyond the closest hit so far by more than a conservative margin
+//                              derived from the shader's own |a| >= 1e-4 acceptance test
+//                              (DESIGN.md "pruning bound"); skipped subtrees cannot contain a hit
+//                              the shader would have preferred.
+#include "bvh.cuh"
+
+namespace {
+
+constexpr int kStack = 128;  // the shader's private stack is 1024 deep (raytracer.glsl:251)
+constexpr int kTraceBlock = 128;
+
+struct Ray {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float ix, iy, iz;  // 1/d, the shader recomputes these per node (:187,:200,:213): same value
+};
+
+struct Hit {
+    float b0, b1, b2, t;
+    uint32_t did_hit, tri;
+};
+
+__device__ __forceinline__ Ray make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+    r.ix = __fdiv_rn(1.0f, dx); r.iy = __fdiv_rn(1.0f, dy); r.iz = __fdiv_rn(1.0f, dz);
+    return r;
+}
+
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+// GLSL cross(x, y) = (x.y*y.z - y.y*x.z, x.z*y.x - y.z*x.x, x.x*y.y - y.x*x.y)
+__device__ __forceinline__ void cross3(float xx, float xy, float xz, float yx, float yy, float yz,
+                                       float& ox, float& oy, float& oz) {
+    ox = __fsub_rn(__fmul_rn(xy, yz), __fmul_rn(yy, xz));
+    oy = __fsub_rn(__fmul_rn(xz, yx), __fmul_rn(yz, xx));
+    oz = __fsub_rn(__fmul_rn(xx, yy), __fmul_rn(yx, xy));
+}
+// normalize(v) := v / sqrt(dot(v, v)) (pinned definition, see oracle/rtr_oracle.c normalize3)
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z) {
+    const float len = __fsqrt_rn(dot3(x, y, z, x, y, z));
+    x = __fdiv_rn(x, len); y = __fdiv_rn(y, len); z = __fdiv_rn(z, len);
+}
+
+// raytracer.glsl:92-100 + :303-305
+__device__ __forceinline__ Ray camera_ray(const rtr_camera& cam, uint32_t x, uint32_t y, uint32_t denom_w,
+                                          uint32_t denom_h) {
+    const float px = __fdiv_rn((float)x, (float)denom_w);
+    const float py = __fdiv_rn((float)y, (float)denom_h);
+    const float v0 = __fmul_rn(__fsub_rn(px, 0.5f), cam.plane_width);
+    const float v1 = __fmul_rn(__fsub_rn(py, 0.5f), cam.plane_height);
+    const float v2 = __fmul_rn(1.f, cam.plane_near);
+    const float v3 = 1.f;
+    const float* m = cam.inv_view;
+    float pw[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        pw[r] = __fadd_rn(__fadd_rn(__fmul_rn(m[0 + r], v0), __fmul_rn(m[4 + r], v1)),
+                          __fadd_rn(__fmul_rn(m[8 + r], v2), __fmul_rn(m[12 + r], v3)));
+    const float d0 = __fsub_rn(pw[0], cam.eye[0]), d1 = __fsub_rn(pw[1], cam.eye[1]);
+    const float d2 = __fsub_rn(pw[2], cam.eye[2]), d3 = __fsub_rn(pw[3], cam.eye[3]);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
+                                           __fmul_rn(d3, d3)));
+    return make_ray(cam.eye[0], cam.eye[1], cam.eye[2], __fdiv_rn(d0, len), __fdiv_rn(d1, len), __fdiv_rn(d2, len));
+}
+
+// world-space vertices in SHADER naming (Q8): shader _P1 = host _P2, shader _P2 = host _P1
+struct TriWorld { float3 p0, p1, p2; };
+__device__ __forceinline__ TriWorld shader_vertices(const rtr_triangle* __restrict__ tris,
+                                                    const rtr_mesh* __restrict__ meshes, uint32_t tri) {
+    const TriRec t = load_tri(tris, tri);
+    const Mat3x4 M = load_model(meshes, t.model_id);
+    TriWorld w;
+    w.p0 = mat_mul_point(M, t.p0);
+    w.p1 = mat_mul_point(M, t.p2);
+    w.p2 = mat_mul_point(M, t.p1);
+    return w;
+}
+
+// raytracer.glsl:102-147
+__device__ __forceinline__ bool ray_triangle(const Ray& r, const rtr_triangle* __restrict__ tris,
+                                             const rtr_mesh* __restrict__ meshes, uint32_t tri, Hit& hit) {
+    const TriWorld w = shader_vertices(tris, meshes, tri);
+    const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
+    const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
+    float nx, ny, nz;
+    cross3(e1x, e1y, e1z, e0x, e0y, e0z, nx, ny, nz);
+    normalize3(nx, ny, nz);
+    float qx, qy, qz;
+    cross3(r.dx, r.dy, r.dz, e1x, e1y, e1z, qx, qy, qz);
+    const float a = dot3(e0x, e0y, e0z, qx, qy, qz);
+    if (dot3(nx, ny, nz, r.dx, r.dy, r.dz) >= 0.f || fabsf(a) < 1e-4f) return false;
+    const float sx = __fdiv_rn(__fsub_rn(r.ox, w.p0.x), a);
+    const float sy = __fdiv_rn(__fsub_rn(r.oy, w.p0.y), a);
+    const float sz = __fdiv_rn(__fsub_rn(r.oz, w.p0.z), a);
+    float rx, ry, rz;
+    cross3(sx, sy, sz, e0x, e0y, e0z, rx, ry, rz);
+    const float bx = dot3(sx, sy, sz, qx, qy, qz);
+    const float by = dot3(rx, ry, rz, r.dx, r.dy, r.dz);
+    const float bz = __fsub_rn(__fsub_rn(1.f, bx), by);
+    if (bx < 0.f || by < 0.f || bz < 0.f) return false;
+    const float t = dot3(e1x, e1y, e1z, rx, ry, rz);
+    if (t < 0.f) return false;
+    hit.b0 = bx; hit.b1 = by; hit.b2 = bz; hit.t = t; hit.did_hit = 1u; hit.tri = tri;
+    return true;
+}
+
+// raytracer.glsl:182-237 (edge code 2 folded into "hit"); IEEE fminf/fmaxf (Q11)
+__device__ __forceinline__ bool intersect_box(const Ray& r, const float4 lo, const float4 hi, float& t_entry) {
+    const float tx1 = __fmul_rn(__fsub_rn(lo.x, r.ox), r.ix), tx2 = __fmul_rn(__fsub_rn(hi.x, r.ox), r.ix);
+    float tMin = fminf(tx1, tx2), tMax = fmaxf(tx1, tx2);
+    if (tMax < 0.f || tMin > tMax) return false;
+    const float ty1 = __fmul_rn(__fsub_rn(lo.y, r.oy), r.iy), ty2 = __fmul_rn(__fsub_rn(hi.y, r.oy), r.iy);
+    tMin = fmaxf(tMin, fminf(ty1, ty2));
+    tMax = fminf(tMax, fmaxf(ty1, ty2));
+    if (tMax < 0.f || tMin > tMax) return false;
+    const float tz1 = __fmul_rn(__fsub_rn(lo.z, r.oz), r.iz), tz2 = __fmul_rn(__fsub_rn(hi.z, r.oz), r.iz);
+    tMin = fmaxf(tMin, fminf(tz1, tz2));
+    tMax = fminf(tMax, fmaxf(tz1, tz2));
+    t_entry = tMin;
+    return tMax >= 0.f && tMin <= tMax;
+}
+
+struct NodeRec {
+    float4 lo;  // min.xyz, pad
+    float4 hi;  // max.xyz, pad
+    uint32_t tri, left, right;
+};
+__device__ __forceinline__ NodeRec load_node(const rtr_node* __restrict__ nodes, uint32_t idx) {
+    const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    NodeRec n;
+    n.lo = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), 0.f);
+    n.hi = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), 0.f);
+    n.tri = c.x; n.left = c.y; n.right = c.z;
+    return n;
+}
+
+// Conservative pruning bound.  A triangle accepted by ray_triangle has |a| >= 1e-4, which bounds the
+// rounding error of its computed t by 40*u*(|e0||e1|/1e-4)*(t_true + Emax); with
+// K = 64*u*Emax^2/1e-4 no triangle inside a box whose computed entry distance exceeds
+// (t_best + K*Emax)*(1 + 2K) can produce a computed t below t_best.  K >= 0.25 disables pruning.
+struct PruneBound {
+    float k, kemax;
+    bool enabled;
+};
+__device__ __forceinline__ PruneBound make_prune_bound(const TraceParams* tp, bool want) {
+    PruneBound pb;
+    pb.enabled = false; pb.k = 0.f; pb.kemax = 0.f;
+    if (!want) return pb;
+    const float emax2 = ordered_to_float(tp->emax2_ordered);
+    if (!(emax2 >= 0.f) || tp->emax2_ordered == 0u) { pb.enabled = true; return pb; }  // no triangles with extent
+    const float k = 64.f * 5.9604645e-8f * emax2 * 1.0e4f * 1.01f;
+    if (k < 0.25f) { pb.enabled = true; pb.k = k; pb.kemax = k * sqrtf(emax2) * 1.01f; }
+    return pb;
+}
+__device__ __forceinline__ float prune_limit(const PruneBound& pb, float t_best) {
+    return (t_best + pb.kemax) * (1.f + 2.f * pb.k);
+}
+
+template <bool PRUNE>
+__device__ __forceinline__ Hit closest_hit(const Ray& r, const rtr_node* __restrict__ nodes,
+                                           const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
+                                           const PruneBound& pb, uint32_t* overflow) {
+    Hit best;
+    best.b0 = best.b1 = best.b2 = best.t = 0.f; best.did_hit = 0u; best.tri = 0u;
+    float limit = INFINITY;
+    uint32_t stack[kStack];
+    int sp = 0;
+    stack[sp++] = 0u;
+    while (sp > 0) {
+        const uint32_t idx = stack[--sp];
+        const NodeRec n = load_node(nodes, idx);
+        float t_entry;
+        if (!intersect_box(r, n.lo, n.hi, t_entry)) continue;
+        if (PRUNE && t_entry > limit) continue;
+        if (n.left == 0u && n.right == 0u) {
+            Hit h;
+            if (ray_triangle(r, tris, meshes, n.tri, h)) {
+                if (best.did_hit == 0u || h.t < best.t) {
+                    best = h;
+                    if (PRUNE && pb.enabled) limit = prune_limit(pb, h.t);
+                }
+            }
+        } else if (sp + 2 <= kStack) {
+            stack[sp++] = n.left;
+            stack[sp++] = n.right;
+        } else if (overflow) {
+            *overflow = 1u;
+        }
+    }
+    return best;
+}
+
+// any-hit: 1 iff some reachable triangle passes ray_triangle with t < t_max (order independent)
+template <bool PRUNE>
+__device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const rtr_node* __restrict__ nodes,
+                                        const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
+                                        const PruneBound& pb) {
+    const float limit = (PRUNE && pb.enabled) ? prune_limit(pb, t_max) : INFINITY;
+    uint32_t stack[kStack];
+    int sp = 0;
+    stack[sp++] = 0u;
+    while (sp > 0) {
+        const uint32_t idx = stack[--sp];
+        const NodeRec n = load_node(nodes, idx);
+        float t_entry;
+        if (!intersect_box(r, n.lo, n.hi, t_entry)) continue;
+        if (PRUNE && t_entry > limit) continue;
+        if (n.left == 0u && n.right == 0u) {
+            Hit h;
+            if (ray_triangle(r, tris, meshes, n.tri, h) && h.t < t_max) return true;
+        } else if (sp + 2 <= kStack) {
+            stack[sp++] = n.left;
+            stack[sp++] = n.right;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, const Hit& h) {
+    // 24-byte records: three 8-byte stores
+    uint2* p = reinterpret_cast<uint2*>(out + i);
+    p[0] = make_uint2(__float_as_uint(h.b0), __float_as_uint(h.b1));
+    p[1] = make_uint2(__float_as_uint(h.b2), __float_as_uint(h.t));
+    p[2] = make_uint2(h.did_hit, h.tri);
+}
+
+// hit frame shared by both secondary rays: unit front normal and offset origin h + n*1e-3
+__device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const rtr_triangle* __restrict__ tris,
+                                          const rtr_mesh* __restrict__ meshes, float& nx, float& ny, float& nz,
+                                          float& ox, float& oy, float& oz) {
+    const TriWorld w = shader_vertices(tris, meshes, h.tri);
+    const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
+    const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
+    cross3(e1x, e1y, e1z, e0x, e0y, e0z, nx, ny, nz);
+    normalize3(nx, ny, nz);
+    ox = __fadd_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, h.t)), __fmul_rn(nx, 1e-3f));
+    oy = __fadd_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, h.t)), __fmul_rn(ny, 1e-3f));
+    oz = __fadd_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, h.t)), __fmul_rn(nz, 1e-3f));
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+// Pixels are mapped to threads in 8x4 blocks per warp (2-D locality => coherent node fetches).
+__device__ __forceinline__ bool pixel_of_thread(uint32_t width, uint32_t rows, uint32_t& x, uint32_t& y_local) {
+    const uint32_t tiles_x = (width + 7) / 8;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tx = warp_global % tiles_x, ty = warp_global / tiles_x;
+    x = tx * 8 + (lane & 7u);
+    y_local = ty * 4 + (lane >> 3);
+    return x < width && y_local < rows;
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(kTraceBlock)
+trace_primary_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
+                     const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp, const rtr_camera cam,
+                     uint32_t width, uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t rows,
+                     rtr_hit* __restrict__ hits) {
+    uint32_t x, yl;
+    if (!pixel_of_thread(width, rows, x, yl)) return;
+    const uint32_t y = row0 + yl;
+    Hit h;
+    h.b0 = h.b1 = h.b2 = h.t = 0.f; h.did_hit = 0u; h.tri = 0u;
+    if (x < denom_w && y < denom_h) {
+        const PruneBound pb = make_prune_bound(tp, PRUNE);
+        const Ray r = camera_ray(cam, x, y, denom_w, denom_h);
+        uint32_t ovf = 0;
+        h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+        if (ovf) atomicAdd(&tp->stack_overflows, 1u);
+    }
+    store_hit(hits, (size_t)yl * width + x, h);
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(kTraceBlock)
+trace_rays_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
+                  const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp,
+                  const rtr_ray* __restrict__ rays, uint64_t n_rays, int want_any, const float* __restrict__ t_max,
+                  rtr_hit* __restrict__ hits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const float4 o = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
+    const Ray r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
+    const PruneBound pb = make_prune_bound(tp, PRUNE);
+    Hit h;
+    h.b0 = h.b1 = h.b2 = h.t = 0.f; h.did_hit = 0u; h.tri = 0u;
+    if (want_any) {
+        const float tm = t_max ? t_max[i] : INFINITY;
+        h.did_hit = any_hit<PRUNE>(r, tm, nodes, tris, meshes, pb) ? 1u : 0u;
+    } else {
+        uint32_t ovf = 0;
+        h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+        if (ovf) atomicAdd(&tp->stack_overflows, 1u);
+    }
+    store_hit(hits, i, h);
+}
+
+// Multi-bounce frame, one thread per pixel (definition: oracle/rtr_oracle.c orc_render).
+template <bool PRUNE>
+__global__ void __launch_bounds__(kTraceBlock)
+render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
+              const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp, const rtr_camera cam,
+              uint32_t width, uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t rows,
+              uint32_t bounces, int shadow, float lx, float ly, float lz,
+              float4* __restrict__ rgba, rtr_hit* __restrict__ hits, unsigned long long* __restrict__ rays_traced) {
+    uint32_t x, yl;
+    const bool live = pixel_of_thread(width, rows, x, yl);
+    uint32_t traced = 0;
+    if (live) {
+        const uint32_t y = row0 + yl;
+        float L = 0.f, wgt = 1.f;
+        Hit first;
+        first.b0 = first.b1 = first.b2 = first.t = 0.f; first.did_hit = 0u; first.tri = 0u;
+        if (x < denom_w && y < denom_h) {
+            const PruneBound pb = make_prune_bound(tp, PRUNE);
+            Ray r = camera_ray(cam, x, y, denom_w, denom_h);
+            for (uint32_t k = 0; k <= bounces; ++k) {
+                uint32_t ovf = 0;
+                const Hit h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+                ++traced;
+                if (k == 0) first = h;
+                if (!h.did_hit) break;
+                float nx, ny, nz, ox, oy, oz, c;
+                hit_frame(r, h, tris, meshes, nx, ny, nz, ox, oy, oz);
+                if (shadow) {
+                    const float sx = __fsub_rn(lx, ox), sy = __fsub_rn(ly, oy), sz = __fsub_rn(lz, oz);
+                    const float len = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
+                    const Ray sr = make_ray(ox, oy, oz, __fdiv_rn(sx, len), __fdiv_rn(sy, len), __fdiv_rn(sz, len));
+                    const bool occ = any_hit<PRUNE>(sr, len, nodes, tris, meshes, pb);
+                    ++traced;
+                    const float ndl = dot3(nx, ny, nz, sr.dx, sr.dy, sr.dz);
+                    c = occ ? 0.f : fmaxf(0.f, ndl);
+                } else {
+                    c = -dot3(nx, ny, nz, r.dx, r.dy, r.dz);
+                }
+                L = __fadd_rn(L, __fmul_rn(wgt, c));
+                wgt = __fmul_rn(wgt, 0.5f);
+                if (k < bounces) {
+                    const float kk = __fmul_rn(2.f, dot3(r.dx, r.dy, r.dz, nx, ny, nz));
+                    float rx = __fsub_rn(r.dx, __fmul_rn(nx, kk));
+                    float ry = __fsub_rn(r.dy, __fmul_rn(ny, kk));
+                    float rz = __fsub_rn(r.dz, __fmul_rn(nz, kk));
+                    normalize3(rx, ry, rz);
+                    r = make_ray(ox, oy, oz, rx, ry, rz);
+                }
+            }
+        }
+        const size_t o = (size_t)yl * width + x;
+        if (rgba) rgba[o] = make_float4(L, L, L, 1.f);
+        if (hits) store_hit(hits, o, first);
+    }
+    if (rays_traced) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) traced += __shfl_xor_sync(0xffffffffu, traced, o);
+        if ((threadIdx.x & 31u) == 0 && traced) atomicAdd(rays_traced, (unsigned long long)traced);
+    }
+}
+
+inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
+    const uint64_t warps = (uint64_t)((width + 7) / 8) * ((rows + 3) / 4);
+    return (uint32_t)((warps * 32 + kTraceBlock - 1) / kTraceBlock);
+}
+
+}  // namespace
+
+static void resolve_denoms(uint32_t width, uint32_t height, uint32_t& dw, uint32_t& dh) {
+    if (dw == 0) dw = (width / 16) * 16;   // application.cpp:225-226 + raytracer.glsl:304-305 (Q5)
+    if (dh == 0) dh = (height / 16) * 16;
+}
+
+int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                             uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t flags,
+                             rtr_hit* hits) {
+    resolve_denoms(width, height, denom_w, denom_h);
+    if (row1 == 0) row1 = height;
+    if (width == 0 || row0 >= row1 || row1 > height || denom_w == 0 || denom_h == 0)
+        return rtr_set_error(ctx, RTR_E_INVALID, "trace_primary: bad image geometry %ux%u rows [%u,%u) denom %ux%u",
+                             width, height, row0, row1, denom_w, denom_h);
+    const uint32_t rows = row1 - row0;
+    const uint32_t grid = pixel_grid(width, rows);
+    if (flags & RTR_TRACE_REFERENCE_ORDER)
+        trace_primary_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, cam,
+                                                                           width, denom_w, denom_h, row0, rows, hits);
+    else
+        trace_primary_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, cam,
+                                                                          width, denom_w, denom_h, row0, rows, hits);
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}
+
+int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t n_rays, int any, const float* t_max,
+                          uint32_t flags, rtr_hit* hits) {
+    if (n_rays == 0) return RTR_OK;
+    const uint64_t grid64 = (n_rays + kTraceBlock - 1) / kTraceBlock;
+    if (grid64 > 0x7FFFFFFFull) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_rays: too many rays");
+    const uint32_t grid = (uint32_t)grid64;
+    if (flags & RTR_TRACE_REFERENCE_ORDER)
+        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, rays,
+                                                                        n_rays, any, t_max, hits);
+    else
+        trace_rays_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, rays,
+                                                                       n_rays, any, t_max, hits);
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}
+
+int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                      uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
+                      const float light[3], uint32_t flags, float* rgba, rtr_hit* hits, uint64_t* rays) {
+    resolve_denoms(width, height, denom_w, denom_h);
+    if (row1 == 0) row1 = height;
+    if (width == 0 || row0 >= row1 || row1 > height || denom_w == 0 || denom_h == 0)
+        return rtr_set_error(ctx, RTR_E_INVALID, "render: bad image geometry %ux%u rows [%u,%u) denom %ux%u", width,
+                             height, row0, row1, denom_w, denom_h);
+    const uint32_t rows = row1 - row0;
+    const uint32_t grid = pixel_grid(width, rows);
+    const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
+    if (flags & RTR_TRACE_REFERENCE_ORDER)
+        render_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(
+            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, row0, rows, bounces, shadow, lx, ly,
+            lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+    else
+        render_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(
+            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, row0, rows, bounces, shadow, lx, ly,
+            lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}

@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference's srcCommon scene/BVH interface for the accelerated path.
+
+Same names and argument meaning as the reference so parity tests read like its own code:
+
+* ``BVH(nbTriangles, unsortedTriangles, meshesInTheScene)``  <- cr::BVH::BVH, bvh.hpp:89-91.
+  The constructor runs the whole build synchronously (bvh.cpp:11-24) -- on the GPU, through
+  rtr_bvh_build -- and the result is read from the public ``_InternalStruct`` (bvh.hpp:86)
+  whose members carry the reference's names (BVH_Params, bvh.hpp:44-63).
+* ``Scene`` with ``addMesh`` / ``getBVH_NodesToGPUData`` / ``sendDataToGpu``  <- glr::Scene,
+  srcOpenGL/scene/scene.hpp:50-54, scene.cpp:110-220: pads nothing (no MAX_NB_TRIANGLES cap)
+  unless ``reference_padding=True`` reproduces the 65 536 / 64 entry vectors of scene.cpp:18,27 (Q2).
+
+Error behaviour: the reference prints and exit()s on fatal errors (errorHandler.cpp:13-29);
+here every failure raises ``RtrError`` carrying the C ABI's code and message.
+"""
+import numpy as np
+
+from . import capi
+from .layouts import MESH, NONE, TRIANGLE
+
+MAX_NB_TRIANGLES = 2 << 15  # triangle.hpp:21
+MAX_NB_MESHES = 2 << 5      # mesh.hpp:26
+
+
+class BVH_Params:
+    """BVH_Params (bvh.hpp:44-63).  Optionals become arrays with RTR_NONE (0xFFFFFFFF) for nullopt."""
+
+    def __init__(self):
+        self._NbTriangles = 0
+        self._Clusters = None         # NODE[2n-1] by cluster id (internal links are 0, Q10)
+        self._IsLeaf = None           # uint8[2n-1]; 1 <=> has_value() in the reference (Q9)
+        self._Parent = None           # uint32[2n-1]
+        self._LeftChild = None        # uint32[2n-1]
+        self._RightChild = None       # uint32[2n-1]
+        self._TriangleIndices = None  # uint32[n]
+        self._MortonCodes = None      # uint32[n] sorted (PlocParams::_MortonCodes)
+
+
+class BVH:
+    def __init__(self, nbTriangles, unsortedTriangles, meshesInTheScene, ctx: capi.Context = None,
+                 search_radius: int = 16):
+        self._ctx = ctx if ctx is not None else capi.Context(0)
+        tris = np.ascontiguousarray(unsortedTriangles, dtype=TRIANGLE)
+        meshes = np.ascontiguousarray(meshesInTheScene, dtype=MESH)
+        self._handle = capi.Bvh(self._ctx).build(tris, meshes, n=int(nbTriangles), search_radius=search_radius)
+        p = BVH_Params()
+        p._NbTriangles = int(nbTriangles)
+        p._Clusters, p._Parent, p._LeftChild, p._RightChild, p._IsLeaf = self._handle.clusters()
+        p._TriangleIndices = self._handle.triangle_indices()
+        p._MortonCodes = self._handle.morton_codes()
+        self._InternalStruct = p
+
+    @property
+    def handle(self) -> capi.Bvh:
+        return self._handle
+
+
+def getBVH_NodesToGPUData(bvh: BVH) -> np.ndarray:
+    """glr::Scene::getBVH_NodesToGPUData (scene.cpp:203-208): DFS pre-order BVH_NodeGPU array."""
+    return bvh.handle.flat_nodes()
+
+
+class Scene:
+    """The slice of glr::Scene that feeds the accelerated path."""
+
+    def __init__(self, ctx: capi.Context = None, reference_padding: bool = False):
+        self._ctx = ctx
+        self._Meshes = []  # list of (triangles TRIANGLE[], mesh MESH[1])
+        self._NbTriangles = 0
+        self._NbMeshes = 0
+        self._BVH = None
+        self._reference_padding = reference_padding
+
+    def addMesh(self, triangles: np.ndarray, model=None, material_id: int = 0):
+        """scene.cpp:42-47; triangles' _ModelId is set to the mesh slot like Mesh::_Id."""
+        if self._reference_padding and len(self._Meshes) == MAX_NB_MESHES:
+            return
+        mesh = np.zeros(1, dtype=MESH)
+        mesh["m"][0] = (np.eye(4, dtype=np.float32) if model is None else np.asarray(model, dtype=np.float32)).T.reshape(16)
+        mesh["material_id"][0] = material_id
+        tris = np.array(triangles, dtype=TRIANGLE)
+        tris["model_id"] = len(self._Meshes)
+        self._Meshes.append((tris, mesh))
+        self._NbMeshes += 1
+        self._NbTriangles += tris.size if not self._reference_padding else min(tris.size, MAX_NB_TRIANGLES)
+
+    def getTriangleToGPUData(self) -> np.ndarray:
+        """scene.cpp:26-40 (zero padded to MAX_NB_TRIANGLES only with reference_padding)."""
+        allt = np.concatenate([t for t, _ in self._Meshes]) if self._Meshes else np.zeros(0, dtype=TRIANGLE)
+        if not self._reference_padding:
+            return allt
+        out = np.zeros(MAX_NB_TRIANGLES, dtype=TRIANGLE)
+        k = min(allt.size, MAX_NB_TRIANGLES)
+        out[:k] = allt[:k]
+        return out
+
+    def getMeshModelToGPUData(self) -> np.ndarray:
+        """scene.cpp:17-23"""
+        allm = np.concatenate([m for _, m in self._Meshes]) if self._Meshes else np.zeros(0, dtype=MESH)
+        if not self._reference_padding:
+            return allm
+        out = np.zeros(MAX_NB_MESHES, dtype=MESH)
+        out["m"][:] = np.eye(4, dtype=np.float32).reshape(16)  # MeshModelGPU default, mesh.hpp:13
+        out[:allm.size] = allm
+        return out
+
+    def sendDataToGpu(self):
+        """scene.cpp:210-220 -> bindSSBO :110-187: build the BVH (scene.cpp:148) and return the flat
+        node array that the reference uploads to SSBO binding 5."""
+        nb = min(self._NbTriangles, MAX_NB_TRIANGLES) if self._reference_padding else self._NbTriangles
+        self._BVH = BVH(nb, self.getTriangleToGPUData(), self.getMeshModelToGPUData(), ctx=self._ctx)
+        return getBVH_NodesToGPUData(self._BVH)
+
+
+__all__ = ["BVH", "BVH_Params", "Scene", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]

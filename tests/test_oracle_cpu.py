@@ -1,0 +1,156 @@
+"""CPU tests of the oracle itself: the reference's own known-answer vectors (tests/testsSortGPU),
+the survey's known-answer hashes of the reference build, internal consistency."""
+import numpy as np
+import pytest
+
+from realtimeraytracing_b200 import synth
+from realtimeraytracing_b200.layouts import hash_words, node_words
+
+import scenes
+
+
+# ---- tests/testsSortGPU/testHistogramCreation.cpp ----
+def test_hist_powers_of_two(oracle):  # :43-53, :145-153
+    keys = np.array([1 << (i % 32) for i in range(130)], dtype=np.uint32)
+    expected = np.zeros(32, dtype=np.uint32)
+    for i in range(130):
+        expected[i % 32] += 1
+    assert expected[0] == 5 and expected[1] == 5 and expected[2] == 4
+    assert np.array_equal(oracle.bit_histogram32(keys), expected)
+
+
+def test_hist_zeros_ones_twos(oracle):  # :55-73, :155-181
+    assert np.array_equal(oracle.bit_histogram32(np.zeros(130, np.uint32)), np.zeros(32, np.uint32))
+    e = np.zeros(32, np.uint32); e[0] = 130
+    assert np.array_equal(oracle.bit_histogram32(np.full(130, 1, np.uint32)), e)
+    e = np.zeros(32, np.uint32); e[1] = 130
+    assert np.array_equal(oracle.bit_histogram32(np.full(130, 2, np.uint32)), e)
+
+
+def test_hist_random_matches_numpy(oracle):  # :17-41 host recurrence, also the Hard variant's size
+    for n in (130, 65536):
+        keys = synth.random_keys_u32(n, seed=n, lo=0, hi=8192)
+        expected = np.array([(keys >> b & 1).sum() for b in range(32)], dtype=np.uint32)
+        assert np.array_equal(oracle.bit_histogram32(keys), expected)
+
+
+# ---- tests/testsSortGPU/testHistogramPrefixSum.cpp ----
+KNOWN_IN = [37, 41, 49, 53, 37, 48, 44, 51, 35, 51, 53, 41] + [0] * 20   # :53-68
+KNOWN_OUT = [0, 37, 78, 127, 0, 37, 85, 129, 0, 35, 86, 139] + [0] * 20  # :70-86
+
+
+def test_prefix_known_values(oracle):
+    assert np.array_equal(oracle.digitplace_exclusive_scan(np.array(KNOWN_IN, np.uint32)), np.array(KNOWN_OUT, np.uint32))
+
+
+def test_prefix_random_recurrence(oracle):  # :43-51
+    keys = synth.random_keys_u32(32, seed=9, lo=0, hi=8192)
+    hist = oracle.bit_histogram32(keys)
+    out = np.zeros(32, np.uint32)
+    for j in range(8):
+        for i in range(1, 4):
+            out[4 * j + i] = hist[4 * j + i - 1] + out[4 * j + i - 1]
+    assert np.array_equal(oracle.digitplace_exclusive_scan(hist), out)
+
+
+# ---- sort ----
+@pytest.mark.parametrize("n", [0, 1, 2, 130, 4099, 100000])
+def test_radix_equals_comparison_sort(oracle, n):
+    keys = synth.random_keys_u32(n, seed=1) if n else np.zeros(0, np.uint32)
+    keys = keys & np.uint32(0x3FF) if n > 1000 else keys  # many duplicates: stability matters
+    idx = np.arange(n, dtype=np.uint32)
+    k1, v1 = oracle.sort_pairs(keys, idx)
+    k2, v2 = oracle.radix_sort_pairs(keys, idx)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k1, keys[order]) and np.array_equal(v1, idx[order])
+    assert np.array_equal(k2, k1) and np.array_equal(v2, v1)
+
+
+def test_radix_u64(oracle):
+    rng = np.random.RandomState(2)
+    keys = (rng.randint(0, 1 << 31, size=5000).astype(np.uint64) << np.uint64(33)) | rng.randint(0, 1 << 31, size=5000).astype(np.uint64)
+    keys[::7] = keys[0]
+    vals = np.arange(5000, dtype=np.uint32)
+    k, v = oracle.radix_sort_pairs_u64(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+    assert np.array_equal(oracle.radix_sort_keys_u64(keys), keys[order])
+
+
+# ---- known answers recorded from the reference's own bvh.cpp ----
+def test_survey_known_answer_scene(oracle):
+    tris, meshes = synth.survey_known_answer_scene()
+    aabb = oracle.scene_aabb(tris, meshes)
+    assert np.allclose(aabb, [-0.349036, -2.04506, -1.04801, 0.348272, 2.047, 1.04835], rtol=0, atol=1e-5)  # survey prints 6 significant digits
+    cube = oracle.circumscribed_cube(aabb)
+    side = cube[3:] - cube[:3]
+    assert np.allclose(side, 0.697308, atol=2e-6)  # Q1: x extent on every axis
+    b = oracle.bvh_build(tris, meshes)
+    flat = oracle.flatten(b.clusters, b.left, b.right)
+    assert flat.size == 39999 and flat[0]["left"] == 1 and flat[0]["right"] == 20100
+    assert "%016x" % oracle.hash_flat_nodes(flat) == "6c2aabd40444c4ec"
+    assert "%016x" % oracle.hash_words(b.triangle_indices) == "cc1bb62a0ae92f47"
+    assert hash_words(node_words(flat)) == oracle.hash_flat_nodes(flat)  # python and C hashes agree
+
+
+def test_tree_invariants(oracle):
+    tris, meshes, _ = scenes.soup(3000)
+    b = oracle.bvh_build(tris, meshes)
+    n = b.n
+    assert b.trace_merges.sum() == n - 1
+    assert b.trace_active[0] == n
+    assert np.all(b.parent[: 2 * n - 2] != 0xFFFFFFFF) and b.parent[2 * n - 2] == 0xFFFFFFFF
+    flat = oracle.flatten(b.clusters, b.left, b.right)
+    leaves = (flat["left"] == 0) & (flat["right"] == 0)
+    assert leaves.sum() == n
+    assert np.array_equal(np.sort(flat["tri"][leaves]), np.arange(n))
+    inner = ~leaves
+    idx = np.nonzero(inner)[0]
+    assert np.all(flat["left"][inner] == idx + 1)
+    # parent box contains both children
+    for side in ("left", "right"):
+        ch = flat[side][inner]
+        assert np.all(flat["bmin"][inner] <= flat["bmin"][ch]) and np.all(flat["bmax"][inner] >= flat["bmax"][ch])
+
+
+def test_single_and_two_triangles(oracle):
+    tris, meshes, _ = scenes.soup(2, seed=4)
+    b1 = oracle.bvh_build(tris[:1], meshes)
+    f1 = oracle.flatten(b1.clusters, b1.left, b1.right)
+    assert f1.size == 1 and f1[0]["left"] == 0 and f1[0]["right"] == 0 and f1[0]["tri"] == 0
+    b2 = oracle.bvh_build(tris, meshes)
+    f2 = oracle.flatten(b2.clusters, b2.left, b2.right)
+    assert f2.size == 3 and f2[0]["left"] == 1 and f2[0]["right"] == 2
+
+
+# ---- traversal: BVH walk == brute force getAllHits semantics (raytracer.glsl:149-157) ----
+def test_bvh_traversal_equals_brute_force(oracle):
+    tris, meshes, L = scenes.soup(2000)
+    b = oracle.bvh_build(tris, meshes)
+    flat = oracle.flatten(b.clusters, b.left, b.right)
+    cam = synth.soup_camera(L, 64, 48)
+    hits = oracle.trace_primary(flat, tris, meshes, cam, 64, 48)
+    rays = oracle.get_rays(cam, 64, 48, 64, 48)
+    brute = oracle.closest_hit_brute(tris, meshes, rays)
+    assert hits["did_hit"].sum() > 200
+    assert np.array_equal(hits["did_hit"], brute["did_hit"])
+    h = hits["did_hit"] == 1
+    assert np.array_equal(hits["t"][h], brute["t"][h])
+    # ids may differ only on exact-t ties (first leaf in right-first DFS vs lowest index)
+    diff = hits["tri"][h] != brute["tri"][h]
+    assert diff.sum() == 0
+
+
+def test_mesh_traversal_ties_and_render(oracle):
+    tris, meshes = synth.grid_mesh(24, 24)
+    b = oracle.bvh_build(tris, meshes)
+    flat = oracle.flatten(b.clusters, b.left, b.right)
+    cam = synth.reference_camera(aspect=64 / 64)
+    hits = oracle.trace_primary(flat, tris, meshes, cam, 64, 64)
+    assert hits["did_hit"].mean() > 0.5
+    rgba, first, nrays = oracle.render(flat, tris, meshes, cam, 64, 64, bounces=2, shadow=True, light=(0.0, 3.0, -4.0))
+    assert np.array_equal(first["tri"], hits["tri"]) and np.array_equal(first["t"], hits["t"])
+    assert nrays >= 64 * 64 + hits["did_hit"].sum()
+    assert np.all(rgba[..., 3] == 1.0) and rgba[..., 0].max() > 0.1
+    barys = np.stack([hits["b0"], hits["b1"], hits["b2"]], 1)[hits["did_hit"] == 1]
+    assert np.all(barys >= 0) and np.allclose(barys.sum(1), 1.0, atol=1e-5)

@@ -1,0 +1,185 @@
+"""Traversal parity: closest-hit records of the CUDA kernels against the CPU restatement of
+raytracer.glsl.  north_star tolerance: triangle ids exact except documented ties, t and barycentrics
+within 1e-5 relative -- the kernels are in fact bit-identical (same fp32 op order, no FMA), which is
+what these tests assert; the 1e-5 bound is asserted too so a future relaxation stays inside it."""
+import numpy as np
+import pytest
+
+import scenes
+from realtimeraytracing_b200 import capi, synth
+from realtimeraytracing_b200.layouts import RAY
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5  # north_star
+
+
+def assert_hits_equal(got, exp, what=""):
+    assert np.array_equal(got["did_hit"], exp["did_hit"]), what + " did_hit"
+    h = exp["did_hit"] == 1
+    assert np.array_equal(got["tri"][h], exp["tri"][h]), what + " triangle ids"
+    for f in ("t", "b0", "b1", "b2"):
+        a, b = got[f][h], exp[f][h]
+        assert np.all(np.abs(a - b) <= REL_TOL * np.maximum(np.abs(b), 1e-30)), what + " " + f
+        assert np.array_equal(a, b), what + " %s is not bit-identical" % f
+    assert not got["t"][~h].any() and not got["tri"][~h].any()
+
+
+def build_pair(ctx, oracle, tris, meshes):
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    flat = bvh.flat_nodes()
+    return bvh, flat
+
+
+@pytest.mark.parametrize("flags", [capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER])
+def test_primary_rays_soup(ctx, oracle, flags):
+    tris, meshes, L = scenes.soup(20000)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 160, 96
+        cam = synth.soup_camera(L, W, H)
+        got = bvh.trace_primary(cam, W, H, W, H, flags=flags)
+        exp = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
+        assert exp["did_hit"].mean() > 0.3
+        assert_hits_equal(got, exp, "soup flags=%d" % flags)
+    finally:
+        bvh.close()
+
+
+@pytest.mark.parametrize("flags", [capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER])
+def test_primary_rays_mesh_with_exact_ties(ctx, oracle, flags):
+    """Connected mesh: rays through shared edges/vertices give equal t on two leaves (SURVEY Q6 ties)."""
+    tris, meshes = synth.grid_mesh(48, 40)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 192, 128
+        cam = synth.reference_camera(aspect=W / H)
+        got = bvh.trace_primary(cam, W, H, W, H, flags=flags)
+        exp = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
+        assert exp["did_hit"].mean() > 0.4
+        assert_hits_equal(got, exp, "mesh flags=%d" % flags)
+    finally:
+        bvh.close()
+
+
+def test_reference_pixel_mapping_q5(ctx, oracle):
+    """1920x1080-style geometry: floor(H/16)*16 rows are traced and divide the pixel position (Q5)."""
+    tris, meshes, L = scenes.soup(5000)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 120, 67  # floor -> 112 x 64
+        cam = synth.soup_camera(L, W, H)
+        got = bvh.trace_primary(cam, W, H)  # denominators default to the reference formula
+        dw, dh = synth.reference_denominators(W, H)
+        assert (dw, dh) == (112, 64)
+        exp = oracle.render(flat, tris, meshes, cam, W, H, dw, dh)[1]
+        assert_hits_equal(got, exp, "Q5")
+        g = got.reshape(H, W)
+        assert not g["did_hit"][dh:, :].any() and not g["did_hit"][:, dw:].any()
+    finally:
+        bvh.close()
+
+
+def test_two_meshes_with_model_matrices(ctx, oracle):
+    tris, meshes = scenes.two_mesh_scene()
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 128, 96
+        cam = synth.reference_camera(eye=(0.0, 0.0, -9.0), aspect=W / H)
+        got = bvh.trace_primary(cam, W, H, W, H)
+        exp = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
+        assert exp["did_hit"].sum() > 100
+        assert_hits_equal(got, exp, "two meshes")
+    finally:
+        bvh.close()
+
+
+def test_explicit_ray_batch_and_any_hit(ctx, oracle):
+    tris, meshes, L = scenes.soup(8000)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        rng = np.random.RandomState(3)
+        n = 5000
+        rays = np.zeros(n, dtype=RAY)
+        rays["o"][:, :3] = rng.uniform(-L, L, size=(n, 3))
+        rays["o"][:, 3] = 1.0
+        d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays["d"][:, :3] = d
+        rays["d"][::50, 0] = 0.0  # axis-parallel components: +-inf slabs (Q11)
+        for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER):
+            got = bvh.trace_rays(rays, flags=flags)
+            exp = oracle.trace_rays(flat, tris, meshes, rays)
+            assert_hits_equal(got, exp, "batch flags=%d" % flags)
+        tmax = rng.uniform(0.0, L, size=n).astype(np.float32)
+        occ = bvh.trace_rays(rays, any_hit=True, t_max=tmax)
+        assert np.array_equal(occ["did_hit"], oracle.any_hit(flat, tris, meshes, rays, tmax))
+        occ_inf = bvh.trace_rays(rays, any_hit=True)
+        assert np.array_equal(occ_inf["did_hit"], exp["did_hit"])
+    finally:
+        bvh.close()
+
+
+@pytest.mark.parametrize("shadow", [False, True])
+def test_multi_bounce_render(ctx, oracle, shadow):
+    tris, meshes, L = scenes.soup(20000)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 96, 64
+        cam = synth.soup_camera(L, W, H)
+        light = (0.3 * L, 0.8 * L, -1.2 * L)
+        for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER):
+            rgba, hits, nrays = bvh.render(cam, W, H, W, H, bounces=2, shadow=shadow, light=light, flags=flags)
+            ergba, ehits, enrays = oracle.render(flat, tris, meshes, cam, W, H, W, H, bounces=2, shadow=shadow, light=light)
+            assert nrays == enrays
+            assert_hits_equal(hits, ehits, "render primary")
+            assert np.array_equal(rgba, ergba), "image is not bit-identical"
+            assert rgba[..., 0].max() > 0.05
+    finally:
+        bvh.close()
+
+
+def test_row_ranges_tile_the_frame(ctx):
+    """Rows [row0,row1) rendered separately equal the full frame (what the multi-GPU sharding relies on)."""
+    tris, meshes, L = scenes.soup(10000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H = 128, 80
+        cam = synth.soup_camera(L, W, H)
+        full, fh, fr = bvh.render(cam, W, H, W, H, bounces=1)
+        parts, total = [], 0
+        for r0 in range(0, H, 16):
+            rgba, _, nr = bvh.render(cam, W, H, W, H, row0=r0, row1=min(H, r0 + 16), bounces=1)
+            parts.append(rgba); total += nr
+        assert np.array_equal(np.concatenate(parts, axis=0), full) and total == fr
+    finally:
+        bvh.close()
+
+
+def test_pruned_equals_reference_order_on_a_big_frame(ctx):
+    """Size-independent property at scale: the default (pruned) order returns exactly the records of the
+    shader's order on a 1M-triangle scene at 1280x720 (no oracle needed)."""
+    tris, meshes, L = scenes.soup(1_000_000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H = 1280, 720
+        cam = synth.soup_camera(L, W, H)
+        a = bvh.trace_primary(cam, W, H, flags=capi.TRACE_DEFAULT)
+        b = bvh.trace_primary(cam, W, H, flags=capi.TRACE_REFERENCE_ORDER)
+        assert a["did_hit"].mean() > 0.5
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    finally:
+        bvh.close()
+
+
+def test_adopted_bvh_traces_identically(ctx):
+    tris, meshes, L = scenes.soup(6000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H = 64, 48
+        cam = synth.soup_camera(L, W, H)
+        exp = bvh.trace_primary(cam, W, H, W, H)
+        other = capi.Bvh(ctx).adopt_dev(bvh.device_nodes, tris.size, bvh.device_triangles, bvh.device_meshes, meshes.size)
+        got = other.trace_primary(cam, W, H, W, H)
+        assert np.array_equal(got.view(np.uint8), exp.view(np.uint8))
+        other.close()
+    finally:
+        bvh.close()
