@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the acceleration-structure + ray-cast path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched with torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a 10M-triangle synthetic
+soup, FULL rebuild per frame (scene box + Morton -> Onesweep sort -> PLOC -> flatten), then one 3840x2160
+frame of primary + 2 bounce rays.  One "step" is one such frame.  With N>1 the rebuild stays on rank 0
+(PLOC does not shard), its result is broadcast over NVLink, image row blocks are dealt to the ranks and
+all-gathered (configs[4] layout, same bounce count so the per-N values are comparable): strong scaling.
+
+value  = rays traced by all ranks / device time of the step, inputs resident in HBM
+e2e    = the same through the host-pointer C ABI: triangles uploaded from pinned host memory every step
+         (rtr_bvh_build), image read back to pinned host memory every step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s"
+WORKLOAD = "10M-triangle soup, full BVH rebuild per frame + 3840x2160 primary + 2-bounce rays"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--tris", type=int, default=10_000_000)
+    p.add_argument("--width", type=int, default=3840)
+    p.add_argument("--height", type=int, default=2160)
+    p.add_argument("--bounces", type=int, default=2)
+    p.add_argument("--rows-per-block", type=int, default=16)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-kernel side measurements")
+    p.add_argument("--reference-order", action="store_true", help="trace in the shader's exact visiting order (no pruning)")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own bvh.cpp (oracle/_ref) for the rebuild + the oracle's restatement of
+# raytracer.glsl for the rays, on the host cores.  Used for cpu_baseline and --impl reference.
+# This is the ONLY place bench.py touches oracle/.
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_sizes(args, budget_s):
+    """Bounded sample of the workload: triangles and pixels scaled by the same factor f, chosen from a
+    quick calibration (65 536-triangle rebuild + a 256x144 frame) so one step costs about budget_s."""
+    cal = CpuArm(args, 65536, 256, 144)
+    rays, secs, build_s = cal.step(split=True)
+    per_tri = build_s / cal.n * 1.4            # the reference's build cost grows slightly faster than n
+    per_ray = (secs - build_s) / max(1, rays) * 2.5   # unpruned walks visit ~N^(1/3) more nodes at scale
+    full = args.tris * per_tri + args.width * args.height * 2.4 * per_ray
+    f = min(0.1, max(0.001, budget_s / full))
+    n = min(int(args.tris * f), 1_000_000)
+    w = int(round(args.width * f ** 0.5 / 16)) * 16
+    h = int(round(args.height * f ** 0.5 / 16)) * 16
+    return max(n, 1000), max(w, 64), max(h, 32)
+
+
+class CpuArm:
+    """Reference build: OMP_NUM_THREADS=1, the reference's fastest configuration -- its OpenMP path is
+    slower than serial -- rays: all host cores."""
+
+    def __init__(self, args, n, w, h):
+        os.environ["OMP_NUM_THREADS"] = "1"
+        from oracle import Oracle, Reference, reference_available
+        from realtimeraytracing_b200 import synth
+        self.o = Oracle()
+        self.n, self.w, self.h, self.bounces = n, w, h, args.bounces
+        self.tris, self.meshes, L = synth.triangle_soup(n)
+        self.cam = synth.soup_camera(L, w, h)
+        cap = 65536 if n <= 65536 else 1048576
+        self.ref = Reference(cap) if reference_available(cap) else None
+        self.kind = "reference" if self.ref is not None else "port"
+        self.cores = os.cpu_count() or 1
+
+    def step(self, split=False):
+        """One frame: rebuild + flatten + all rays.  Returns (rays, seconds[, build seconds])."""
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            rb = self.ref.bvh_build(self.tris, self.meshes, want_morton=False)  # the reference's own bvh.cpp
+            clusters, left, right = rb.clusters, rb.left, rb.right
+        else:
+            ob = self.o.bvh_build(self.tris, self.meshes)
+            clusters, left, right = ob.clusters, ob.left, ob.right
+        flat = self.o.flatten(clusters, left, right)              # scene.cpp:189-208 restated (GL file, not compilable)
+        t1 = time.perf_counter()
+        _, _, rays = self.o.render(flat, self.tris, self.meshes, self.cam, self.w, self.h, self.w, self.h,
+                                   bounces=self.bounces, threads=self.cores)  # raytracer.glsl restated, OpenMP over rows
+        t2 = time.perf_counter()
+        return (rays, t2 - t0, t1 - t0) if split else (rays, t2 - t0)
+
+    def describe(self):
+        build = "reference bvh.cpp via oracle/_ref, 1 thread (its OpenMP path is slower)" \
+            if self.kind == "reference" else "oracle C port, 1 thread"
+        return "%d-triangle soup rebuild [%s] + %dx%d primary+%d-bounce rays [oracle traversal, %d threads]" % (
+            self.n, build, self.w, self.h, self.bounces, self.cores)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    n, w, h = cpu_sample_sizes(args, 150.0 / max(1, total))
+    arm = CpuArm(args, n, w, h)
+    for _ in range(args.warmup):
+        arm.step()
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, s = arm.step()
+        rays += r; secs += s
+    val = rays / secs / 1e6
+    line = {
+        "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "sample": arm.describe()},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+ALGO_BYTES = {  # algorithmic HBM bytes per launch as a function of (n triangles / keys); DESIGN.md section 4
+    "onesweep_kernel<u32,pairs>": lambda n: 16.0 * n,   # read 8 + write 8 per (code,index) pair and pass
+    "onesweep_kernel<u32,keys>": lambda n: 8.0 * n,
+    "radix_histogram_kernel": lambda n: 4.0 * n,
+    "scene_aabb_kernel": lambda n: 64.0 * n,
+    "morton_kernel": lambda n: 72.0 * n,                 # 64 read + code 4 + index 4
+    "leaf_init_kernel": lambda n: 104.0 * n,             # index 4 + triangle 64 + node 32 + active id 4
+}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from realtimeraytracing_b200 import build as rbuild, capi, parallel, synth
+    from realtimeraytracing_b200.layouts import MESH, TRIANGLE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs `python -m torch.distributed.run --nproc-per-node %d bench.py ...`" % (args.gpus, args.gpus))
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: librtr_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rbuild.build()
+
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    comm = parallel.RankComm(ctx) if world > 1 else None
+
+    n, W, H, bounces, rpb = args.tris, args.width, args.height, args.bounces, args.rows_per_block
+    flags = capi.TRACE_REFERENCE_ORDER if args.reference_order else capi.TRACE_DEFAULT
+    dw, dh = synth.reference_denominators(W, H)
+    L = synth.soup_extent(n)
+    cam = synth.soup_camera(L, W, H)
+
+    # ---- inputs: generated on the host once, resident in HBM for `value`, pinned for `e2e` ----
+    tris_pinned = meshes_np = None
+    d_tris = d_meshes = None
+    if rank == 0:
+        tris_np, meshes_np, _ = synth.triangle_soup(n)
+        tris_pinned = torch.empty(n * TRIANGLE.itemsize, dtype=torch.uint8, pin_memory=True)
+        tris_pinned.numpy().view(TRIANGLE)[:] = tris_np
+        del tris_np
+        with torch.cuda.stream(stream):
+            d_tris = torch.empty(n * TRIANGLE.itemsize, dtype=torch.uint8, device=dev)
+            d_tris.copy_(tris_pinned, non_blocking=True)
+            d_meshes = torch.from_numpy(meshes_np.view(np.uint8).copy()).to(dev)
+    with torch.cuda.stream(stream):
+        d_rgba = torch.zeros(H * W * 4, dtype=torch.float32, device=dev)
+        d_rays = torch.zeros(1, dtype=torch.int64, device=dev)
+    rgba_pinned = torch.empty(H * W * 4, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    stream.synchronize()
+
+    bvh = capi.Bvh(ctx)
+
+    def frame_device():
+        """value path: inputs resident in HBM."""
+        if rank == 0:
+            bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+        if world > 1:
+            bvh.broadcast(0)
+        bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, rank, world, rays_dev=d_rays.data_ptr(),
+                               bounces=bounces, flags=flags)
+        if world > 1:
+            ctx.allgather_rows(d_rgba.data_ptr(), W, H, 16, rpb)
+
+    def frame_e2e():
+        """e2e path: host triangles in, host image out, through the host-pointer C ABI."""
+        if rank == 0:
+            bvh.build(tris_pinned.numpy().view(TRIANGLE), meshes_np)      # H2D of the triangles inside rtr_bvh_build
+        if world > 1:
+            bvh.broadcast(0)
+        bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, rank, world, rays_dev=d_rays.data_ptr(),
+                               bounces=bounces, flags=flags)
+        if world > 1:
+            ctx.allgather_rows(d_rgba.data_ptr(), W, H, 16, rpb)
+        if rank == 0:
+            ctx.download(rgba_pinned.numpy(), d_rgba.data_ptr())          # D2H of the frame (synchronises)
+        else:
+            ctx.sync()
+
+    def barrier():
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """device time of `steps` calls: events on the launching stream, barrier + sync both sides, max over ranks"""
+        barrier()
+        with torch.cuda.stream(stream):
+            d_rays.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ctx.launch_count
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count - launches0
+        rays = int(d_rays.item())
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            r = torch.tensor([rays, launches], dtype=torch.int64, device=dev)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            rays, launches = int(r[0].item()), int(r[1].item())
+        return ms, rays, launches
+
+    # ---- warm-up, then the timed region ----
+    for _ in range(max(3, args.warmup)):
+        frame_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, rays, launches = timed(frame_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = rays / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-pointer ABI ----
+    for _ in range(2):
+        frame_e2e()
+    e2e_steps = args.steps
+    e2e_ms, e2e_rays, _ = timed(frame_e2e, e2e_steps)
+    e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+    h2d = n * TRIANGLE.itemsize + MESH.itemsize + 284
+    d2h = H * W * 16
+
+    extras = {}
+    roofline = None
+    if rank == 0 and not args.no_extras:
+        # per-stage device times of the rebuild (events inside the library)
+        bvh.enable_stage_timing(True)
+        stage = np.zeros(6)
+        reps = 5
+        for _ in range(reps):
+            bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            stage += bvh.stage_ms()
+        stage /= reps
+        bvh.enable_stage_timing(False)
+        active, merges = bvh.iteration_trace()
+        extras["build_ms"] = {"morton": stage[0], "sort": stage[1], "leaf_init": stage[2], "ploc_loop": stage[3],
+                              "flatten": stage[4], "total": stage[5], "ploc_iterations": int(active.size),
+                              "sum_active_over_n": float(active.sum()) / n}
+        extras["sort_gkeys_s"] = n / (stage[1] * 1e-3) / 1e9
+        # algorithmic bytes of the whole rebuild from this run's own iteration trace (SURVEY.md 8d formula)
+        ploc_bytes = float((active.astype(np.float64) * 40).sum() + (merges.astype(np.float64) * 64).sum())
+        build_bytes = n * (64 + 64 + 8) + n * 68.0 + n * (4 + 64 + 48) + ploc_bytes + (2 * n - 1) * 96.0
+        # per-kernel times of one frame (CUDA events around every launch of the dominant kernels)
+        ctx.profile_enable(True)
+        if world == 1:
+            frame_device()
+        else:
+            bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        step_ms = ms / args.steps
+        kern = {}
+        for name, (tot, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            kern[name] = {"ms_total": tot, "launches": cnt, "share_of_step": tot / step_ms}
+            if name in ALGO_BYTES:
+                gbs = ALGO_BYTES[name](n) * cnt / (tot * 1e-3) / 1e9
+                kern[name]["algorithmic_GBps"] = gbs
+        if "ploc_iteration_kernel" in kern:
+            big = active[active > 1024].astype(np.float64)
+            kern["ploc_iteration_kernel"]["algorithmic_GBps"] = float(
+                (big * 40).sum() + (merges[: big.size].astype(np.float64) * 64).sum()) / (kern["ploc_iteration_kernel"]["ms_total"] * 1e-3) / 1e9
+        extras["kernels"] = kern
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # dominant HBM-bound kernel of the rebuild
+        hbm_kernels = [(k, v) for k, v in kern.items() if "algorithmic_GBps" in v]
+        if hbm_kernels:
+            name, v = max(hbm_kernels, key=lambda kv: kv[1]["ms_total"])
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "kernel": name, "achieved": v["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                        "frac": v["algorithmic_GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                        "avg_launch_ms": v["ms_total"] / v["launches"]}
+        extras["build_roofline"] = {"algorithmic_bytes": build_bytes, "achieved_GBps": build_bytes / (stage[5] * 1e-3) / 1e9,
+                                    "frac_of_peak": build_bytes / (stage[5] * 1e-3) / 1e9 / peak}
+        extras["sort_roofline"] = {"algorithmic_bytes": 68.0 * n, "achieved_GBps": 68.0 * n / (stage[1] * 1e-3) / 1e9,
+                                   "frac_of_peak": 68.0 * n / (stage[1] * 1e-3) / 1e9 / peak}
+        # traversal alone (BVH already built): the Mrays/s the rays see
+        tr_ms, tr_rays, _ = timed(lambda: bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, rays_dev=d_rays.data_ptr(),
+                                                                 bounces=bounces, flags=flags), 3) if world == 1 else (None, None, None)
+        if tr_ms:
+            extras["trace_only"] = {"ms_per_frame": tr_ms / 3, "mrays_s": tr_rays / (tr_ms * 1e-3) / 1e6,
+                                    "rays_per_frame": tr_rays // 3}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cn, cw, ch = cpu_sample_sizes(args, 12.0)
+        arm = CpuArm(args, cn, cw, ch)
+        crays, csecs = arm.step()
+        cpu_baseline = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind,
+                        "sample": arm.describe(), "seconds": csecs}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (n, W, H, bounces) == (10_000_000, 3840, 2160, 2) else
+                       "%d-triangle soup, full BVH rebuild per frame + %dx%d primary + %d-bounce rays" % (n, W, H, bounces),
+                       "triangles": n, "image": [W, H], "traced_pixels": [dw, dh], "bounces": bounces,
+                       "rays_per_step": rays // args.steps, "search_radius": 16,
+                       "trace_order": "reference" if args.reference_order else "pruned (identical records)",
+                       "parallelism": "build on rank 0 + NCCL broadcast + %d-row blocks dealt to %d rank(s)" % (rpb, world),
+                       "l2": "inputs larger than L2 (640 MB of triangles + 960 MB of nodes per step), no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        line.update(extras)
+        print(json.dumps(line, default=float))
+
+    bvh.close()
+    if comm:
+        comm.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

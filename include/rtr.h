@@ -112,6 +112,14 @@ int rtr_ctx_sm_count(const rtr_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
 uint64_t rtr_ctx_launch_count(const rtr_ctx* ctx);
 
+/* per-kernel device times: while enabled, the launches of the kernels that dominate the path are
+ * bracketed by CUDA events; read returns one line per kernel name in `names` ('\n' separated) with its
+ * summed milliseconds and launch count since enable.  Replaces the reference's commented-out
+ * glfwGetTime phase timers (bvh.cpp:21-23,65-103). */
+int rtr_ctx_profile_enable(rtr_ctx* ctx, int enable);
+int rtr_ctx_profile_read(rtr_ctx* ctx, char* names, size_t names_bytes, float* total_ms, uint32_t* counts,
+                         uint32_t capacity, uint32_t* n_out);
+
 /* pinned host buffers for the host-pointer entry points (plain malloc'd memory also works) */
 int rtr_host_alloc(size_t bytes, void** out);
 int rtr_host_free(void* p);
@@ -228,6 +236,14 @@ int rtr_render_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
                    uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
                    uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
                    uint32_t flags, float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
+
+/* the same frame, but only the row blocks dealt to shard_rank (block b of rows_per_block rows belongs
+ * to rank b % shard_count); rgba_dev / primary_hits_dev are FULL-image buffers written at global rows */
+int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+                           uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+                           uint32_t rows_per_block, uint32_t shard_rank, uint32_t shard_count,
+                           uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
+                           float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
 /* ---- multi-GPU (one process per GPU; NCCL resolved at run time with dlopen("libnccl.so.2"),
  * so inside a torch process it is the very library torch.distributed already loaded) ---- */

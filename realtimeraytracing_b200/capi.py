@@ -31,7 +31,7 @@ SYMBOLS = [
     "rtr_bvh_triangle_indices", "rtr_bvh_clusters", "rtr_bvh_flat_nodes", "rtr_bvh_device_nodes",
     "rtr_bvh_device_triangles", "rtr_bvh_device_meshes", "rtr_bvh_adopt_dev",
     "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
-    "rtr_render_dev",
+    "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
 ]
 
@@ -119,6 +119,9 @@ def load_library():
     L.rtr_trace_rays_dev.argtypes = [vp, vp, vp, u64, i32, vp, u32, vp]
     L.rtr_render.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_render_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, u32, vp, vp, vp]
+    L.rtr_render_sharded_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, u32, i32, vp, u32, vp, vp, vp]
+    L.rtr_ctx_profile_enable.argtypes = [vp, i32]
+    L.rtr_ctx_profile_read.argtypes = [vp, vp, sz, vp, vp, u32, vp]
     L.rtr_comm_unique_id.argtypes = [vp]
     L.rtr_comm_init.argtypes = [vp, vp, i32, i32]
     L.rtr_comm_destroy.argtypes = [vp]
@@ -198,6 +201,20 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.rtr_ctx_launch_count(self.handle))
+
+    def profile_enable(self, enable: bool = True):
+        self.check(self.lib.rtr_ctx_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since profile_enable(True)."""
+        cap = 64
+        names = C.create_string_buffer(8192)
+        ms = np.zeros(cap, dtype=np.float32)
+        cnt = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self.check(self.lib.rtr_ctx_profile_read(self.handle, names, 8192, _ptr(ms), _ptr(cnt), cap, C.byref(n)))
+        keys = [k for k in names.value.decode().split("\n") if k]
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}
 
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -456,6 +473,15 @@ class Bvh:
                                            row0, row1, bounces, 1 if shadow else 0, _ptr(light), flags, _ptr(rgba),
                                            _ptr(hits), _ptr(nrays)))
         return rgba, hits, int(nrays[0])
+
+    def render_sharded_dev(self, camera, width, height, rgba_dev, rows_per_block, shard_rank, shard_count, hits_dev=None,
+                           rays_dev=None, denom_w=0, denom_h=0, bounces=0, shadow=False, light=(0.0, 0.0, 0.0), flags=0):
+        camera = _as(camera, CAMERA)
+        light = np.asarray(light, dtype=np.float32)
+        self.ctx.check(self.lib.rtr_render_sharded_dev(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w,
+                                                       denom_h, rows_per_block, shard_rank, shard_count, bounces,
+                                                       1 if shadow else 0, _ptr(light), flags, _ptr(rgba_dev),
+                                                       _ptr(hits_dev), _ptr(rays_dev)))
 
     def render_dev(self, camera, width, height, rgba_dev, hits_dev=None, rays_dev=None, denom_w=0, denom_h=0, row0=0,
                    row1=0, bounces=0, shadow=False, light=(0.0, 0.0, 0.0), flags=0):

@@ -32,6 +32,23 @@ int rtr_ws_reserve(rtr_ctx* ctx, size_t bytes) {
     return RTR_OK;
 }
 
+static cudaEvent_t prof_event(rtr_ctx* ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+void rtr_prof_begin(rtr_ctx* ctx, const char* name) {
+    rtr_ctx::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->prof.push_back(r);
+    ctx->prof_open = true;
+}
+void rtr_prof_end(rtr_ctx* ctx) {
+    cudaEventRecord(ctx->prof.back().e1, ctx->stream);
+    ctx->prof_open = false;
+}
+
 namespace {
 
 template <typename T>
@@ -255,6 +272,8 @@ int rtr_ctx_destroy(rtr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     rtr_comm_destroy(ctx);
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -281,6 +300,45 @@ int rtr_ctx_set_stream(rtr_ctx* ctx, void* stream) {
 int rtr_ctx_device(const rtr_ctx* ctx) { return ctx ? ctx->device : -1; }
 int rtr_ctx_sm_count(const rtr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t rtr_ctx_launch_count(const rtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rtr_ctx_profile_enable(rtr_ctx* ctx, int enable) {
+    if (!ctx) return RTR_E_INVALID;
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof) { ctx->prof_pool.push_back(r.e0); ctx->prof_pool.push_back(r.e1); }
+    ctx->prof.clear();
+    ctx->prof_open = false;
+    ctx->profiling = enable != 0;
+    return RTR_OK;
+}
+
+int rtr_ctx_profile_read(rtr_ctx* ctx, char* names, size_t names_bytes, float* total_ms, uint32_t* counts,
+                         uint32_t capacity, uint32_t* n_out) {
+    if (!ctx || !n_out) return RTR_E_INVALID;
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<const char*> keys;
+    std::vector<float> ms;
+    std::vector<uint32_t> cnt;
+    for (auto& r : ctx->prof) {
+        float t = 0.f;
+        RTR_CUDA(ctx, cudaEventElapsedTime(&t, r.e0, r.e1));
+        size_t k = 0;
+        for (; k < keys.size(); ++k) if (strcmp(keys[k], r.name) == 0) break;
+        if (k == keys.size()) { keys.push_back(r.name); ms.push_back(0.f); cnt.push_back(0); }
+        ms[k] += t; cnt[k] += 1;
+    }
+    *n_out = (uint32_t)keys.size();
+    size_t off = 0;
+    if (names && names_bytes) names[0] = 0;
+    for (size_t k = 0; k < keys.size() && k < capacity; ++k) {
+        if (total_ms) total_ms[k] = ms[k];
+        if (counts) counts[k] = cnt[k];
+        if (names) {
+            const size_t len = strlen(keys[k]);
+            if (off + len + 2 <= names_bytes) { memcpy(names + off, keys[k], len); off += len; names[off++] = '\n'; names[off] = 0; }
+        }
+    }
+    return RTR_OK;
+}
 
 int rtr_host_alloc(size_t bytes, void** out) {
     if (!out) return RTR_E_INVALID;
@@ -674,6 +732,17 @@ int rtr_render_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
     return rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, row0, row1, bounces, shadow, light_pos, flags,
                              rgba_dev, hits_dev, rays_dev);
+}
+
+int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
+                           uint32_t denom_w, uint32_t denom_h, uint32_t rows_per_block, uint32_t shard_rank,
+                           uint32_t shard_count, uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
+                           float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
+    RTR_CHECK(trace_args_ok(ctx, b, cam));
+    if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
+    if (shard_count == 0) return rtr_set_error(ctx, RTR_E_INVALID, "render: shard_count == 0");
+    return rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, bounces, shadow, light_pos, flags,
+                             rgba_dev, hits_dev, rays_dev, rows_per_block, shard_rank, shard_count);
 }
 
 int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height, uint32_t denom_w,

@@ -30,6 +30,12 @@ struct rtr_ctx {
     // small pinned host scratch for counters read back during a build
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // optional per-kernel timing (rtr_ctx_profile_*): CUDA events around the launches that matter
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
+    bool prof_open = false;
     // NCCL (resolved with dlopen at rtr_comm_init)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -53,9 +59,19 @@ int rtr_ws_reserve(rtr_ctx* ctx, size_t bytes);  // ensures ctx->ws has >= bytes
         if (_r != RTR_OK) return _r; \
     } while (0)
 
+void rtr_prof_begin(rtr_ctx* ctx, const char* name);
+void rtr_prof_end(rtr_ctx* ctx);
+
+// put before a kernel launch whose duration should be reported by rtr_ctx_profile_read
+#define RTR_PROF(ctx, name)                               \
+    do {                                                  \
+        if ((ctx)->profiling) rtr_prof_begin((ctx), name); \
+    } while (0)
+
 #define RTR_LAUNCH_CHECK(ctx)                   \
     do {                                        \
         (ctx)->launches++;                      \
+        if ((ctx)->prof_open) rtr_prof_end(ctx); \
         RTR_CUDA((ctx), cudaGetLastError());    \
     } while (0)
 

@@ -178,10 +178,12 @@ int rtr_morton_launch(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32
         uint32_t blocks = (array_len + kBlock - 1) / kBlock;
         const uint32_t cap = (uint32_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
         if (blocks > cap) blocks = cap;
+        RTR_PROF(ctx, "scene_aabb_kernel");
         scene_aabb_kernel<<<blocks, kBlock, 0, ctx->stream>>>(tris, array_len, meshes, ordered6);
         RTR_LAUNCH_CHECK(ctx);
     }
     const uint32_t blocks = n ? (n + kBlock - 1) / kBlock : 1;
+    RTR_PROF(ctx, "morton_kernel");
     morton_kernel<<<blocks, kBlock, 0, ctx->stream>>>(tris, n, meshes, ordered6, codes, indices, codes64, bounds12);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;

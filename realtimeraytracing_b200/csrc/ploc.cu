@@ -488,6 +488,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     RTR_CHECK(record(b, 2));
     // 3. leaves
     RTR_CUDA(ctx, cudaMemsetAsync(b->tparams, 0, sizeof(TraceParams), ctx->stream));
+    RTR_PROF(ctx, "leaf_init_kernel");
     leaf_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->tri_idx, n, b->node_lo,
                                                                b->node_hi, b->cin, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
@@ -509,6 +510,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     while (bound_n > kTailN) {
         const uint32_t tiles = (bound_n + kTileT - 1) / kTileT;
         for (int k = 0; k < kChunk; ++k) {
+            RTR_PROF(ctx, "ploc_iteration_kernel");
             ploc_iteration_kernel<<<tiles, kPBlock, 0, ctx->stream>>>(
                 launch_idx, n, radius, b->cin, b->cout, b->node_lo, b->node_hi, b->isize, b->state, b->tile_status,
                 b->trace_active, b->trace_merges, b->iter_first_id);
@@ -527,6 +529,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         last_iter = h_state->iter;
         bound_n = h_state->n_active;
     }
+    RTR_PROF(ctx, "ploc_tail_kernel");
     ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(launch_idx, n, radius, b->cin, b->cout, b->node_lo,
                                                                    b->node_hi, b->isize, b->state, b->trace_active,
                                                                    b->trace_merges, b->iter_first_id);
@@ -559,6 +562,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         while (it >= 0) {
             const uint32_t count = b->h_first_id[it + 1] - b->h_first_id[it];
             if (count > kSmall) {
+                RTR_PROF(ctx, "flatten_level_kernel");
                 flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node_lo,
                                                                                    b->node_hi, b->isize, b->ipos, b->flat);
                 RTR_LAUNCH_CHECK(ctx);
@@ -566,6 +570,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             } else {
                 int lo = it;
                 while (lo - 1 >= 0 && b->h_first_id[lo] - b->h_first_id[lo - 1] <= kSmall) --lo;
+                RTR_PROF(ctx, "flatten_small_levels_kernel");
                 flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node_lo,
                                                                          b->node_hi, b->isize, b->ipos, b->flat);
                 RTR_LAUNCH_CHECK(ctx);

@@ -379,6 +379,8 @@ int launch_pass(rtr_ctx* ctx, const KeyT* kin, KeyT* kout, const uint32_t* vin, 
         RTR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    RTR_PROF(ctx, sizeof(KeyT) == 4 ? (PAIRS ? "onesweep_kernel<u32,pairs>" : "onesweep_kernel<u32,keys>")
+                                    : (PAIRS ? "onesweep_kernel<u64,pairs>" : "onesweep_kernel<u64,keys>"));
     kern<<<tiles, Cfg::BLOCK, smem, ctx->stream>>>(kin, kout, vin, vout, n, tiles, shift, mask, gbase, status, counter);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
@@ -407,6 +409,7 @@ int sort_impl(rtr_ctx* ctx, KeyT* keys, uint32_t* vals, uint32_t n, int begin_bi
         uint32_t blocks = (n / 4 + 511) / 512;
         const uint32_t cap = (uint32_t)ctx->sm_count * 4;
         blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+        RTR_PROF(ctx, "radix_histogram_kernel");
         radix_histogram_kernel<KeyT, Cfg::MAX_PASSES><<<blocks, 512, 0, ctx->stream>>>(keys, n, begin_bit, end_bit, passes, ws.ghist);
         RTR_LAUNCH_CHECK(ctx);
         radix_scan_kernel<<<passes, kRadix, 0, ctx->stream>>>(ws.ghist, ws.gbase);

@@ -257,6 +257,20 @@ __device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const rtr_
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
+// Which image rows a launch covers: a contiguous range [row0, row0+rows) written at local row
+// indices, or (count > 1) the row blocks dealt to one rank -- block b of rows_per_block rows belongs
+// to rank b % count -- written at their global rows of the full image.
+struct RowMap {
+    uint32_t row0, rows, height;
+    uint32_t rpb, rank, count;
+};
+__device__ __forceinline__ bool map_row(const RowMap& m, uint32_t y_local, uint32_t& y, uint32_t& out_row) {
+    if (m.count <= 1) { y = m.row0 + y_local; out_row = y_local; return true; }
+    y = (m.rank + (y_local / m.rpb) * m.count) * m.rpb + (y_local % m.rpb);
+    out_row = y;
+    return y < m.height;
+}
+
 // Pixels are mapped to threads in 8x4 blocks per warp (2-D locality => coherent node fetches).
 __device__ __forceinline__ bool pixel_of_thread(uint32_t width, uint32_t rows, uint32_t& x, uint32_t& y_local) {
     const uint32_t tiles_x = (width + 7) / 8;
@@ -319,14 +333,13 @@ template <bool PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
 render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
               const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp, const rtr_camera cam,
-              uint32_t width, uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t rows,
+              uint32_t width, uint32_t denom_w, uint32_t denom_h, const RowMap rm,
               uint32_t bounces, int shadow, float lx, float ly, float lz,
               float4* __restrict__ rgba, rtr_hit* __restrict__ hits, unsigned long long* __restrict__ rays_traced) {
-    uint32_t x, yl;
-    const bool live = pixel_of_thread(width, rows, x, yl);
+    uint32_t x, yl, y = 0, out_row = 0;
+    const bool live = pixel_of_thread(width, rm.rows, x, yl) && map_row(rm, yl, y, out_row);
     uint32_t traced = 0;
     if (live) {
-        const uint32_t y = row0 + yl;
         float L = 0.f, wgt = 1.f;
         Hit first;
         first.b0 = first.b1 = first.b2 = first.t = 0.f; first.did_hit = 0u; first.tri = 0u;
@@ -364,7 +377,7 @@ render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict
                 }
             }
         }
-        const size_t o = (size_t)yl * width + x;
+        const size_t o = (size_t)out_row * width + x;
         if (rgba) rgba[o] = make_float4(L, L, L, 1.f);
         if (hits) store_hit(hits, o, first);
     }
@@ -397,6 +410,7 @@ int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& c
                              width, height, row0, row1, denom_w, denom_h);
     const uint32_t rows = row1 - row0;
     const uint32_t grid = pixel_grid(width, rows);
+    RTR_PROF(ctx, "trace_primary_kernel");
     if (flags & RTR_TRACE_REFERENCE_ORDER)
         trace_primary_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, cam,
                                                                            width, denom_w, denom_h, row0, rows, hits);
@@ -425,22 +439,34 @@ int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, u
 
 int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
                       uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
-                      const float light[3], uint32_t flags, float* rgba, rtr_hit* hits, uint64_t* rays) {
+                      const float light[3], uint32_t flags, float* rgba, rtr_hit* hits, uint64_t* rays,
+                      uint32_t rows_per_block, uint32_t shard_rank, uint32_t shard_count) {
     resolve_denoms(width, height, denom_w, denom_h);
     if (row1 == 0) row1 = height;
     if (width == 0 || row0 >= row1 || row1 > height || denom_w == 0 || denom_h == 0)
         return rtr_set_error(ctx, RTR_E_INVALID, "render: bad image geometry %ux%u rows [%u,%u) denom %ux%u", width,
                              height, row0, row1, denom_w, denom_h);
-    const uint32_t rows = row1 - row0;
+    RowMap rm;
+    rm.row0 = row0; rm.rows = row1 - row0; rm.height = height; rm.rpb = 1; rm.rank = 0; rm.count = 1;
+    if (shard_count > 1) {
+        if (rows_per_block == 0 || shard_rank >= shard_count)
+            return rtr_set_error(ctx, RTR_E_INVALID, "render: bad shard %u/%u rows_per_block %u", shard_rank, shard_count, rows_per_block);
+        const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
+        const uint32_t mine = blocks > shard_rank ? (blocks - shard_rank + shard_count - 1) / shard_count : 0;
+        if (mine == 0) return RTR_OK;
+        rm.row0 = 0; rm.rows = mine * rows_per_block; rm.rpb = rows_per_block; rm.rank = shard_rank; rm.count = shard_count;
+    }
+    const uint32_t rows = rm.rows;
     const uint32_t grid = pixel_grid(width, rows);
+    RTR_PROF(ctx, "render_kernel");
     const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
     if (flags & RTR_TRACE_REFERENCE_ORDER)
         render_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, row0, rows, bounces, shadow, lx, ly,
+            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly,
             lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
     else
         render_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, row0, rows, bounces, shadow, lx, ly,
+            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly,
             lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
