@@ -56,6 +56,14 @@ struct rtr_bvh {
     rtr_node* flat_recv = nullptr; // receive buffer of rtr_bvh_broadcast on non-root ranks
     size_t recv_cap = 0;           // triangles flat_recv/tris_own were sized for by a broadcast
     TraceParams* tparams = nullptr;
+    // world-space triangle cache read by the traversal kernels: 3 float4 per triangle
+    // (P0.xyz,P1.x)(P1.yz,P2.xy)(P2.z,-,-,-).  Built BVH: slot = leaf cluster id (Morton rank), which the
+    // flatten also stores in the leaf's third padding word; adopted nodes: slot = triangle id.
+    float4* wtri = nullptr;             // [3*cap] written by leaf_init_kernel
+    float4* wtri_own = nullptr;         // adopted / received BVHs
+    size_t wtri_own_cap = 0;            // triangles wtri_own was sized for
+    const float4* wtri_view = nullptr;  // what traversal reads
+    bool wtri_by_rank = true;
 
     // host mirrors of the last build
     uint32_t iterations = 0;

@@ -120,13 +120,15 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
     uint32_t* h_hdr = static_cast<uint32_t*>(ctx->pinned) + 64;
     uint32_t* d_hdr = static_cast<uint32_t*>(ctx->ws);
     if (is_root) {
-        h_hdr[0] = (*bvh)->n; h_hdr[1] = (*bvh)->nb_meshes; h_hdr[2] = 0; h_hdr[3] = 0;
+        // [2]: the root's triangle-cache indexing (1 = by leaf rank, a BVH built here; 0 = by triangle id, adopted)
+        h_hdr[0] = (*bvh)->n; h_hdr[1] = (*bvh)->nb_meshes; h_hdr[2] = (*bvh)->wtri_by_rank ? 1u : 0u; h_hdr[3] = 0;
         RTR_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr, 16, cudaMemcpyHostToDevice, ctx->stream));
     }
     RTR_NCCL(ctx, g_nccl.Broadcast(d_hdr, d_hdr, 16, kNcclUint8, root, comm, ctx->stream));
     RTR_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
     RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint32_t n = h_hdr[0], nb_meshes = h_hdr[1];
+    const bool by_rank = h_hdr[2] != 0;
     if (n == 0 || nb_meshes == 0) return rtr_set_error(ctx, RTR_E_COMM, "bvh_broadcast: empty header from root");
     const size_t nc = 2 * (size_t)n - 1;
 
@@ -157,22 +159,33 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
             b->meshes_own_cap = nb_meshes;
         }
         if (!b->tparams) RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->tparams), sizeof(TraceParams)));
+        if (b->wtri_own_cap < n) {
+            RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (b->wtri_own) cudaFree(b->wtri_own);
+            b->wtri_own = nullptr; b->wtri_own_cap = 0;
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->wtri_own), (size_t)n * 3 * sizeof(float4)));
+            b->wtri_own_cap = n;
+        }
     }
     void* nodes = is_root ? const_cast<rtr_node*>(b->flat_view) : b->flat_recv;
     void* tris = is_root ? const_cast<rtr_triangle*>(b->tris) : b->tris_own;
     void* meshes = is_root ? const_cast<rtr_mesh*>(b->meshes) : b->meshes_own;
+    void* wtri = is_root ? const_cast<float4*>(b->wtri_view) : b->wtri_own;
 
-    // 3. one grouped broadcast: flat nodes (48 B*(2n-1)) + triangles (64 B*n) + meshes + trace constants
+    // 3. one grouped broadcast: flat nodes (48 B*(2n-1)) + triangles (64 B*n) + meshes + world-space
+    //    triangle cache (48 B*n) + trace constants
     RTR_NCCL(ctx, g_nccl.GroupStart());
     RTR_NCCL(ctx, g_nccl.Broadcast(nodes, nodes, nc * sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
     RTR_NCCL(ctx, g_nccl.Broadcast(tris, tris, (size_t)n * sizeof(rtr_triangle), kNcclUint8, root, comm, ctx->stream));
     RTR_NCCL(ctx, g_nccl.Broadcast(meshes, meshes, (size_t)nb_meshes * sizeof(rtr_mesh), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(wtri, wtri, (size_t)n * 3 * sizeof(float4), kNcclUint8, root, comm, ctx->stream));
     RTR_NCCL(ctx, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
     RTR_NCCL(ctx, g_nccl.GroupEnd());
 
     if (!is_root) {
         b->n = n; b->array_len = n; b->nb_meshes = nb_meshes;
         b->tris = b->tris_own; b->meshes = b->meshes_own; b->flat_view = b->flat_recv;
+        b->wtri_view = b->wtri_own; b->wtri_by_rank = by_rank;
         b->adopted = true;
         b->built = true;
     }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256)
 leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
                  const uint32_t* __restrict__ tri_idx, uint32_t n,
                  float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t* __restrict__ cin,
-                 TraceParams* __restrict__ tparams) {
+                 float4* __restrict__ wtri, TraceParams* __restrict__ tparams) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float e2 = 0.f;
     if (i < n) {
@@ -118,6 +118,10 @@ leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restri
         node_lo[i] = make_float4(mnx, mny, mnz, mxx);
         node_hi[i] = make_float4(mxy, mxz, __uint_as_float(ti), __uint_as_float(RTR_NONE));
         cin[i] = i;
+        // world-space vertices for the traversal kernels (the M*P of raytracer.glsl:105-107), leaf order
+        wtri[3 * (size_t)i + 0] = make_float4(a.x, a.y, a.z, b.x);
+        wtri[3 * (size_t)i + 1] = make_float4(b.y, b.z, c.x, c.y);
+        wtri[3 * (size_t)i + 2] = make_float4(c.z, 0.f, 0.f, 0.f);
         // longest squared edge (conservative traversal pruning bound, see trace.cu)
         const float abx = b.x - a.x, aby = b.y - a.y, abz = b.z - a.z;
         const float acx = c.x - a.x, acy = c.y - a.y, acz = c.z - a.z;
@@ -130,15 +134,19 @@ leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restri
     if (lane_id() == 0 && e2 > 0.f) atomicMax(&tparams->emax2_ordered, float_to_ordered(e2));
 }
 
+// adopted node arrays: same cache, indexed by triangle id
 __global__ void __launch_bounds__(256)
 edge_bound_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes, uint32_t n,
-                  TraceParams* __restrict__ tparams) {
+                  float4* __restrict__ wtri, TraceParams* __restrict__ tparams) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float e2 = 0.f;
     if (i < n) {
         const TriRec t = load_tri(tris, i);
         const Mat3x4 M = load_model(meshes, t.model_id);
         const float3 a = mat_mul_point(M, t.p0), b = mat_mul_point(M, t.p1), c = mat_mul_point(M, t.p2);
+        wtri[3 * (size_t)i + 0] = make_float4(a.x, a.y, a.z, b.x);
+        wtri[3 * (size_t)i + 1] = make_float4(b.y, b.z, c.x, c.y);
+        wtri[3 * (size_t)i + 2] = make_float4(c.z, 0.f, 0.f, 0.f);
         const float abx = b.x - a.x, aby = b.y - a.y, abz = b.z - a.z;
         const float acx = c.x - a.x, acy = c.y - a.y, acz = c.z - a.z;
         const float bcx = c.x - b.x, bcy = c.y - b.y, bcz = c.z - b.z;
@@ -374,12 +382,14 @@ ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
 // ---------------------------------------------------------------------------------------
 // flatten: scene.cpp:189-208 as a top-down pass over creation levels (iterations, last first)
 // ---------------------------------------------------------------------------------------
+// `slot` goes to the third padding word (bytes 44-47, unspecified in the reference layout): leaves keep
+// their cluster id = wtri slot there for the traversal kernels
 __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t pos, const float4 lo, const float4 hi,
-                                           uint32_t tri, uint32_t left, uint32_t right) {
+                                           uint32_t tri, uint32_t left, uint32_t right, uint32_t slot = 0u) {
     uint4* dst = reinterpret_cast<uint4*>(flat + pos);
     dst[0] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), 0u);
     dst[1] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.x), __float_as_uint(hi.y), 0u);
-    dst[2] = make_uint4(tri, left, right, 0u);
+    dst[2] = make_uint4(tri, left, right, slot);
 }
 
 __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
@@ -394,13 +404,13 @@ __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
     store_node(flat, p, lo, hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
     if (L < n_leaves) {
         const float4 llo = node_lo[L], lhi = node_hi[L];
-        store_node(flat, pos_l, llo, lhi, __float_as_uint(lhi.z), 0u, 0u);
+        store_node(flat, pos_l, llo, lhi, __float_as_uint(lhi.z), 0u, 0u, L);
     } else {
         ipos[L - n_leaves] = pos_l;
     }
     if (R < n_leaves) {
         const float4 rlo = node_lo[R], rhi = node_hi[R];
-        store_node(flat, pos_r, rlo, rhi, __float_as_uint(rhi.z), 0u, 0u);
+        store_node(flat, pos_r, rlo, rhi, __float_as_uint(rhi.z), 0u, 0u, R);
     } else {
         ipos[R - n_leaves] = pos_r;
     }
@@ -429,7 +439,7 @@ flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_h
 
 __global__ void flatten_single_leaf_kernel(const float4* node_lo, const float4* node_hi, rtr_node* flat) {
     const float4 lo = node_lo[0], hi = node_hi[0];
-    store_node(flat, 0, lo, hi, __float_as_uint(hi.z), 0u, 0u);
+    store_node(flat, 0, lo, hi, __float_as_uint(hi.z), 0u, 0u, 0u);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -459,10 +469,19 @@ export_clusters_kernel(uint32_t n_leaves, const float4* __restrict__ node_lo, co
 int rtr_bvh_compute_trace_params(rtr_bvh* b) {
     rtr_ctx* ctx = b->ctx;
     RTR_CUDA(ctx, cudaMemsetAsync(b->tparams, 0, sizeof(TraceParams), ctx->stream));
+    if (b->wtri_own_cap < b->n) {
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (b->wtri_own) cudaFree(b->wtri_own);
+        b->wtri_own = nullptr; b->wtri_own_cap = 0;
+        RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->wtri_own), (size_t)b->n * 3 * sizeof(float4)));
+        b->wtri_own_cap = b->n;
+    }
     if (b->n) {
-        edge_bound_kernel<<<(b->n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->n, b->tparams);
+        edge_bound_kernel<<<(b->n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->n, b->wtri_own, b->tparams);
         RTR_LAUNCH_CHECK(ctx);
     }
+    b->wtri_view = b->wtri_own;
+    b->wtri_by_rank = false;
     return RTR_OK;
 }
 
@@ -490,7 +509,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     RTR_CUDA(ctx, cudaMemsetAsync(b->tparams, 0, sizeof(TraceParams), ctx->stream));
     RTR_PROF(ctx, "leaf_init_kernel");
     leaf_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->tri_idx, n, b->node_lo,
-                                                               b->node_hi, b->cin, b->tparams);
+                                                               b->node_hi, b->cin, b->wtri, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
     ploc_state_init_kernel<<<1, 1, 0, ctx->stream>>>(b->state, n, b->iter_first_id);
     RTR_LAUNCH_CHECK(ctx);
@@ -580,6 +599,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     }
     RTR_CHECK(record(b, 5));
     b->flat_view = b->flat;
+    b->wtri_view = b->wtri;
+    b->wtri_by_rank = true;
     b->built = true;
     return RTR_OK;
 }

@@ -10,11 +10,20 @@
 // Two visiting orders produce the same records:
 //   RTR_TRACE_REFERENCE_ORDER  exactly the shader's loop: pop, box test, leaf -> triangle test,
 //                              else push Left then Right; no pruning.
-//   default                    same loop, but a node is skipped when its slab entry distance is
-//                              beyond the closest hit so far by more than a conservative margin
-//                              derived from the shader's own |a| >= 1e-4 acceptance test
-//                              (DESIGN.md "pruning bound"); skipped subtrees cannot contain a hit
-//                              the shader would have preferred.
+//   default                    front-to-back: at an inner node both child boxes are tested (the same
+//                              slab tests the shader performs when it pops them), the nearer child is
+//                              entered first and the farther one is stacked with its entry distance;
+//                              a node is skipped when that distance is beyond the closest hit so far
+//                              by more than a conservative margin derived from the shader's own
+//                              |a| >= 1e-4 acceptance test (DESIGN.md "pruning bound"), so skipped
+//                              subtrees cannot contain a hit the shader would have preferred.  The
+//                              shader keeps the FIRST of several equal-t hits it meets and meets leaves
+//                              in descending flat index (right child first), so here an equal-t hit
+//                              replaces the current one iff its leaf index is larger.
+//
+// Triangles are read from the world-space cache the build writes beside the leaves (wtri, 48 B per
+// triangle in leaf = Morton order; the leaf's slot is kept in the node's third padding word), i.e. the
+// M*P products the shader recomputes at every test (:105-107), evaluated once with the same fp32 ops.
 #include "bvh.cuh"
 
 namespace {
@@ -31,6 +40,19 @@ struct Ray {
 struct Hit {
     float b0, b1, b2, t;
     uint32_t did_hit, tri;
+    uint32_t slot;  // wtri slot of the triangle (not part of the record)
+};
+__device__ __forceinline__ Hit no_hit() {
+    Hit h;
+    h.b0 = h.b1 = h.b2 = h.t = 0.f; h.did_hit = 0u; h.tri = 0u; h.slot = 0u;
+    return h;
+}
+
+// where the traversal finds its data
+struct Accel {
+    const rtr_node* __restrict__ nodes;
+    const float4* __restrict__ wtri;
+    uint32_t by_rank;  // 1: wtri slot = leaf's third padding word (built here); 0: slot = triangle id (adopted nodes)
 };
 
 __device__ __forceinline__ Ray make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
@@ -78,23 +100,23 @@ __device__ __forceinline__ Ray camera_ray(const rtr_camera& cam, uint32_t x, uin
     return make_ray(cam.eye[0], cam.eye[1], cam.eye[2], __fdiv_rn(d0, len), __fdiv_rn(d1, len), __fdiv_rn(d2, len));
 }
 
-// world-space vertices in SHADER naming (Q8): shader _P1 = host _P2, shader _P2 = host _P1
+// world-space vertices in SHADER naming (Q8): shader _P1 = host _P2, shader _P2 = host _P1.
+// wtri slot = 3 float4: (P0.xyz, P1.x) (P1.yz, P2.xy) (P2.z, -, -, -), host naming, world space.
 struct TriWorld { float3 p0, p1, p2; };
-__device__ __forceinline__ TriWorld shader_vertices(const rtr_triangle* __restrict__ tris,
-                                                    const rtr_mesh* __restrict__ meshes, uint32_t tri) {
-    const TriRec t = load_tri(tris, tri);
-    const Mat3x4 M = load_model(meshes, t.model_id);
+__device__ __forceinline__ TriWorld shader_vertices(const float4* __restrict__ wtri, uint32_t slot) {
+    const float4* p = wtri + (size_t)slot * 3;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     TriWorld w;
-    w.p0 = mat_mul_point(M, t.p0);
-    w.p1 = mat_mul_point(M, t.p2);
-    w.p2 = mat_mul_point(M, t.p1);
+    w.p0 = make_float3(a.x, a.y, a.z);
+    w.p1 = make_float3(b.z, b.w, c.x);
+    w.p2 = make_float3(a.w, b.x, b.y);
     return w;
 }
 
 // raytracer.glsl:102-147
-__device__ __forceinline__ bool ray_triangle(const Ray& r, const rtr_triangle* __restrict__ tris,
-                                             const rtr_mesh* __restrict__ meshes, uint32_t tri, Hit& hit) {
-    const TriWorld w = shader_vertices(tris, meshes, tri);
+__device__ __forceinline__ bool ray_triangle(const Ray& r, const float4* __restrict__ wtri, uint32_t slot,
+                                             uint32_t tri, Hit& hit) {
+    const TriWorld w = shader_vertices(wtri, slot);
     const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
     const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
     float nx, ny, nz;
@@ -115,7 +137,7 @@ __device__ __forceinline__ bool ray_triangle(const Ray& r, const rtr_triangle* _
     if (bx < 0.f || by < 0.f || bz < 0.f) return false;
     const float t = dot3(e1x, e1y, e1z, rx, ry, rz);
     if (t < 0.f) return false;
-    hit.b0 = bx; hit.b1 = by; hit.b2 = bz; hit.t = t; hit.did_hit = 1u; hit.tri = tri;
+    hit.b0 = bx; hit.b1 = by; hit.b2 = bz; hit.t = t; hit.did_hit = 1u; hit.tri = tri; hit.slot = slot;
     return true;
 }
 
@@ -138,7 +160,7 @@ __device__ __forceinline__ bool intersect_box(const Ray& r, const float4 lo, con
 struct NodeRec {
     float4 lo;  // min.xyz, pad
     float4 hi;  // max.xyz, pad
-    uint32_t tri, left, right;
+    uint4 links;  // triangle id, left, right, wtri slot (third padding word)
 };
 __device__ __forceinline__ NodeRec load_node(const rtr_node* __restrict__ nodes, uint32_t idx) {
     const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
@@ -146,14 +168,19 @@ __device__ __forceinline__ NodeRec load_node(const rtr_node* __restrict__ nodes,
     NodeRec n;
     n.lo = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), 0.f);
     n.hi = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), 0.f);
-    n.tri = c.x; n.left = c.y; n.right = c.z;
+    n.links = c;
     return n;
 }
+__device__ __forceinline__ uint4 load_links(const rtr_node* __restrict__ nodes, uint32_t idx) {
+    return __ldg(reinterpret_cast<const uint4*>(nodes + idx) + 2);
+}
+__device__ __forceinline__ bool is_leaf(const uint4 links) { return links.y == 0u && links.z == 0u; }
+__device__ __forceinline__ uint32_t slot_of(const Accel& A, const uint4 links) { return A.by_rank ? links.w : links.x; }
 
 // Conservative pruning bound.  A triangle accepted by ray_triangle has |a| >= 1e-4, which bounds the
 // rounding error of its computed t by 40*u*(|e0||e1|/1e-4)*(t_true + Emax); with
 // K = 64*u*Emax^2/1e-4 no triangle inside a box whose computed entry distance exceeds
-// (t_best + K*Emax)*(1 + 2K) can produce a computed t below t_best.  K >= 0.25 disables pruning.
+// (t_best + K*Emax)*(1 + 2K) can produce a computed t at or below t_best.  K >= 0.25 disables pruning.
 struct PruneBound {
     float k, kemax;
     bool enabled;
@@ -172,64 +199,123 @@ __device__ __forceinline__ float prune_limit(const PruneBound& pb, float t_best)
     return (t_best + pb.kemax) * (1.f + 2.f * pb.k);
 }
 
-template <bool PRUNE>
-__device__ __forceinline__ Hit closest_hit(const Ray& r, const rtr_node* __restrict__ nodes,
-                                           const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
-                                           const PruneBound& pb, uint32_t* overflow) {
-    Hit best;
-    best.b0 = best.b1 = best.b2 = best.t = 0.f; best.did_hit = 0u; best.tri = 0u;
-    float limit = INFINITY;
+// ---- the shader's own loop (raytracer.glsl:246-295): RTR_TRACE_REFERENCE_ORDER ----
+__device__ __forceinline__ Hit closest_hit_reference(const Ray& r, const Accel& A, uint32_t* overflow) {
+    Hit best = no_hit();
     uint32_t stack[kStack];
     int sp = 0;
     stack[sp++] = 0u;
     while (sp > 0) {
         const uint32_t idx = stack[--sp];
-        const NodeRec n = load_node(nodes, idx);
+        const NodeRec n = load_node(A.nodes, idx);
         float t_entry;
         if (!intersect_box(r, n.lo, n.hi, t_entry)) continue;
-        if (PRUNE && t_entry > limit) continue;
-        if (n.left == 0u && n.right == 0u) {
+        if (is_leaf(n.links)) {
             Hit h;
-            if (ray_triangle(r, tris, meshes, n.tri, h)) {
-                if (best.did_hit == 0u || h.t < best.t) {
-                    best = h;
-                    if (PRUNE && pb.enabled) limit = prune_limit(pb, h.t);
-                }
+            if (ray_triangle(r, A.wtri, slot_of(A, n.links), n.links.x, h)) {
+                if (best.did_hit == 0u || h.t < best.t) best = h;
             }
         } else if (sp + 2 <= kStack) {
-            stack[sp++] = n.left;
-            stack[sp++] = n.right;
-        } else if (overflow) {
+            stack[sp++] = n.links.y;
+            stack[sp++] = n.links.z;
+        } else {
             *overflow = 1u;
         }
     }
     return best;
 }
-
-// any-hit: 1 iff some reachable triangle passes ray_triangle with t < t_max (order independent)
-template <bool PRUNE>
-__device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const rtr_node* __restrict__ nodes,
-                                        const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
-                                        const PruneBound& pb) {
-    const float limit = (PRUNE && pb.enabled) ? prune_limit(pb, t_max) : INFINITY;
+__device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, const Accel& A) {
     uint32_t stack[kStack];
     int sp = 0;
     stack[sp++] = 0u;
     while (sp > 0) {
         const uint32_t idx = stack[--sp];
-        const NodeRec n = load_node(nodes, idx);
+        const NodeRec n = load_node(A.nodes, idx);
         float t_entry;
         if (!intersect_box(r, n.lo, n.hi, t_entry)) continue;
-        if (PRUNE && t_entry > limit) continue;
-        if (n.left == 0u && n.right == 0u) {
+        if (is_leaf(n.links)) {
             Hit h;
-            if (ray_triangle(r, tris, meshes, n.tri, h) && h.t < t_max) return true;
+            if (ray_triangle(r, A.wtri, slot_of(A, n.links), n.links.x, h) && h.t < t_max) return true;
         } else if (sp + 2 <= kStack) {
-            stack[sp++] = n.left;
-            stack[sp++] = n.right;
+            stack[sp++] = n.links.y;
+            stack[sp++] = n.links.z;
         }
     }
     return false;
+}
+
+// ---- front-to-back traversal with conservative pruning; same records as the loop above ----
+// ANY: return as soon as a triangle passes with t < t_max (did_hit only).
+template <bool ANY>
+__device__ __forceinline__ Hit trace_ordered(const Ray& r, float t_max, const Accel& A, const PruneBound& pb,
+                                             uint32_t* overflow) {
+    Hit best = no_hit();
+    uint32_t best_node = 0u;
+    float limit = (ANY && pb.enabled) ? prune_limit(pb, t_max) : INFINITY;
+    uint32_t cur = 0u;
+    uint4 links;
+    {
+        const NodeRec root = load_node(A.nodes, 0u);
+        float te;
+        if (!intersect_box(r, root.lo, root.hi, te) || te > limit) return best;
+        links = root.links;
+    }
+    uint2 stack[kStack];  // (node, bits of its entry distance); both boxes of a pair were already tested
+    int sp = 0;
+    while (true) {
+        if (is_leaf(links)) {
+            Hit h;
+            if (ray_triangle(r, A.wtri, slot_of(A, links), links.x, h)) {
+                if (ANY) {
+                    if (h.t < t_max) return h;
+                } else if (best.did_hit == 0u || h.t < best.t || (h.t == best.t && cur > best_node)) {
+                    best = h; best_node = cur;
+                    if (pb.enabled) limit = prune_limit(pb, h.t);
+                }
+            }
+        } else {
+            const uint32_t li = links.y, ri = links.z;
+            const NodeRec L = load_node(A.nodes, li), R = load_node(A.nodes, ri);
+            float tl, tr;
+            const bool hl = intersect_box(r, L.lo, L.hi, tl) && !(tl > limit);
+            const bool hr = intersect_box(r, R.lo, R.hi, tr) && !(tr > limit);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                if (sp < kStack) stack[sp++] = left_first ? make_uint2(ri, __float_as_uint(tr)) : make_uint2(li, __float_as_uint(tl));
+                else *overflow = 1u;
+                cur = left_first ? li : ri;
+                links = left_first ? L.links : R.links;
+                continue;
+            }
+            if (hl) { cur = li; links = L.links; continue; }
+            if (hr) { cur = ri; links = R.links; continue; }
+        }
+        bool found = false;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) > limit) continue;
+            cur = e.x;
+            links = load_links(A.nodes, cur);
+            found = true;
+            break;
+        }
+        if (!found) break;
+    }
+    return best;
+}
+
+template <bool PRUNE>
+__device__ __forceinline__ Hit closest_hit(const Ray& r, const Accel& A, const PruneBound& pb, uint32_t* overflow) {
+    if (PRUNE) return trace_ordered<false>(r, INFINITY, A, pb, overflow);
+    return closest_hit_reference(r, A, overflow);
+}
+template <bool PRUNE>
+__device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const Accel& A, const PruneBound& pb) {
+    if (PRUNE) {
+        uint32_t ovf = 0u;
+        return trace_ordered<true>(r, t_max, A, pb, &ovf).did_hit != 0u;
+    }
+    return any_hit_reference(r, t_max, A);
 }
 
 __device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, const Hit& h) {
@@ -241,10 +327,9 @@ __device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, c
 }
 
 // hit frame shared by both secondary rays: unit front normal and offset origin h + n*1e-3
-__device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const rtr_triangle* __restrict__ tris,
-                                          const rtr_mesh* __restrict__ meshes, float& nx, float& ny, float& nz,
+__device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const Accel& A, float& nx, float& ny, float& nz,
                                           float& ox, float& oy, float& oz) {
-    const TriWorld w = shader_vertices(tris, meshes, h.tri);
+    const TriWorld w = shader_vertices(A.wtri, h.slot);
     const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
     const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
     cross3(e1x, e1y, e1z, e0x, e0y, e0z, nx, ny, nz);
@@ -284,20 +369,18 @@ __device__ __forceinline__ bool pixel_of_thread(uint32_t width, uint32_t rows, u
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
-trace_primary_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
-                     const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp, const rtr_camera cam,
+trace_primary_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
                      uint32_t width, uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t rows,
                      rtr_hit* __restrict__ hits) {
     uint32_t x, yl;
     if (!pixel_of_thread(width, rows, x, yl)) return;
     const uint32_t y = row0 + yl;
-    Hit h;
-    h.b0 = h.b1 = h.b2 = h.t = 0.f; h.did_hit = 0u; h.tri = 0u;
+    Hit h = no_hit();
     if (x < denom_w && y < denom_h) {
         const PruneBound pb = make_prune_bound(tp, PRUNE);
         const Ray r = camera_ray(cam, x, y, denom_w, denom_h);
         uint32_t ovf = 0;
-        h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+        h = closest_hit<PRUNE>(r, A, pb, &ovf);
         if (ovf) atomicAdd(&tp->stack_overflows, 1u);
     }
     store_hit(hits, (size_t)yl * width + x, h);
@@ -305,8 +388,7 @@ trace_primary_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __r
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
-trace_rays_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
-                  const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp,
+trace_rays_kernel(const Accel A, TraceParams* __restrict__ tp,
                   const rtr_ray* __restrict__ rays, uint64_t n_rays, int want_any, const float* __restrict__ t_max,
                   rtr_hit* __restrict__ hits) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,14 +397,13 @@ trace_rays_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __rest
     const float4 d = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
     const Ray r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
     const PruneBound pb = make_prune_bound(tp, PRUNE);
-    Hit h;
-    h.b0 = h.b1 = h.b2 = h.t = 0.f; h.did_hit = 0u; h.tri = 0u;
+    Hit h = no_hit();
     if (want_any) {
         const float tm = t_max ? t_max[i] : INFINITY;
-        h.did_hit = any_hit<PRUNE>(r, tm, nodes, tris, meshes, pb) ? 1u : 0u;
+        h.did_hit = any_hit<PRUNE>(r, tm, A, pb) ? 1u : 0u;
     } else {
         uint32_t ovf = 0;
-        h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+        h = closest_hit<PRUNE>(r, A, pb, &ovf);
         if (ovf) atomicAdd(&tp->stack_overflows, 1u);
     }
     store_hit(hits, i, h);
@@ -331,8 +412,7 @@ trace_rays_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __rest
 // Multi-bounce frame, one thread per pixel (definition: oracle/rtr_oracle.c orc_render).
 template <bool PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
-render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict__ tris,
-              const rtr_mesh* __restrict__ meshes, TraceParams* __restrict__ tp, const rtr_camera cam,
+render_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
               uint32_t width, uint32_t denom_w, uint32_t denom_h, const RowMap rm,
               uint32_t bounces, int shadow, float lx, float ly, float lz,
               float4* __restrict__ rgba, rtr_hit* __restrict__ hits, unsigned long long* __restrict__ rays_traced) {
@@ -341,24 +421,23 @@ render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict
     uint32_t traced = 0;
     if (live) {
         float L = 0.f, wgt = 1.f;
-        Hit first;
-        first.b0 = first.b1 = first.b2 = first.t = 0.f; first.did_hit = 0u; first.tri = 0u;
+        Hit first = no_hit();
         if (x < denom_w && y < denom_h) {
             const PruneBound pb = make_prune_bound(tp, PRUNE);
             Ray r = camera_ray(cam, x, y, denom_w, denom_h);
+            uint32_t ovf = 0;
             for (uint32_t k = 0; k <= bounces; ++k) {
-                uint32_t ovf = 0;
-                const Hit h = closest_hit<PRUNE>(r, nodes, tris, meshes, pb, &ovf);
+                const Hit h = closest_hit<PRUNE>(r, A, pb, &ovf);
                 ++traced;
                 if (k == 0) first = h;
                 if (!h.did_hit) break;
                 float nx, ny, nz, ox, oy, oz, c;
-                hit_frame(r, h, tris, meshes, nx, ny, nz, ox, oy, oz);
+                hit_frame(r, h, A, nx, ny, nz, ox, oy, oz);
                 if (shadow) {
                     const float sx = __fsub_rn(lx, ox), sy = __fsub_rn(ly, oy), sz = __fsub_rn(lz, oz);
                     const float len = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
                     const Ray sr = make_ray(ox, oy, oz, __fdiv_rn(sx, len), __fdiv_rn(sy, len), __fdiv_rn(sz, len));
-                    const bool occ = any_hit<PRUNE>(sr, len, nodes, tris, meshes, pb);
+                    const bool occ = any_hit<PRUNE>(sr, len, A, pb);
                     ++traced;
                     const float ndl = dot3(nx, ny, nz, sr.dx, sr.dy, sr.dz);
                     c = occ ? 0.f : fmaxf(0.f, ndl);
@@ -376,6 +455,7 @@ render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict
                     r = make_ray(ox, oy, oz, rx, ry, rz);
                 }
             }
+            if (ovf) atomicAdd(&tp->stack_overflows, 1u);
         }
         const size_t o = (size_t)out_row * width + x;
         if (rgba) rgba[o] = make_float4(L, L, L, 1.f);
@@ -391,6 +471,12 @@ render_kernel(const rtr_node* __restrict__ nodes, const rtr_triangle* __restrict
 inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
     const uint64_t warps = (uint64_t)((width + 7) / 8) * ((rows + 3) / 4);
     return (uint32_t)((warps * 32 + kTraceBlock - 1) / kTraceBlock);
+}
+
+inline Accel accel_of(const rtr_bvh* b) {
+    Accel A;
+    A.nodes = b->flat_view; A.wtri = b->wtri_view; A.by_rank = b->wtri_by_rank ? 1u : 0u;
+    return A;
 }
 
 }  // namespace
@@ -410,13 +496,14 @@ int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& c
                              width, height, row0, row1, denom_w, denom_h);
     const uint32_t rows = row1 - row0;
     const uint32_t grid = pixel_grid(width, rows);
+    const Accel A = accel_of(b);
     RTR_PROF(ctx, "trace_primary_kernel");
     if (flags & RTR_TRACE_REFERENCE_ORDER)
-        trace_primary_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, cam,
-                                                                           width, denom_w, denom_h, row0, rows, hits);
+        trace_primary_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, cam, width, denom_w, denom_h, row0,
+                                                                           rows, hits);
     else
-        trace_primary_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, cam,
-                                                                          width, denom_w, denom_h, row0, rows, hits);
+        trace_primary_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, cam, width, denom_w, denom_h, row0,
+                                                                          rows, hits);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
 }
@@ -427,12 +514,12 @@ int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, u
     const uint64_t grid64 = (n_rays + kTraceBlock - 1) / kTraceBlock;
     if (grid64 > 0x7FFFFFFFull) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_rays: too many rays");
     const uint32_t grid = (uint32_t)grid64;
+    const Accel A = accel_of(b);
+    RTR_PROF(ctx, "trace_rays_kernel");
     if (flags & RTR_TRACE_REFERENCE_ORDER)
-        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, rays,
-                                                                        n_rays, any, t_max, hits);
+        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, rays, n_rays, any, t_max, hits);
     else
-        trace_rays_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(b->flat_view, b->tris, b->meshes, b->tparams, rays,
-                                                                       n_rays, any, t_max, hits);
+        trace_rays_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, rays, n_rays, any, t_max, hits);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
 }
@@ -458,16 +545,17 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
     }
     const uint32_t rows = rm.rows;
     const uint32_t grid = pixel_grid(width, rows);
+    const Accel A = accel_of(b);
     RTR_PROF(ctx, "render_kernel");
     const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
     if (flags & RTR_TRACE_REFERENCE_ORDER)
         render_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly,
-            lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+            A, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
+            reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
     else
         render_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            b->flat_view, b->tris, b->meshes, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly,
-            lz, reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+            A, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
+            reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
 }
