@@ -55,10 +55,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     procs = []
     objs = []
+    tuning = os.environ.get("RTR_NVCC_EXTRA", "").split()  # e.g. "-DRTR_LEAF_BATCH=8" for parameter sweeps
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + tuning + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
     failed = False
     for src, p in procs:

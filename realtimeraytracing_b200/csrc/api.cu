@@ -62,7 +62,7 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 void bvh_free_arrays(rtr_bvh* b) {
     void* ptrs[] = {b->codes, b->tri_idx, b->node_lo, b->node_hi, b->isize, b->ipos, b->cin, b->cout, b->tile_status,
                     b->state, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
-                    b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own};
+                    b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     b->codes = b->tri_idx = b->isize = b->ipos = b->cin = b->cout = nullptr;
@@ -73,6 +73,7 @@ void bvh_free_arrays(rtr_bvh* b) {
     b->tris_own = nullptr; b->meshes_own = nullptr; b->tris_own_cap = b->meshes_own_cap = 0;
     b->flat_recv = nullptr; b->recv_cap = 0;
     b->wtri = nullptr; b->wtri_own = nullptr; b->wtri_own_cap = 0; b->wtri_view = nullptr;
+    b->pairs = nullptr; b->pairs_own = nullptr; b->pairs_own_cap = 0; b->pairs_view = nullptr;
     b->capacity = 0;
 }
 
@@ -106,6 +107,7 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     RTR_CHECK(dev_alloc(ctx, &b->flat, nc));
     RTR_CHECK(dev_alloc(ctx, &b->tparams, 1));
     RTR_CHECK(dev_alloc(ctx, &b->wtri, 3 * cap));
+    RTR_CHECK(dev_alloc(ctx, &b->pairs, 4 * nc));
     b->capacity = n;
     return RTR_OK;
 }

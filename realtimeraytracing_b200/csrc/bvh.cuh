@@ -14,7 +14,8 @@ struct PlocState {
 struct TraceParams {
     uint32_t emax2_ordered;  // max squared edge length over all triangles, ordered-uint encoded
     uint32_t stack_overflows;
-    uint32_t pad0, pad1;
+    uint32_t job_counter;    // next 32-job tile of the persistent traversal launch in flight
+    uint32_t pad1;
 };
 
 constexpr uint32_t kMaxPlocIterations = 1u << 16;
@@ -64,6 +65,15 @@ struct rtr_bvh {
     size_t wtri_own_cap = 0;            // triangles wtri_own was sized for
     const float4* wtri_view = nullptr;  // what traversal reads
     bool wtri_by_rank = true;
+    // child-pair records read by the default traversal: one 64-byte record per inner node of the flat array
+    // (indexed by flat index; leaf entries unused) = both children's boxes + their links, copied bit for
+    // bit from the flat nodes by pack_pairs_kernel:
+    //   (L.min.xyz, L.max.x) (L.max.yz, R.min.xy) (R.min.z, R.max.xyz) (L.word, R.word, L.aux, R.aux)
+    //   word = child flat index, or 0x80000000 | index for a leaf whose aux is its wtri slot
+    uint4* pairs = nullptr;        // [4*(2cap-1)]
+    uint4* pairs_own = nullptr;    // adopted / received BVHs
+    size_t pairs_own_cap = 0;      // triangles pairs_own was sized for
+    const uint4* pairs_view = nullptr;
 
     // host mirrors of the last build
     uint32_t iterations = 0;
@@ -78,6 +88,8 @@ int rtr_bvh_run_build(rtr_bvh* b);
 int rtr_bvh_export_clusters(rtr_bvh* b, rtr_node* clusters_dev, uint32_t* parent_dev, uint32_t* left_dev,
                             uint32_t* right_dev, uint8_t* is_leaf_dev);
 int rtr_bvh_compute_trace_params(rtr_bvh* b);
+// (re)derive the child-pair records of an adopted / received flat array (flat_view, wtri_by_rank must be set)
+int rtr_bvh_pack_pairs_own(rtr_bvh* b);
 // trace.cu
 int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
                              uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t flags,

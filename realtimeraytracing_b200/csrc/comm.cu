@@ -187,6 +187,7 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
         b->tris = b->tris_own; b->meshes = b->meshes_own; b->flat_view = b->flat_recv;
         b->wtri_view = b->wtri_own; b->wtri_by_rank = by_rank;
         b->adopted = true;
+        RTR_CHECK(rtr_bvh_pack_pairs_own(b));  // derived locally: cheaper than 64 B*(2n-1) more on the wire
         b->built = true;
     }
     return RTR_OK;

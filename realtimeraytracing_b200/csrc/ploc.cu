@@ -442,6 +442,26 @@ __global__ void flatten_single_leaf_kernel(const float4* node_lo, const float4* 
     store_node(flat, 0, lo, hi, __float_as_uint(hi.z), 0u, 0u, 0u);
 }
 
+// child-pair records for the traversal kernels (layout in bvh.cuh): pure repacking of the flat array
+__global__ void __launch_bounds__(256)
+pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t by_rank, uint4* __restrict__ pairs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb_nodes) return;
+    const uint4 links = __ldg(reinterpret_cast<const uint4*>(flat + i) + 2);
+    if (links.y == 0u && links.z == 0u) return;  // leaf: no record
+    const uint4* l = reinterpret_cast<const uint4*>(flat + links.y);
+    const uint4* r = reinterpret_cast<const uint4*>(flat + links.z);
+    const uint4 l0 = __ldg(l), l1 = __ldg(l + 1), l2 = __ldg(l + 2);
+    const uint4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+    const bool lleaf = l2.y == 0u && l2.z == 0u, rleaf = r2.y == 0u && r2.z == 0u;
+    uint4* dst = pairs + (size_t)i * 4;
+    dst[0] = make_uint4(l0.x, l0.y, l0.z, l1.x);
+    dst[1] = make_uint4(l1.y, l1.z, r0.x, r0.y);
+    dst[2] = make_uint4(r0.z, r1.x, r1.y, r1.z);
+    dst[3] = make_uint4(lleaf ? (0x80000000u | links.y) : links.y, rleaf ? (0x80000000u | links.z) : links.z,
+                        lleaf ? (by_rank ? l2.w : l2.x) : 0u, rleaf ? (by_rank ? r2.w : r2.x) : 0u);
+}
+
 // ---------------------------------------------------------------------------------------
 // BVH_Params view by cluster id for the accessors / the cr::BVH shim (not on the timed path)
 // ---------------------------------------------------------------------------------------
@@ -482,6 +502,22 @@ int rtr_bvh_compute_trace_params(rtr_bvh* b) {
     }
     b->wtri_view = b->wtri_own;
     b->wtri_by_rank = false;
+    return rtr_bvh_pack_pairs_own(b);
+}
+
+int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
+    rtr_ctx* ctx = b->ctx;
+    if (b->pairs_own_cap < b->n) {
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (b->pairs_own) cudaFree(b->pairs_own);
+        b->pairs_own = nullptr; b->pairs_own_cap = 0;
+        RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->pairs_own), (2 * (size_t)b->n - 1) * 4 * sizeof(uint4)));
+        b->pairs_own_cap = b->n;
+    }
+    const uint32_t nc = 2 * b->n - 1;
+    pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->pairs_own);
+    RTR_LAUNCH_CHECK(ctx);
+    b->pairs_view = b->pairs_own;
     return RTR_OK;
 }
 
@@ -596,6 +632,13 @@ int rtr_bvh_run_build(rtr_bvh* b) {
                 it = lo - 1;
             }
         }
+    }
+    {   // child-pair records of the default traversal (part of the flatten stage time)
+        const uint32_t nc = 2 * n - 1;
+        RTR_PROF(ctx, "pack_pairs_kernel");
+        pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat, nc, 1u, b->pairs);
+        RTR_LAUNCH_CHECK(ctx);
+        b->pairs_view = b->pairs;
     }
     RTR_CHECK(record(b, 5));
     b->flat_view = b->flat;

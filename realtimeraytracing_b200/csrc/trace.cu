@@ -52,6 +52,7 @@ __device__ __forceinline__ Hit no_hit() {
 struct Accel {
     const rtr_node* __restrict__ nodes;
     const float4* __restrict__ wtri;
+    const uint4* __restrict__ pairs;  // child-pair records (bvh.cuh), default traversal only
     uint32_t by_rank;  // 1: wtri slot = leaf's third padding word (built here); 0: slot = triangle id (adopted nodes)
 };
 
@@ -473,10 +474,339 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
     return (uint32_t)((warps * 32 + kTraceBlock - 1) / kTraceBlock);
 }
 
+// ---------------------------------------------------------------------------------------
+// Persistent traversal (default order).  Rays of a soup diverge badly under one-thread-one-pixel:
+// lanes wait for the longest path of their warp and almost every loop iteration executes both the
+// box branch and the triangle branch for a handful of lanes (ncu: 6.5 of 32 threads active per
+// instruction, profiles/r01_ncu_v2_render.txt).  Here
+//   * a launch is one CTA per resident slot; warps pull 32-job tiles (an 8x4 pixel block or 32 rays)
+//     from a global counter and hand them to lanes as they fall idle, a lane keeps its pixel through
+//     all bounces;
+//   * a lane that reaches a leaf parks it (one pending leaf) and keeps walking; the triangle tests of
+//     a warp run together once a lane is blocked on a second leaf or enough leaves are parked;
+//   * finished rays are shaded / replaced in batches.
+// The per-ray arithmetic and the set of leaves a ray meets before its stack runs dry are those of
+// trace_ordered; only the interleaving between lanes changes, so records stay bit-identical.
+// ---------------------------------------------------------------------------------------
+#ifndef RTR_LEAF_BATCH
+#define RTR_LEAF_BATCH 10
+#endif
+#ifndef RTR_FIN_BATCH
+#define RTR_FIN_BATCH 4
+#endif
+#ifndef RTR_TRACE_MIN_CTAS
+#define RTR_TRACE_MIN_CTAS 6
+#endif
+constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
+constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kDry = 0xFFFFFFFFu;  // stack ran dry (also the state of an idle lane)
+#ifndef RTR_SMEM_STACK
+#define RTR_SMEM_STACK 12
+#endif
+constexpr int kSmemStack = RTR_SMEM_STACK;
+
+struct JobDesc {
+    uint32_t kind;   // 0: pixels (render / primary), 1: explicit rays
+    uint32_t total;  // jobs: 32 per 8x4 pixel block, or rays
+    // pixels
+    rtr_camera cam;
+    uint32_t width, denom_w, denom_h;
+    RowMap rm;
+    uint32_t bounces;
+    int shadow;
+    float lx, ly, lz;
+    float4* rgba;
+    rtr_hit* hits;
+    // rays
+    const rtr_ray* rays;
+    const float* t_max;
+    int want_any;
+};
+
+// Lane state is kept small (occupancy hides the node-fetch latency): the node being expanded is the pair
+// (a, b) = (left, right) of an inner node or (kLeafBit | index, wtri slot) of a leaf, stack entries carry
+// the same pair plus the entry distance so a pop needs no global load, and the best hit is (t, leaf index)
+// only -- its barycentrics and triangle id are regenerated by one more ray_triangle when the ray finishes.
+__global__ void __launch_bounds__(kTraceBlock, RTR_TRACE_MIN_CTAS)
+trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDesc jd,
+                        unsigned long long* __restrict__ rays_traced) {
+    // Traversal stack: the top kSmemStack entries of every thread live in shared memory, laid out
+    // [word][depth][thread] so that any mix of depths across a warp is bank-conflict free (bank = lane);
+    // a divergent local-memory access would cost one L1 tag lookup per lane instead.  Deeper entries
+    // spill to local memory.
+    __shared__ uint32_t s_stack[3][kSmemStack][kTraceBlock];
+    __shared__ float s_pb[2];                   // pruning bound constants k, k*Emax (negative k: disabled)
+    __shared__ float s_stash[6][kTraceBlock];   // normal + incoming direction while a shadow ray is out
+    if (threadIdx.x == 0) {
+        const PruneBound pb = make_prune_bound(tp, true);
+        s_pb[0] = pb.enabled ? pb.k : -1.f;
+        s_pb[1] = pb.kemax;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+
+    // warp-uniform
+    uint32_t pool_next = 0u, pool_end = 0u, traced = 0u;
+    bool exhausted = false;
+
+    // lane state
+    uint32_t job = RTR_NONE;
+    Ray r = make_ray(0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
+    float best_t = INFINITY;        // closest hit so far; for an any-hit ray: its t_max
+    uint32_t best_node = RTR_NONE;  // leaf of the best hit
+    float limit = INFINITY;
+    uint32_t a = kDry, b = 0u;      // node being expanded: inner flat index, or kLeafBit | index with b = wtri slot
+    uint32_t pend_node = RTR_NONE, pend_slot = 0u;
+    int sp = 0;
+    uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen
+    float L = 0.f;
+    float stack_t[kStack - kSmemStack];
+    uint32_t stack_a[kStack - kSmemStack], stack_b[kStack - kSmemStack];
+
+    auto limit_of = [&](float t) -> float {
+        const float k = s_pb[0];
+        return (k < 0.f) ? INFINITY : (t + s_pb[1]) * (1.f + 2.f * k);
+    };
+
+    // begin walking ray r: root test (raytracer.glsl:255-262 pops node 0 first)
+    auto start_ray = [&](bool any, float tm) {
+        st = (st & 0xFFFFu) | (any ? 0x10000u : 0u) | (st & 0x20000u);
+        best_t = tm; best_node = RTR_NONE; sp = 0; pend_node = RTR_NONE;
+        limit = any ? limit_of(tm) : INFINITY;
+        const NodeRec root = load_node(A.nodes, 0u);
+        float te;
+        a = kDry;
+        if (intersect_box(r, root.lo, root.hi, te) && !(te > limit)) {
+            if (is_leaf(root.links)) { a = kLeafBit; b = slot_of(A, root.links); }
+            else a = 0u;
+        }
+    };
+    auto pop_next = [&]() {
+        a = kDry;
+        while (sp > 0) {
+            --sp;
+            if (sp < kSmemStack) {
+                if (__uint_as_float(s_stack[0][sp][threadIdx.x]) > limit) continue;
+                a = s_stack[1][sp][threadIdx.x]; b = s_stack[2][sp][threadIdx.x];
+            } else {
+                if (stack_t[sp - kSmemStack] > limit) continue;
+                a = stack_a[sp - kSmemStack]; b = stack_b[sp - kSmemStack];
+            }
+            break;
+        }
+    };
+    auto job_pixel = [&](uint32_t j, uint32_t& x, uint32_t& y, uint32_t& out_row) -> bool {
+        const uint32_t tiles_x = (jd.width + 7u) / 8u;
+        const uint32_t wg = j >> 5, ln = j & 31u;
+        x = (wg % tiles_x) * 8u + (ln & 7u);
+        const uint32_t yl = (wg / tiles_x) * 4u + (ln >> 3);
+        return x < jd.width && yl < jd.rm.rows && map_row(jd.rm, yl, y, out_row);
+    };
+
+    while (true) {
+        // ---- hand jobs to idle lanes ----
+        uint32_t idle = __ballot_sync(0xffffffffu, job == RTR_NONE);
+        while (idle != 0u && !exhausted) {
+            if (pool_next == pool_end) {
+                uint32_t base = 0u;
+                if (lane == 0u) base = atomicAdd(&tp->job_counter, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= jd.total) { exhausted = true; break; }
+                pool_next = base;
+                pool_end = min(base + 32u, jd.total);
+            }
+            const uint32_t avail = pool_end - pool_next;
+            const uint32_t rank = __popc(idle & lanemask_lt());
+            if (job == RTR_NONE && rank < avail) {
+                job = pool_next + rank;
+                st = 0u; L = 0.f;
+                if (jd.kind == 0u) {
+                    uint32_t x, y, out_row;
+                    if (!job_pixel(job, x, y, out_row)) {
+                        job = RTR_NONE;  // padding of the 8x4 block
+                    } else if (x < jd.denom_w && y < jd.denom_h) {
+                        r = camera_ray(jd.cam, x, y, jd.denom_w, jd.denom_h);
+                        start_ray(false, INFINITY);
+                    } else {  // not traced (Q5): zero record, black pixel
+                        const size_t o = (size_t)out_row * jd.width + x;
+                        if (jd.rgba) jd.rgba[o] = make_float4(0.f, 0.f, 0.f, 1.f);
+                        if (jd.hits) store_hit(jd.hits, o, no_hit());
+                        job = RTR_NONE;
+                    }
+                } else {
+                    const float4 o = __ldg(reinterpret_cast<const float4*>(jd.rays) + 2 * (size_t)job);
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(jd.rays) + 2 * (size_t)job + 1);
+                    r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
+                    const bool any = jd.want_any != 0;
+                    start_ray(any, (any && jd.t_max) ? jd.t_max[job] : INFINITY);
+                }
+            }
+            pool_next += min(avail, (uint32_t)__popc(idle));
+            idle = __ballot_sync(0xffffffffu, job == RTR_NONE);
+        }
+        if (idle == 0xffffffffu) break;
+
+        // ---- walk: one step per iteration for every lane that can move (idle lanes keep a == 0) ----
+        while (true) {
+            if (a != kDry) {
+                if (a & kLeafBit) {
+                    if (pend_node == RTR_NONE) {  // park the leaf and keep walking
+                        pend_node = a & ~kLeafBit; pend_slot = b;
+                        pop_next();
+                    }
+                } else {
+                    const uint4* rec = A.pairs + (size_t)a * 4;
+                    const uint4 c0 = __ldg(rec), c1 = __ldg(rec + 1), c2 = __ldg(rec + 2), c3 = __ldg(rec + 3);
+                    const float4 llo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
+                    const float4 lhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
+                    const float4 rlo = make_float4(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x), 0.f);
+                    const float4 rhi = make_float4(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w), 0.f);
+                    float tl, tr;
+                    const bool hl = intersect_box(r, llo, lhi, tl) && !(tl > limit);
+                    const bool hr = intersect_box(r, rlo, rhi, tr) && !(tr > limit);
+                    if (hl && hr) {
+                        const bool left_first = tl <= tr;
+                        const float tf = left_first ? tr : tl;
+                        const uint32_t fa = left_first ? c3.y : c3.x, fb = left_first ? c3.w : c3.z;  // far child -> stack
+                        if (sp < kSmemStack) {
+                            s_stack[0][sp][threadIdx.x] = __float_as_uint(tf); s_stack[1][sp][threadIdx.x] = fa; s_stack[2][sp][threadIdx.x] = fb;
+                            ++sp;
+                        } else if (sp < kStack) {
+                            stack_t[sp - kSmemStack] = tf; stack_a[sp - kSmemStack] = fa; stack_b[sp - kSmemStack] = fb;
+                            ++sp;
+                        } else st |= 0x20000u;
+                        a = left_first ? c3.x : c3.y; b = left_first ? c3.z : c3.w;
+                    } else if (hl) { a = c3.x; b = c3.z; }
+                    else if (hr) { a = c3.y; b = c3.w; }
+                    else pop_next();
+                }
+            }
+            const bool busy = job != RTR_NONE;
+            const bool blocked = a != kDry && (a & kLeafBit) != 0u && pend_node != RTR_NONE;
+            const uint32_t m_blocked = __ballot_sync(0xffffffffu, blocked);
+            const uint32_t m_pend = __ballot_sync(0xffffffffu, pend_node != RTR_NONE);
+            const uint32_t m_walk = __ballot_sync(0xffffffffu, a != kDry);
+            const uint32_t m_dry = __ballot_sync(0xffffffffu, busy && a == kDry);
+            const uint32_t movable = m_walk & ~m_blocked;
+            const bool want_fin = m_dry != 0u && ((uint32_t)__popc(m_dry) >= kFinBatch || (uint32_t)__popc(m_walk) < 16u);
+            if (m_blocked != 0u || (uint32_t)__popc(m_pend) >= kLeafBatch || movable == 0u || (want_fin && (m_dry & m_pend) != 0u)) {
+                // ---- triangle step: every parked leaf of the warp ----
+                if (pend_node != RTR_NONE) {
+                    Hit h;
+                    if (ray_triangle(r, A.wtri, pend_slot, 0u, h)) {
+                        if (st & 0x10000u) {
+                            if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; }
+                        } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
+                            best_t = h.t; best_node = pend_node;
+                            limit = limit_of(h.t);
+                        }
+                    }
+                    pend_node = RTR_NONE;
+                }
+            }
+            if (want_fin || (movable == 0u && m_blocked == 0u)) break;
+        }
+
+        // ---- rays whose stack ran dry: shade, continue the path or retire the job ----
+        const bool fin = job != RTR_NONE && a == kDry && pend_node == RTR_NONE;
+        traced += __popc(__ballot_sync(0xffffffffu, fin));
+        if (fin) {
+            const bool any_mode = (st & 0x10000u) != 0u;
+            // regenerate the record of the best hit (same inputs, same ops => same bits)
+            Hit best = no_hit();
+            if (best_node != RTR_NONE) {
+                if (any_mode) best.did_hit = 1u;
+                else {
+                    const uint4 bl = load_links(A.nodes, best_node);
+                    ray_triangle(r, A.wtri, slot_of(A, bl), bl.x, best);
+                }
+            }
+            if (jd.kind != 0u) {
+                store_hit(jd.hits, job, best);
+                job = RTR_NONE;
+            } else {
+                uint32_t x, y, out_row;
+                job_pixel(job, x, y, out_row);
+                const size_t o = (size_t)out_row * jd.width + x;
+                const uint32_t k = st & 0xFFFFu;
+                bool path_done = false, shade = false;
+                float nx = 0.f, ny = 0.f, nz = 0.f, ox = r.ox, oy = r.oy, oz = r.oz, dx = 0.f, dy = 0.f, dz = 0.f, c = 0.f;
+                if (!any_mode) {
+                    if (k == 0u && jd.hits) store_hit(jd.hits, o, best);
+                    if (!best.did_hit) {
+                        path_done = true;
+                    } else {
+                        hit_frame(r, best, A, nx, ny, nz, ox, oy, oz);
+                        dx = r.dx; dy = r.dy; dz = r.dz;
+                        if (jd.shadow) {
+                            const float sx = __fsub_rn(jd.lx, ox), sy = __fsub_rn(jd.ly, oy), sz = __fsub_rn(jd.lz, oz);
+                            const float len = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
+                            s_stash[0][threadIdx.x] = nx; s_stash[1][threadIdx.x] = ny; s_stash[2][threadIdx.x] = nz;
+                            s_stash[3][threadIdx.x] = dx; s_stash[4][threadIdx.x] = dy; s_stash[5][threadIdx.x] = dz;
+                            r = make_ray(ox, oy, oz, __fdiv_rn(sx, len), __fdiv_rn(sy, len), __fdiv_rn(sz, len));
+                            start_ray(true, len);
+                        } else {
+                            c = -dot3(nx, ny, nz, dx, dy, dz);
+                            shade = true;
+                        }
+                    }
+                } else {  // shadow ray finished; its origin is the bounce origin
+                    nx = s_stash[0][threadIdx.x]; ny = s_stash[1][threadIdx.x]; nz = s_stash[2][threadIdx.x];
+                    dx = s_stash[3][threadIdx.x]; dy = s_stash[4][threadIdx.x]; dz = s_stash[5][threadIdx.x];
+                    const float ndl = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
+                    c = best.did_hit ? 0.f : fmaxf(0.f, ndl);
+                    shade = true;
+                }
+                if (shade) {
+                    const float wgt = ldexpf(1.f, -(int)k);  // 0.5^k, the product of k exact halvings
+                    L = __fadd_rn(L, __fmul_rn(wgt, c));
+                    if (k < jd.bounces) {
+                        const float kk = __fmul_rn(2.f, dot3(dx, dy, dz, nx, ny, nz));
+                        float rx = __fsub_rn(dx, __fmul_rn(nx, kk));
+                        float ry = __fsub_rn(dy, __fmul_rn(ny, kk));
+                        float rz = __fsub_rn(dz, __fmul_rn(nz, kk));
+                        normalize3(rx, ry, rz);
+                        r = make_ray(ox, oy, oz, rx, ry, rz);
+                        st = (st & ~0xFFFFu) | (k + 1u);
+                        start_ray(false, INFINITY);
+                    } else {
+                        path_done = true;
+                    }
+                }
+                if (path_done) {
+                    if (jd.rgba) jd.rgba[o] = make_float4(L, L, L, 1.f);
+                    if (st & 0x20000u) atomicAdd(&tp->stack_overflows, 1u);
+                    job = RTR_NONE;
+                }
+            }
+        }
+    }
+    if (rays_traced && lane == 0u && traced) atomicAdd(rays_traced, (unsigned long long)traced);
+}
+
 inline Accel accel_of(const rtr_bvh* b) {
     Accel A;
-    A.nodes = b->flat_view; A.wtri = b->wtri_view; A.by_rank = b->wtri_by_rank ? 1u : 0u;
+    A.nodes = b->flat_view; A.wtri = b->wtri_view; A.pairs = b->pairs_view; A.by_rank = b->wtri_by_rank ? 1u : 0u;
     return A;
+}
+
+// one CTA per resident slot of the device
+int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_t* rays) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, trace_persistent_kernel, kTraceBlock, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const uint32_t need = (jd.total + kTraceBlock - 1) / kTraceBlock;
+    uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    if (grid > need) grid = need;
+    if (grid == 0) return RTR_OK;
+    RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->job_counter, 0, sizeof(uint32_t), ctx->stream));
+    trace_persistent_kernel<<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, jd,
+                                                                   reinterpret_cast<unsigned long long*>(rays));
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
 }
 
 }  // namespace
@@ -484,6 +814,19 @@ inline Accel accel_of(const rtr_bvh* b) {
 static void resolve_denoms(uint32_t width, uint32_t height, uint32_t& dw, uint32_t& dh) {
     if (dw == 0) dw = (width / 16) * 16;   // application.cpp:225-226 + raytracer.glsl:304-305 (Q5)
     if (dh == 0) dh = (height / 16) * 16;
+}
+
+static JobDesc pixel_jobs(const rtr_camera& cam, uint32_t width, uint32_t denom_w, uint32_t denom_h, const RowMap& rm,
+                          uint32_t bounces, int shadow, const float light[3], float* rgba, rtr_hit* hits) {
+    JobDesc jd;
+    memset(&jd, 0, sizeof(jd));
+    jd.kind = 0u;
+    jd.cam = cam; jd.width = width; jd.denom_w = denom_w; jd.denom_h = denom_h; jd.rm = rm;
+    jd.bounces = bounces; jd.shadow = shadow;
+    jd.lx = light ? light[0] : 0.f; jd.ly = light ? light[1] : 0.f; jd.lz = light ? light[2] : 0.f;
+    jd.rgba = reinterpret_cast<float4*>(rgba); jd.hits = hits;
+    jd.total = ((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u;
+    return jd;
 }
 
 int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
@@ -495,33 +838,35 @@ int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& c
         return rtr_set_error(ctx, RTR_E_INVALID, "trace_primary: bad image geometry %ux%u rows [%u,%u) denom %ux%u",
                              width, height, row0, row1, denom_w, denom_h);
     const uint32_t rows = row1 - row0;
-    const uint32_t grid = pixel_grid(width, rows);
-    const Accel A = accel_of(b);
+    if ((uint64_t)((width + 7) / 8) * ((rows + 3) / 4) * 32u >= 0xFFFFFF00ull)
+        return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_primary: image too large");
     RTR_PROF(ctx, "trace_primary_kernel");
-    if (flags & RTR_TRACE_REFERENCE_ORDER)
-        trace_primary_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, cam, width, denom_w, denom_h, row0,
-                                                                           rows, hits);
-    else
-        trace_primary_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, cam, width, denom_w, denom_h, row0,
-                                                                          rows, hits);
-    RTR_LAUNCH_CHECK(ctx);
-    return RTR_OK;
+    if (flags & RTR_TRACE_REFERENCE_ORDER) {
+        trace_primary_kernel<false><<<pixel_grid(width, rows), kTraceBlock, 0, ctx->stream>>>(
+            accel_of(b), b->tparams, cam, width, denom_w, denom_h, row0, rows, hits);
+        RTR_LAUNCH_CHECK(ctx);
+        return RTR_OK;
+    }
+    RowMap rm;
+    rm.row0 = row0; rm.rows = rows; rm.height = height; rm.rpb = 1; rm.rank = 0; rm.count = 1;
+    return launch_persistent(ctx, b, pixel_jobs(cam, width, denom_w, denom_h, rm, 0u, 0, nullptr, nullptr, hits), nullptr);
 }
 
 int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t n_rays, int any, const float* t_max,
                           uint32_t flags, rtr_hit* hits) {
     if (n_rays == 0) return RTR_OK;
-    const uint64_t grid64 = (n_rays + kTraceBlock - 1) / kTraceBlock;
-    if (grid64 > 0x7FFFFFFFull) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_rays: too many rays");
-    const uint32_t grid = (uint32_t)grid64;
-    const Accel A = accel_of(b);
+    if (n_rays >= 0xFFFFFF00ull) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_rays: too many rays");
     RTR_PROF(ctx, "trace_rays_kernel");
-    if (flags & RTR_TRACE_REFERENCE_ORDER)
-        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, rays, n_rays, any, t_max, hits);
-    else
-        trace_rays_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(A, b->tparams, rays, n_rays, any, t_max, hits);
-    RTR_LAUNCH_CHECK(ctx);
-    return RTR_OK;
+    if (flags & RTR_TRACE_REFERENCE_ORDER) {
+        const uint32_t grid = (uint32_t)((n_rays + kTraceBlock - 1) / kTraceBlock);
+        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, rays, n_rays, any, t_max, hits);
+        RTR_LAUNCH_CHECK(ctx);
+        return RTR_OK;
+    }
+    JobDesc jd;
+    memset(&jd, 0, sizeof(jd));
+    jd.kind = 1u; jd.total = (uint32_t)n_rays; jd.rays = rays; jd.t_max = t_max; jd.want_any = any; jd.hits = hits;
+    return launch_persistent(ctx, b, jd, nullptr);
 }
 
 int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
@@ -543,19 +888,16 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
         if (mine == 0) return RTR_OK;
         rm.row0 = 0; rm.rows = mine * rows_per_block; rm.rpb = rows_per_block; rm.rank = shard_rank; rm.count = shard_count;
     }
-    const uint32_t rows = rm.rows;
-    const uint32_t grid = pixel_grid(width, rows);
-    const Accel A = accel_of(b);
+    if ((uint64_t)((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u >= 0xFFFFFF00ull)
+        return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "render: image too large");
     RTR_PROF(ctx, "render_kernel");
-    const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
-    if (flags & RTR_TRACE_REFERENCE_ORDER)
-        render_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            A, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
+    if (flags & RTR_TRACE_REFERENCE_ORDER) {
+        const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
+        render_kernel<false><<<pixel_grid(width, rm.rows), kTraceBlock, 0, ctx->stream>>>(
+            accel_of(b), b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
             reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
-    else
-        render_kernel<true><<<grid, kTraceBlock, 0, ctx->stream>>>(
-            A, b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
-            reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
-    RTR_LAUNCH_CHECK(ctx);
-    return RTR_OK;
+        RTR_LAUNCH_CHECK(ctx);
+        return RTR_OK;
+    }
+    return launch_persistent(ctx, b, pixel_jobs(cam, width, denom_w, denom_h, rm, bounces, shadow, light, rgba, hits), rays);
 }
