@@ -172,6 +172,12 @@ __device__ __forceinline__ NodeRec load_node(const rtr_node* __restrict__ nodes,
     n.links = c;
     return n;
 }
+// 256-bit read-only load; p must be 32-byte aligned
+__device__ __forceinline__ void ld_nc_256(const uint4* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ uint4 load_links(const rtr_node* __restrict__ nodes, uint32_t idx) {
     return __ldg(reinterpret_cast<const uint4*>(nodes + idx) + 2);
 }
@@ -656,8 +662,11 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         pop_next();
                     }
                 } else {
-                    const uint4* rec = A.pairs + (size_t)a * 4;
-                    const uint4 c0 = __ldg(rec), c1 = __ldg(rec + 1), c2 = __ldg(rec + 2), c3 = __ldg(rec + 3);
+                    // one 64-byte record = two 256-bit loads (LDG.E.256, sm_100+): one L1 data-pipe pass per
+                    // 32-byte sector instead of two
+                    uint4 c0, c1, c2, c3;
+                    ld_nc_256(A.pairs + (size_t)a * 4, c0, c1);
+                    ld_nc_256(A.pairs + (size_t)a * 4 + 2, c2, c3);
                     const float4 llo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
                     const float4 lhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
                     const float4 rlo = make_float4(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x), 0.f);
