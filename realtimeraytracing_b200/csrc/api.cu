@@ -60,13 +60,13 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 }
 
 void bvh_free_arrays(rtr_bvh* b) {
-    void* ptrs[] = {b->codes, b->tri_idx, b->node_lo, b->node_hi, b->isize, b->ipos, b->cin, b->cout, b->tile_status,
+    void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->cin, b->cout, b->tile_status,
                     b->state, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
                     b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     b->codes = b->tri_idx = b->isize = b->ipos = b->cin = b->cout = nullptr;
-    b->node_lo = b->node_hi = nullptr;
+    b->node = nullptr;
     b->tile_status = nullptr; b->state = nullptr;
     b->trace_active = b->trace_merges = b->iter_first_id = nullptr;
     b->bounds12 = nullptr; b->ordered6 = nullptr; b->flat = nullptr; b->tparams = nullptr;
@@ -88,11 +88,10 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     b->tris_own = keep_t; b->tris_own_cap = keep_tc; b->meshes_own = keep_m; b->meshes_own_cap = keep_mc;
     b->adopted = false;
     const size_t cap = n, nc = 2 * (size_t)n - 1;
-    const size_t tiles = (cap + 479) / 480 + 1;
+    const size_t tiles = (cap + kPlocTile - 1) / kPlocTile + 1;
     RTR_CHECK(dev_alloc(ctx, &b->codes, cap));
     RTR_CHECK(dev_alloc(ctx, &b->tri_idx, cap));
-    RTR_CHECK(dev_alloc(ctx, &b->node_lo, nc));
-    RTR_CHECK(dev_alloc(ctx, &b->node_hi, nc));
+    RTR_CHECK(dev_alloc(ctx, &b->node, 2 * nc));
     RTR_CHECK(dev_alloc(ctx, &b->isize, cap));
     RTR_CHECK(dev_alloc(ctx, &b->ipos, cap));
     RTR_CHECK(dev_alloc(ctx, &b->cin, cap));
@@ -133,7 +132,7 @@ int bvh_build_common(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uin
     RTR_CHECK(rtr_ws_reserve(ctx, rtr_sort_ws_bytes(n, 4, true)));
     b->n = n; b->array_len = array_len; b->nb_meshes = nb_meshes; b->radius = radius;
     b->tris = tris_dev; b->meshes = meshes_dev;
-    RTR_CUDA(ctx, cudaMemsetAsync(b->tile_status, 0, sizeof(uint64_t) * ((n + 479) / 480 + 1), ctx->stream));
+    RTR_CUDA(ctx, cudaMemsetAsync(b->tile_status, 0, sizeof(uint64_t) * ((n + kPlocTile - 1) / kPlocTile + 1), ctx->stream));
     return rtr_bvh_run_build(b);
 }
 

@@ -19,6 +19,7 @@ struct TraceParams {
 };
 
 constexpr uint32_t kMaxPlocIterations = 1u << 16;
+constexpr int kPlocTile = 480;  // positions decided per CTA of ploc_iteration_kernel (ploc.cu)
 
 struct rtr_bvh {
     rtr_ctx* ctx = nullptr;
@@ -39,8 +40,7 @@ struct rtr_bvh {
     // build arrays (device), sized by capacity
     uint32_t* codes = nullptr;     // [cap]  sorted Morton codes
     uint32_t* tri_idx = nullptr;   // [cap]  BVH_Params::_TriangleIndices
-    float4* node_lo = nullptr;     // [2cap-1] by cluster id: min.xyz, max.x
-    float4* node_hi = nullptr;     // [2cap-1] max.y, max.z, bits(left | triangle id), bits(right | NONE)
+    float4* node = nullptr;        // [2*(2cap-1)] by cluster id, 32 B records: (min.xyz, max.x)(max.y, max.z, bits(left | triangle id), bits(right | NONE))
     uint32_t* isize = nullptr;     // [cap] nodes in the subtree of internal cluster (id - n)
     uint32_t* ipos = nullptr;      // [cap] DFS pre-order position of internal cluster (id - n)
     uint32_t* cin = nullptr;       // [cap] active list, ping

@@ -5,32 +5,43 @@
 // plocNearestNeighborSearch (:193-210), plocMerging (:159-191), plocPrefixScan (:125-148),
 // plocCompaction (:150-156), and glr::Scene::getBVH_NodesToGPUData (scene.cpp:189-208).
 //
-// Layout in HBM (by cluster id, SoA of two float4 so a box is two 16-byte loads):
-//   node_lo[c] = (min.x, min.y, min.z, max.x)      node_hi[c] = (max.y, max.z, L, R)
+// Layout in HBM (by cluster id, one 32-byte record = one sector, read with a single 256-bit load):
+//   node[2c] = (min.x, min.y, min.z, max.x)      node[2c+1] = (max.y, max.z, L, R)
 //   leaves c < n:  L = triangle id, R = RTR_NONE;  internal c >= n: L/R = child cluster ids
 //   isize[c-n] = nodes in the subtree of internal cluster c (lets flatten place the right child)
 //   cin/cout   = active cluster ids in Morton order (the reference's C_In/C_Out)
 //
-// One kernel per PLOC iteration (ploc_iteration_kernel): each 512-thread CTA takes a tile of 480
-// positions plus a 32-position halo on each side, gathers ids + boxes into shared memory, finds
-// every nearest neighbour in the +-16 window (argmin of merged surface area, lowest j on ties,
-// fp32 ops in the reference's order), decides mutual pairs, ranks merges and survivors with a
-// CTA scan + decoupled look-back across tiles, writes the merged nodes at id = total + rank
-// (== the reference's serial counter, Q3) and compacts survivors -- NN search, merge, prefix scan
-// and compaction of the reference fused into one pass over the active list.  The iteration
-// count is data dependent, so the loop state lives on the device (PlocState, double buffered by
-// launch parity) and launches that find n_active <= kTailN are no-ops; a single-CTA tail kernel
-// finishes the last <= 1024 clusters entirely in shared memory (PLOC++ 4.4).
+// One kernel per PLOC iteration (ploc_iteration_kernel), NN search + merge + prefix scan + compaction
+// of the reference fused into one pass over the active list.  A CTA decides a tile of 480 positions;
+// it stages the ids and boxes of the tile plus a 32-position halo on each side in shared memory
+// (float4 + float2 per box, interleaved so that no access pattern below has bank conflicts), every
+// thread owns kPP consecutive positions whose boxes it keeps in registers, reads each neighbour box of
+// its +-16 window once and tries it against all of them: argmin of the merged surface area in
+// ascending j with strict '<', i.e. lowest j on ties (bvh.cpp:199-208), every fp32 op individually
+// rounded in the reference's order.  Mutual pairs are ranked with a CTA scan + decoupled look-back
+// across tiles: merged nodes go to id = total + rank (== the reference's serial counter, Q3) and
+// survivors are compacted in place order.  The iteration count is data dependent, so the loop state
+// lives on the device (PlocState, double buffered by launch parity) and launches that find
+// n_active <= kTailN are no-ops; a single-CTA tail kernel finishes the last <= 1024 clusters entirely
+// in shared memory (PLOC++ 4.4).
 #include "bvh.cuh"
 
 namespace {
 
 constexpr int kR = RTR_MAX_SEARCH_RADIUS;       // 16
-constexpr int kPBlock = 512;
-constexpr int kTileT = kPBlock - 2 * kR;        // 480 positions decided per CTA
-constexpr int kExt = kTileT + 4 * kR;           // 544 positions staged per CTA
+#ifndef RTR_PLOC_PP
+#define RTR_PLOC_PP 4
+#endif
+constexpr int kPP = RTR_PLOC_PP;                 // positions per thread
+constexpr int kPT = 512 / kPP;                   // threads per CTA
+constexpr int kEval = kPT * kPP;                 // 512 positions whose nearest neighbour a CTA computes
+constexpr int kTileT = kPlocTile;                // 480 positions decided per CTA (= kEval - 2 kR)
+constexpr int kStage = kEval + 2 * kR;           // 544 positions staged (tile + 2 kR halo each side)
+constexpr int kStageQ = kStage / kPP;            // staged arrays are stored [e % kPP][e / kPP] (conflict free)
 constexpr uint32_t kTailN = 1024;
 constexpr int kChunk = 8;                        // iteration launches between host checks
+static_assert(kTileT == kEval - 2 * kR, "tile geometry");
+static_assert(kStage % kPP == 0, "staging layout");
 
 // look-back word: [0,27) merges (lo partners), [27,54) removed (hi partners), [54,56) flag, [56,64) tag
 constexpr uint64_t kCntMask = (1ull << 27) - 1;
@@ -47,7 +58,25 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-struct BoxSoA {  // views into shared memory
+// one 32-byte cluster record
+struct Box {
+    float4 lo;  // min.xyz, max.x
+    float4 hi;  // max.y, max.z, bits(L), bits(R)
+};
+__device__ __forceinline__ Box load_box(const float4* __restrict__ node, uint32_t c) {
+    Box b;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(b.lo.x), "=f"(b.lo.y), "=f"(b.lo.z), "=f"(b.lo.w), "=f"(b.hi.x), "=f"(b.hi.y), "=f"(b.hi.z), "=f"(b.hi.w)
+                 : "l"(node + 2 * (size_t)c));
+    return b;
+}
+__device__ __forceinline__ void store_box(float4* __restrict__ node, uint32_t c, const float4 lo, const float4 hi) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(node + 2 * (size_t)c), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
+
+struct BoxSoA {  // views into shared memory (tail kernel)
     float* minx; float* miny; float* minz; float* maxx; float* maxy; float* maxz;
 };
 
@@ -57,6 +86,13 @@ __device__ __forceinline__ float merged_half_area(const BoxSoA& b, int i, int j)
     const float dx = __fsub_rn(fmaxf(b.maxx[i], b.maxx[j]), fminf(b.minx[i], b.minx[j]));
     const float dy = __fsub_rn(fmaxf(b.maxy[i], b.maxy[j]), fminf(b.miny[i], b.miny[j]));
     const float dz = __fsub_rn(fmaxf(b.maxz[i], b.maxz[j]), fminf(b.minz[i], b.minz[j]));
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dy, dz)), __fmul_rn(dz, dx));
+}
+// the same on register boxes: lo = (min.xyz, max.x), hi = (max.y, max.z)
+__device__ __forceinline__ float pair_half_area(const float4 alo, const float2 ahi, const float4 blo, const float2 bhi) {
+    const float dx = __fsub_rn(fmaxf(alo.w, blo.w), fminf(alo.x, blo.x));
+    const float dy = __fsub_rn(fmaxf(ahi.x, bhi.x), fminf(alo.y, blo.y));
+    const float dz = __fsub_rn(fmaxf(ahi.y, bhi.y), fminf(alo.z, blo.z));
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dy, dz)), __fmul_rn(dz, dx));
 }
 
@@ -104,7 +140,7 @@ __device__ __forceinline__ uint32_t block_scan_incl(uint32_t v, uint32_t* s_warp
 __global__ void __launch_bounds__(256)
 leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restrict__ meshes,
                  const uint32_t* __restrict__ tri_idx, uint32_t n,
-                 float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t* __restrict__ cin,
+                 float4* __restrict__ node, uint32_t* __restrict__ cin,
                  float4* __restrict__ wtri, TraceParams* __restrict__ tparams) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float e2 = 0.f;
@@ -115,8 +151,8 @@ leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restri
         const float3 a = mat_mul_point(M, t.p0), b = mat_mul_point(M, t.p1), c = mat_mul_point(M, t.p2);
         const float mnx = fminf(a.x, fminf(b.x, c.x)), mny = fminf(a.y, fminf(b.y, c.y)), mnz = fminf(a.z, fminf(b.z, c.z));
         const float mxx = fmaxf(a.x, fmaxf(b.x, c.x)), mxy = fmaxf(a.y, fmaxf(b.y, c.y)), mxz = fmaxf(a.z, fmaxf(b.z, c.z));
-        node_lo[i] = make_float4(mnx, mny, mnz, mxx);
-        node_hi[i] = make_float4(mxy, mxz, __uint_as_float(ti), __uint_as_float(RTR_NONE));
+        store_box(node, i, make_float4(mnx, mny, mnz, mxx),
+                  make_float4(mxy, mxz, __uint_as_float(ti), __uint_as_float(RTR_NONE)));
         cin[i] = i;
         // world-space vertices for the traversal kernels (the M*P of raytracer.glsl:105-107), leaf order
         wtri[3 * (size_t)i + 0] = make_float4(a.x, a.y, a.z, b.x);
@@ -167,20 +203,26 @@ __global__ void ploc_state_init_kernel(PlocState* state, uint32_t n, uint32_t* i
 // ---------------------------------------------------------------------------------------
 // one PLOC iteration over the whole active list
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPBlock)
+struct IterSmem {
+    float4 lo[kStage];            // [e % kPP][e / kPP]: min.xyz, max.x
+    float2 hi[kStage];            //                     max.y, max.z
+    uint32_t id[kStage];          //                     cluster id (RTR_NONE outside the active list)
+    int nn[kEval];                // neighbour (staged index) of staged position kR + q, or -1
+    uint32_t warp[kPT / 32 + 1];
+    uint32_t tile, ex_lo, ex_hi;
+};
+__device__ __forceinline__ int perm_stage(int e) { return (e % kPP) * kStageQ + (e / kPP); }
+
+__global__ void __launch_bounds__(kPT)
 ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                       uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
-                      float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t* __restrict__ isize,
+                      float4* __restrict__ node, uint32_t* __restrict__ isize,
                       PlocState* __restrict__ state, uint64_t* __restrict__ tile_status,
                       uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
                       uint32_t* __restrict__ iter_first_id) {
-    __shared__ float s_box[6][kExt];
-    __shared__ uint32_t s_id[kExt];
-    __shared__ int s_nn[kPBlock];        // neighbour position of q = t0 - kR + x, or -1
-    __shared__ uint32_t s_warp[kPBlock / 32 + 1];
-    __shared__ uint32_t s_tile, s_ex_lo, s_ex_hi;
+    __shared__ IterSmem s;
 
-    const uint32_t tid = threadIdx.x;
+    const int tid = (int)threadIdx.x;
     PlocState* cur = &state[launch_idx & 1u];
     PlocState* nxt = &state[(launch_idx + 1u) & 1u];
     const uint32_t n = cur->n_active, total = cur->total, iter = cur->iter;
@@ -191,58 +233,87 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
         return;
     }
     const uint32_t tiles = (n + kTileT - 1) / kTileT;
-    if (tid == 0) s_tile = atomicAdd(&cur->tile_counter, 1u);
+    if (tid == 0) s.tile = atomicAdd(&cur->tile_counter, 1u);
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = s.tile;
     if (tile >= tiles) return;
 
     const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
     uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
     const int t0 = (int)(tile * kTileT);
-    const int base = t0 - 2 * kR;  // position of shared slot 0
+    const int base = t0 - 2 * kR;  // position of staged slot 0
 
-    // ---- stage ids + boxes of the tile and its halo ----
-    for (int e = tid; e < kExt; e += kPBlock) {
+    // ---- stage ids + boxes of the tile and its halo (one 32-byte gather per position) ----
+    for (int e = tid; e < kStage; e += kPT) {
         const int pos = base + e;
+        const int pe = perm_stage(e);
         if (pos >= 0 && pos < (int)n) {
             const uint32_t id = cin[pos];
-            const float4 lo = node_lo[id], hi = node_hi[id];
-            s_id[e] = id;
-            s_box[0][e] = lo.x; s_box[1][e] = lo.y; s_box[2][e] = lo.z;
-            s_box[3][e] = lo.w; s_box[4][e] = hi.x; s_box[5][e] = hi.y;
+            const Box b = load_box(node, id);
+            s.id[pe] = id;
+            s.lo[pe] = b.lo;
+            s.hi[pe] = make_float2(b.hi.x, b.hi.y);
         } else {
-            s_id[e] = RTR_NONE;
+            s.id[pe] = RTR_NONE;
         }
     }
     __syncthreads();
 
-    // ---- nearest neighbour of every position in [t0 - kR, t0 + kTileT + kR) ----
-    const BoxSoA B{s_box[0], s_box[1], s_box[2], s_box[3], s_box[4], s_box[5]};
-    const int q = t0 - kR + (int)tid;  // this thread's position
-    {
-        int nn = -1;
-        if (q >= 0 && q < (int)n) {
-            const int jlo = max(0, q - radius), jhi = min(q + radius + 1, (int)n);
-            const int e = nearest_neighbour(B, q - base, jlo - base, jhi - base);
-            nn = (e < 0) ? -1 : e + base;
-        }
-        s_nn[tid] = nn;
+    // ---- nearest neighbour of the kPP positions this thread owns: staged e0 .. e0 + kPP - 1 ----
+    // Every neighbour box is read once and tried against all kPP own boxes; j ascending means
+    // ascending candidate position for each own position, strict '<' keeps the lowest on ties.
+    const int e0 = kR + kPP * tid;  // staged index; positions [t0 - kR, t0 + kTileT + kR)
+    float4 lo[kPP]; float2 hi[kPP]; bool ok[kPP];
+#pragma unroll
+    for (int i = 0; i < kPP; ++i) {
+        const int pe = perm_stage(e0 + i);
+        lo[i] = s.lo[pe];
+        hi[i] = s.hi[pe];
+        const int pos = base + e0 + i;
+        ok[i] = pos >= 0 && pos < (int)n;
     }
+    float best[kPP]; int bj[kPP];
+#pragma unroll
+    for (int i = 0; i < kPP; ++i) { best[i] = INFINITY; bj[i] = -1; }
+#pragma unroll
+    for (int j = -kR; j < kPP + kR; ++j) {  // neighbour at staged position e0 + j
+        float4 xlo; float2 xhi;
+        if (j >= 0 && j < kPP) { xlo = lo[j]; xhi = hi[j]; }
+        else { const int pe = perm_stage(e0 + j); xlo = s.lo[pe]; xhi = s.hi[pe]; }
+        const int xpos = base + e0 + j;
+        const bool xok = xpos >= 0 && xpos < (int)n;
+#pragma unroll
+        for (int i = 0; i < kPP; ++i) {
+            const int k = j - i;
+            if (k != 0 && k >= -kR && k <= kR) {
+                const float d = pair_half_area(lo[i], hi[i], xlo, xhi);
+                const bool cand = xok && (k < 0 ? -k : k) <= radius;
+                if (cand && d < best[i]) { best[i] = d; bj[i] = e0 + j; }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kPP; ++i) s.nn[kPP * tid + i] = ok[i] ? bj[i] : -1;
     __syncthreads();
 
     // ---- mutual pairs (plocMerging, bvh.cpp:159-165): lo = lower partner, hi = removed partner ----
-    const bool in_tile = (tid >= (uint32_t)kR) && (tid < (uint32_t)(kR + kTileT)) && (q < (int)n);
-    const int j = in_tile ? s_nn[tid] : -1;
-    bool is_lo = false, is_hi = false;
-    if (j >= 0) {
-        const int nnj = s_nn[j - (t0 - kR)];
-        if (nnj == q) { is_lo = q < j; is_hi = q > j; }
+    bool is_lo[kPP], is_hi[kPP]; int partner[kPP];
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < kPP; ++i) {
+        const int q = e0 + i;  // staged index
+        is_lo[i] = is_hi[i] = false; partner[i] = -1;
+        const bool in_tile = q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
+        if (in_tile) {
+            const int j = s.nn[q - kR];
+            if (j >= 0 && s.nn[j - kR] == q) { is_lo[i] = q < j; is_hi[i] = q > j; partner[i] = j; }
+        }
+        packed += (is_lo[i] ? 1u : 0u) + (is_hi[i] ? 1u << 16 : 0u);
     }
     uint32_t cta_total;
-    const uint32_t packed = (is_lo ? 1u : 0u) | (is_hi ? 1u << 16 : 0u);
-    const uint32_t incl = block_scan_incl<kPBlock>(packed, s_warp, &cta_total);
-    const uint32_t ex_lo_local = (incl & 0xFFFFu) - (is_lo ? 1u : 0u);
-    const uint32_t ex_hi_local = (incl >> 16) - (is_hi ? 1u : 0u);
+    const uint32_t incl = block_scan_incl<kPT>(packed, s.warp, &cta_total);
+    uint32_t ex_lo_local = (incl & 0xFFFFu) - (packed & 0xFFFFu);
+    uint32_t ex_hi_local = (incl >> 16) - (packed >> 16);
 
     // ---- decoupled look-back over tiles (plocPrefixScan, bvh.cpp:125-148, as a single pass) ----
     if (tid == 0) {
@@ -263,7 +334,7 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
             }
         }
         st_relaxed_u64(&tile_status[tile], lb_pack(tag, kLbIncl, ex_lo + agg_lo, ex_hi + agg_hi));
-        s_ex_lo = ex_lo; s_ex_hi = ex_hi;
+        s.ex_lo = ex_lo; s.ex_hi = ex_hi;
         if (tile == tiles - 1) {  // bvh.cpp:105-113
             const uint32_t merges = ex_lo + agg_lo, removed = ex_hi + agg_hi;
             nxt->n_active = n - removed; nxt->total = total + merges; nxt->iter = iter + 1; nxt->tile_counter = 0;
@@ -275,23 +346,30 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     __syncthreads();
 
     // ---- merge (bvh.cpp:166-188) + compaction (bvh.cpp:150-156) ----
-    if (in_tile) {
-        const int e_q = q - base;
-        uint32_t out_id = s_id[e_q];
-        if (is_lo) {
-            const int e_j = j - base;
-            const uint32_t new_id = total + s_ex_lo + ex_lo_local;
-            const uint32_t cl = s_id[e_q], cr = s_id[e_j];
-            node_lo[new_id] = make_float4(fminf(B.minx[e_q], B.minx[e_j]), fminf(B.miny[e_q], B.miny[e_j]),
-                                          fminf(B.minz[e_q], B.minz[e_j]), fmaxf(B.maxx[e_q], B.maxx[e_j]));
-            node_hi[new_id] = make_float4(fmaxf(B.maxy[e_q], B.maxy[e_j]), fmaxf(B.maxz[e_q], B.maxz[e_j]),
-                                          __uint_as_float(cl), __uint_as_float(cr));
-            const uint32_t sl = cl < n_leaves ? 1u : isize[cl - n_leaves];
-            const uint32_t sr = cr < n_leaves ? 1u : isize[cr - n_leaves];
-            isize[new_id - n_leaves] = sl + sr + 1u;
-            out_id = new_id;
+    const uint32_t lo_base = total + s.ex_lo, hi_base = s.ex_hi;
+#pragma unroll
+    for (int i = 0; i < kPP; ++i) {
+        const int q = e0 + i;
+        const bool in_tile = q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
+        if (in_tile) {
+            uint32_t out_id = s.id[perm_stage(q)];
+            if (is_lo[i]) {
+                const int pj = perm_stage(partner[i]);
+                const float4 plo = s.lo[pj]; const float2 phi = s.hi[pj];
+                const uint32_t new_id = lo_base + ex_lo_local;
+                const uint32_t cl = out_id, cr = s.id[pj];
+                store_box(node, new_id,
+                          make_float4(fminf(lo[i].x, plo.x), fminf(lo[i].y, plo.y), fminf(lo[i].z, plo.z), fmaxf(lo[i].w, plo.w)),
+                          make_float4(fmaxf(hi[i].x, phi.x), fmaxf(hi[i].y, phi.y), __uint_as_float(cl), __uint_as_float(cr)));
+                const uint32_t sl = cl < n_leaves ? 1u : isize[cl - n_leaves];
+                const uint32_t sr = cr < n_leaves ? 1u : isize[cr - n_leaves];
+                isize[new_id - n_leaves] = sl + sr + 1u;
+                out_id = new_id;
+                ++ex_lo_local;
+            }
+            if (!is_hi[i]) cout[(uint32_t)(base + q) - (hi_base + ex_hi_local)] = out_id;
+            else ++ex_hi_local;
         }
-        if (!is_hi) cout[(uint32_t)q - (s_ex_hi + ex_hi_local)] = out_id;
     }
 }
 
@@ -309,7 +387,7 @@ struct TailSmem {
 __global__ void __launch_bounds__(kTailN)
 ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                  const uint32_t* __restrict__ buf0, const uint32_t* __restrict__ buf1,
-                 float4* __restrict__ node_lo, float4* __restrict__ node_hi, uint32_t* __restrict__ isize,
+                 float4* __restrict__ node, uint32_t* __restrict__ isize,
                  PlocState* __restrict__ state, uint32_t* __restrict__ trace_active,
                  uint32_t* __restrict__ trace_merges, uint32_t* __restrict__ iter_first_id) {
     extern __shared__ __align__(16) unsigned char tail_raw[];
@@ -326,7 +404,7 @@ ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     int cur_buf = 0;
     if (tid < n) {
         const uint32_t id = cin[tid];
-        const float4 lo = node_lo[id], hi = node_hi[id];
+        const Box bx_ = load_box(node, id); const float4 lo = bx_.lo, hi = bx_.hi;
         s.id[0][tid] = id;
         s.size[0][tid] = id < n_leaves ? 1u : isize[id - n_leaves];
         s.box[0][0][tid] = lo.x; s.box[0][1][tid] = lo.y; s.box[0][2][tid] = lo.z;
@@ -357,8 +435,8 @@ ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                 const float mnz = fminf(B.minz[q], B.minz[nn]), mxx = fmaxf(B.maxx[q], B.maxx[nn]);
                 const float mxy = fmaxf(B.maxy[q], B.maxy[nn]), mxz = fmaxf(B.maxz[q], B.maxz[nn]);
                 const uint32_t sz = s.size[cur_buf][q] + s.size[cur_buf][nn] + 1u;
-                node_lo[new_id] = make_float4(mnx, mny, mnz, mxx);
-                node_hi[new_id] = make_float4(mxy, mxz, __uint_as_float(cl), __uint_as_float(cr));
+                store_box(node, new_id, make_float4(mnx, mny, mnz, mxx),
+                          make_float4(mxy, mxz, __uint_as_float(cl), __uint_as_float(cr)));
                 isize[new_id - n_leaves] = sz;
                 s.id[nb][dst] = new_id; s.size[nb][dst] = sz;
                 s.box[nb][0][dst] = mnx; s.box[nb][1][dst] = mny; s.box[nb][2][dst] = mnz;
@@ -393,23 +471,23 @@ __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t
 }
 
 __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
-                                            const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                                            const float4* __restrict__ node,
                                             const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
                                             rtr_node* __restrict__ flat) {
     const uint32_t p = ipos[c - n_leaves];
-    const float4 lo = node_lo[c], hi = node_hi[c];
+    const Box bx_ = load_box(node, c); const float4 lo = bx_.lo, hi = bx_.hi;
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
     const uint32_t size_l = L < n_leaves ? 1u : isize[L - n_leaves];
     const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
     store_node(flat, p, lo, hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
     if (L < n_leaves) {
-        const float4 llo = node_lo[L], lhi = node_hi[L];
+        const Box bl_ = load_box(node, L); const float4 llo = bl_.lo, lhi = bl_.hi;
         store_node(flat, pos_l, llo, lhi, __float_as_uint(lhi.z), 0u, 0u, L);
     } else {
         ipos[L - n_leaves] = pos_l;
     }
     if (R < n_leaves) {
-        const float4 rlo = node_lo[R], rhi = node_hi[R];
+        const Box br_ = load_box(node, R); const float4 rlo = br_.lo, rhi = br_.hi;
         store_node(flat, pos_r, rlo, rhi, __float_as_uint(rhi.z), 0u, 0u, R);
     } else {
         ipos[R - n_leaves] = pos_r;
@@ -418,27 +496,27 @@ __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
 
 __global__ void __launch_bounds__(256)
 flatten_level_kernel(uint32_t first, uint32_t count, uint32_t n_leaves,
-                     const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                     const float4* __restrict__ node,
                      const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) flatten_one(first + i, n_leaves, node_lo, node_hi, isize, ipos, flat);
+    if (i < count) flatten_one(first + i, n_leaves, node, isize, ipos, flat);
 }
 
 // levels [it_lo, it_hi] processed last-first by one CTA (the top of the tree: many tiny levels)
 __global__ void __launch_bounds__(1024)
 flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_hi, int it_lo, uint32_t n_leaves,
-                            const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                            const float4* __restrict__ node,
                             const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat) {
     for (int it = it_hi; it >= it_lo; --it) {
         const uint32_t first = iter_first_id[it], count = iter_first_id[it + 1] - first;
         for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
-            flatten_one(first + i, n_leaves, node_lo, node_hi, isize, ipos, flat);
+            flatten_one(first + i, n_leaves, node, isize, ipos, flat);
         __syncthreads();
     }
 }
 
-__global__ void flatten_single_leaf_kernel(const float4* node_lo, const float4* node_hi, rtr_node* flat) {
-    const float4 lo = node_lo[0], hi = node_hi[0];
+__global__ void flatten_single_leaf_kernel(const float4* node, rtr_node* flat) {
+    const Box bx_ = load_box(node, 0); const float4 lo = bx_.lo, hi = bx_.hi;
     store_node(flat, 0, lo, hi, __float_as_uint(hi.z), 0u, 0u, 0u);
 }
 
@@ -466,12 +544,12 @@ pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t
 // BVH_Params view by cluster id for the accessors / the cr::BVH shim (not on the timed path)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-export_clusters_kernel(uint32_t n_leaves, const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+export_clusters_kernel(uint32_t n_leaves, const float4* __restrict__ node,
                        rtr_node* __restrict__ clusters, uint32_t* __restrict__ parent, uint32_t* __restrict__ left,
                        uint32_t* __restrict__ right, uint8_t* __restrict__ is_leaf) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= 2 * n_leaves - 1) return;
-    const float4 lo = node_lo[c], hi = node_hi[c];
+    const Box bx_ = load_box(node, c); const float4 lo = bx_.lo, hi = bx_.hi;
     const bool leaf = c < n_leaves;
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
     if (clusters) store_node(clusters, c, lo, hi, leaf ? L : 0u, 0u, 0u);  // links stay 0 (Q10)
@@ -544,8 +622,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     // 3. leaves
     RTR_CUDA(ctx, cudaMemsetAsync(b->tparams, 0, sizeof(TraceParams), ctx->stream));
     RTR_PROF(ctx, "leaf_init_kernel");
-    leaf_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->tri_idx, n, b->node_lo,
-                                                               b->node_hi, b->cin, b->wtri, b->tparams);
+    leaf_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->tri_idx, n, b->node,
+                                                               b->cin, b->wtri, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
     ploc_state_init_kernel<<<1, 1, 0, ctx->stream>>>(b->state, n, b->iter_first_id);
     RTR_LAUNCH_CHECK(ctx);
@@ -557,6 +635,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     uint32_t bound_n = n;  // upper bound of n_active, refreshed from the device every kChunk launches
     static bool tail_configured = false;
     if (!tail_configured) {
+
         RTR_CUDA(ctx, cudaFuncSetAttribute(ploc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(TailSmem)));
         tail_configured = true;
@@ -566,8 +645,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         const uint32_t tiles = (bound_n + kTileT - 1) / kTileT;
         for (int k = 0; k < kChunk; ++k) {
             RTR_PROF(ctx, "ploc_iteration_kernel");
-            ploc_iteration_kernel<<<tiles, kPBlock, 0, ctx->stream>>>(
-                launch_idx, n, radius, b->cin, b->cout, b->node_lo, b->node_hi, b->isize, b->state, b->tile_status,
+            ploc_iteration_kernel<<<tiles, kPT, 0, ctx->stream>>>(
+                launch_idx, n, radius, b->cin, b->cout, b->node, b->isize, b->state, b->tile_status,
                 b->trace_active, b->trace_merges, b->iter_first_id);
             RTR_LAUNCH_CHECK(ctx);
             ++launch_idx;
@@ -585,8 +664,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         bound_n = h_state->n_active;
     }
     RTR_PROF(ctx, "ploc_tail_kernel");
-    ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(launch_idx, n, radius, b->cin, b->cout, b->node_lo,
-                                                                   b->node_hi, b->isize, b->state, b->trace_active,
+    ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(launch_idx, n, radius, b->cin, b->cout, b->node,
+                                                                   b->isize, b->state, b->trace_active,
                                                                    b->trace_merges, b->iter_first_id);
     RTR_LAUNCH_CHECK(ctx);
     ++launch_idx;
@@ -608,7 +687,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
 
     // 5. flatten, last creation level first
     if (n == 1) {
-        flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node_lo, b->node_hi, b->flat);
+        flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node, b->flat);
         RTR_LAUNCH_CHECK(ctx);
     } else {
         RTR_CUDA(ctx, cudaMemsetAsync(b->ipos + (n - 2), 0, sizeof(uint32_t), ctx->stream));  // root 2n-2 -> position 0
@@ -618,16 +697,16 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             const uint32_t count = b->h_first_id[it + 1] - b->h_first_id[it];
             if (count > kSmall) {
                 RTR_PROF(ctx, "flatten_level_kernel");
-                flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node_lo,
-                                                                                   b->node_hi, b->isize, b->ipos, b->flat);
+                flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node,
+                                                                                   b->isize, b->ipos, b->flat);
                 RTR_LAUNCH_CHECK(ctx);
                 --it;
             } else {
                 int lo = it;
                 while (lo - 1 >= 0 && b->h_first_id[lo] - b->h_first_id[lo - 1] <= kSmall) --lo;
                 RTR_PROF(ctx, "flatten_small_levels_kernel");
-                flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node_lo,
-                                                                         b->node_hi, b->isize, b->ipos, b->flat);
+                flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node,
+                                                                         b->isize, b->ipos, b->flat);
                 RTR_LAUNCH_CHECK(ctx);
                 it = lo - 1;
             }
@@ -653,7 +732,7 @@ int rtr_bvh_export_clusters(rtr_bvh* b, rtr_node* clusters, uint32_t* parent, ui
     rtr_ctx* ctx = b->ctx;
     const uint32_t nc = 2 * b->n - 1;
     if (parent) RTR_CUDA(ctx, cudaMemsetAsync(parent, 0xFF, sizeof(uint32_t) * nc, ctx->stream));
-    export_clusters_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->n, b->node_lo, b->node_hi, clusters, parent, left,
+    export_clusters_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->n, b->node, clusters, parent, left,
                                                                      right, is_leaf);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
