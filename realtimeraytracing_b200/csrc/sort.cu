@@ -9,10 +9,13 @@
 // Kernels
 //   radix_histogram_kernel : one read of the keys, all digit places at once (shared atomics)
 //   radix_scan_kernel      : exclusive scan of each 256-bin histogram (one warp-scan CTA)
-//   onesweep_kernel        : per pass; tile = BLOCK*IPT keys staged into shared memory by one
-//                            TMA bulk copy (cp.async.bulk + mbarrier), warp-level match ranking,
-//                            shuffle scans, decoupled look-back over per-tile digit counts,
-//                            shared-memory reorder, coalesced scatter
+//   onesweep_kernel        : per pass; tile = BLOCK*IPT keys (and payload) staged into shared memory by
+//                            TMA bulk copies (cp.async.bulk + one mbarrier), warp-ballot digit ranking
+//                            (8 VOTEs per key; MATCH.ANY measured ~10x slower on sm_100), one shared
+//                            atomic per digit group for the running warp count, shuffle scans, decoupled
+//                            look-back over per-tile digit counts (done before the reorder so the
+//                            aggregate->inclusive window stays short), shared-memory reorder,
+//                            coalesced scatter
 // Algorithmic HBM bytes: n*(s_k + P*2*s_e)  (SURVEY.md 8d): 36 B/key u32 keys, 68 B/pair.
 #include "common.cuh"
 
@@ -23,6 +26,10 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr uint32_t kFlagAgg = 1u << 30;   // tile aggregate available
 constexpr uint32_t kFlagIncl = 2u << 30;  // inclusive prefix available
 constexpr uint32_t kValueMask = (1u << 30) - 1;
+#ifndef RTR_SORT_LOOKBATCH
+#define RTR_SORT_LOOKBATCH 16
+#endif
+constexpr int kLookBatch = RTR_SORT_LOOKBATCH;  // predecessors whose status words one look-back round has in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -134,7 +141,8 @@ struct OnesweepSmem {
     static constexpr int TILE = BLOCK * IPT;
     static constexpr int WARPS = BLOCK / 32;
     alignas(128) KeyT keys[TILE];
-    uint32_t vals[PAIRS ? TILE : 1];
+    alignas(128) uint32_t vals_in[PAIRS ? TILE : 4];   // payload as loaded (TMA destination)
+    alignas(128) uint32_t vals[PAIRS ? TILE : 4];      // payload in tile-sorted order
     uint32_t whist[WARPS][kRadix];  // per-warp digit counts, then warp-exclusive offsets
     uint32_t cta_ofs[kRadix];       // first tile-local slot of each digit
     uint32_t gofs[kRadix];          // global slot of digit's first key of this tile, minus cta_ofs
@@ -144,7 +152,7 @@ struct OnesweepSmem {
 };
 
 template <typename KeyT, bool PAIRS, int BLOCK, int IPT, bool TMA>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 1024 : 1024) / BLOCK)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 uint32_t n, uint32_t num_tiles, int shift, uint32_t mask,
@@ -154,7 +162,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     using Smem = OnesweepSmem<KeyT, PAIRS, BLOCK, IPT>;
     constexpr int TILE = Smem::TILE;
     constexpr int WARPS = Smem::WARPS;
-    static_assert(BLOCK >= kRadix, "one look-back thread per digit");
+    constexpr int DPT = kRadix / BLOCK > 0 ? kRadix / BLOCK : 1;  // digits handled per thread when BLOCK < 256
+    static_assert(BLOCK >= kRadix || kRadix % BLOCK == 0, "digits map onto threads");
+    static_assert(IPT % 4 == 0, "items are ranked in batches of 4");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -172,13 +182,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const uint32_t valid = min((uint32_t)TILE, n - tile_base);
     const bool full = (valid == (uint32_t)TILE);
 
-    // ---- load: warp-striped so that (item, lane) order == memory order (stability) ----
+    // ---- load: warp-striped so that (item, lane) order == memory order (stability).  Full tiles
+    //      arrive as TMA bulk copies (keys and payload in flight together, one mbarrier) ----
     KeyT key[IPT];
     const uint32_t warp_base = warp * 32u * IPT;
     if (TMA && full) {
         if (tid == 0) {
-            mbar_expect_tx(&s.mbar, TILE * sizeof(KeyT));
+            mbar_expect_tx(&s.mbar, TILE * (sizeof(KeyT) + (PAIRS ? 4u : 0u)));
             tma_bulk_g2s(s.keys, keys_in + tile_base, TILE * sizeof(KeyT), &s.mbar);
+            if (PAIRS) tma_bulk_g2s(s.vals_in, vals_in + tile_base, TILE * 4u, &s.mbar);
         }
         mbar_wait(&s.mbar, 0);
 #pragma unroll
@@ -188,85 +200,136 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         for (int k = 0; k < IPT; ++k) {
             const uint32_t i = warp_base + k * 32 + lane;
             key[k] = (i < valid) ? keys_in[tile_base + i] : ~KeyT(0);  // pad sorts last, never written
+            if (PAIRS) s.vals_in[i] = (i < valid) ? vals_in[tile_base + i] : 0u;  // same thread reads it back
         }
     }
 
-    // ---- rank inside the warp with match.any (ballot of equal digits) ----
+    // ---- rank inside the warp: ballots of equal digits for all items first, then per item
+    //      one shared-memory atomic by the group leader for the running warp count ----
     uint32_t rank[IPT];
     uint32_t* wh = s.whist[warp];
     const uint32_t lt = lanemask_lt();
+    // peers of a lane = lanes holding the same digit: intersection of one ballot per digit bit
+    // (MATCH.ANY is an order of magnitude slower than 8 VOTEs on this part, profiles/r01_ncu_v3_onesweep.txt)
+    const int digit_bits = 32 - __clz(mask);  // warp-uniform; 8 except for a last partial digit
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t leader = 31u - __clz(peers);
-        uint32_t prev = 0;
-        if (lane == leader) { prev = wh[d]; wh[d] = prev + __popc(peers); }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[k] = prev + __popc(peers & lt);
-        __syncwarp();
+        uint32_t peers = 0xffffffffu;
+        if (digit_bits == kRadixBits) {
+#pragma unroll
+            for (int bit = 0; bit < kRadixBits; ++bit) {
+                const uint32_t sel = 0u - ((d >> bit) & 1u);  // all ones iff the bit is set
+                peers &= ~(__ballot_sync(0xffffffffu, sel != 0u) ^ sel);
+            }
+        } else {
+            for (int bit = 0; bit < digit_bits; ++bit) {
+                const uint32_t sel = 0u - ((d >> bit) & 1u);
+                peers &= ~(__ballot_sync(0xffffffffu, sel != 0u) ^ sel);
+            }
+        }
+        rank[k] = peers;
     }
-    __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
+#pragma unroll
+    for (int k0 = 0; k0 < IPT; k0 += 4) {
+        uint32_t prev[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t peers = rank[k0 + j];
+            prev[j] = 0;
+            if (lane == 31u - __clz(peers))
+                prev[j] = atomicAdd(&wh[digit_of<KeyT>(key[k0 + j], shift, mask)], (uint32_t)__popc(peers));
+            __syncwarp();  // item k's update is ordered before item k+1's
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t peers = rank[k0 + j];
+            rank[k0 + j] = __shfl_sync(0xffffffffu, prev[j], 31 - __clz(peers)) + __popc(peers & lt);
+        }
+    }
+    __syncthreads();  // all keys are in registers; s.keys / s.vals may be overwritten from here on
 
     // ---- per digit: exclusive offsets across warps, tile total, publish aggregate ----
-    uint32_t total = 0, incl = 0;
-    if (tid < kRadix) {
+    uint32_t total[DPT], incl[DPT];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const uint32_t d = tid * DPT + q;
+        total[q] = 0; incl[q] = 0;
+        if (d < kRadix) {
 #pragma unroll 4
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s.whist[w][tid];
-            s.whist[w][tid] = total;
-            total += c;
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s.whist[w][d];
+                s.whist[w][d] = total[q];
+                total[q] += c;
+            }
+            st_relaxed_u32(&status[(size_t)tile * kRadix + d], (tile == 0 ? kFlagIncl : kFlagAgg) | total[q]);
         }
-        st_relaxed_u32(&status[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagIncl : kFlagAgg) | total);
-        // scan of the 256 totals -> first tile-local slot of each digit (warp level here)
-        incl = total;
+    }
+    // scan of the 256 totals -> first tile-local slot of each digit
+    {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) { incl[q] = mine + total[q]; mine = incl[q]; }  // thread-local inclusive
+        uint32_t x = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
         }
-        if (lane == 31) s.scan_warp[warp] = incl;
-    }
-    __syncthreads();
-    if (tid < kRadix) {
-        uint32_t base = 0;
-        for (uint32_t i = 0; i < warp; ++i) base += s.scan_warp[i];
-        s.cta_ofs[tid] = base + incl - total;
+        if (lane == 31 && warp < kRadix / 32) s.scan_warp[warp] = x;
+        __syncthreads();
+        if (tid * DPT < kRadix) {
+            uint32_t base = x - mine;
+            for (uint32_t i = 0; i < warp; ++i) base += s.scan_warp[i];
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) s.cta_ofs[tid * DPT + q] = base + incl[q] - total[q];
+        }
     }
     __syncthreads();
 
-    // ---- reorder keys inside the tile through shared memory ----
+    // ---- decoupled look-back: one thread per digit, kLookBatch predecessors in flight per round.  Done before
+    //      the reorder so that the window between "aggregate published" and "inclusive published" --
+    //      which is what later tiles have to walk through -- is as short as possible ----
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const uint32_t d = tid * DPT + q;
+        if (d < kRadix) {
+            uint32_t before = 0;
+            if (tile > 0) {
+                int t = (int)tile - 1;
+                bool done = false;
+                while (!done) {
+                    uint32_t v[kLookBatch];
+#pragma unroll
+                    for (int j = 0; j < kLookBatch; ++j)
+                        v[j] = (t - j >= 0) ? ld_relaxed_u32(&status[(size_t)(t - j) * kRadix + d]) : kFlagIncl;
+                    int adv = 0;
+#pragma unroll
+                    for (int j = 0; j < kLookBatch; ++j) {
+                        if (!done && adv == j) {
+                            const uint32_t flag = v[j] & ~kValueMask;
+                            if (flag != 0) {  // published
+                                before += v[j] & kValueMask;
+                                ++adv;
+                                if (flag == kFlagIncl) done = true;
+                            }
+                        }
+                    }
+                    t -= adv;
+                }
+                st_relaxed_u32(&status[(size_t)tile * kRadix + d], kFlagIncl | (before + total[q]));
+            }
+            s.gofs[d] = gbase[d] + before - s.cta_ofs[d];
+        }
+    }
+
+    // ---- reorder keys (and payload) inside the tile through shared memory ----
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
         const uint32_t pos = s.cta_ofs[d] + wh[d] + rank[k];
         s.keys[pos] = key[k];
-        rank[k] = pos;
-    }
-    if (PAIRS) {
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const uint32_t i = warp_base + k * 32 + lane;
-            if (i < valid) s.vals[rank[k]] = __ldg(vals_in + tile_base + i);
-        }
-    }
-
-    // ---- decoupled look-back: one thread per digit ----
-    if (tid < kRadix) {
-        uint32_t prev = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            while (true) {
-                const uint32_t v = ld_relaxed_u32(&status[(size_t)t * kRadix + tid]);
-                const uint32_t flag = v & ~kValueMask;
-                if (flag == 0) continue;  // predecessor has not published yet
-                prev += v & kValueMask;
-                if (flag == kFlagIncl) break;
-                --t;
-            }
-            st_relaxed_u32(&status[(size_t)tile * kRadix + tid], kFlagIncl | (prev + total));
-        }
-        s.gofs[tid] = gbase[tid] + prev - s.cta_ofs[tid];
+        if (PAIRS) s.vals[pos] = s.vals_in[warp_base + k * 32 + lane];
     }
     __syncthreads();
 
@@ -327,8 +390,14 @@ __global__ void digitplace_scan_kernel(const uint32_t* __restrict__ in, uint32_t
 // host side
 // ---------------------------------------------------------------------------------------
 template <typename KeyT> struct SortCfg;
-template <> struct SortCfg<uint32_t> { static constexpr int BLOCK = 512, IPT = 16, MAX_PASSES = 4; };
-template <> struct SortCfg<uint64_t> { static constexpr int BLOCK = 512, IPT = 8, MAX_PASSES = 8; };
+#ifndef RTR_SORT_BLOCK
+#define RTR_SORT_BLOCK 512
+#endif
+#ifndef RTR_SORT_IPT
+#define RTR_SORT_IPT 12
+#endif
+template <> struct SortCfg<uint32_t> { static constexpr int BLOCK = RTR_SORT_BLOCK, IPT = RTR_SORT_IPT, MAX_PASSES = 4; };
+template <> struct SortCfg<uint64_t> { static constexpr int BLOCK = RTR_SORT_BLOCK, IPT = 8, MAX_PASSES = 8; };
 
 struct SortWs {
     void* keys_tmp;
