@@ -213,7 +213,7 @@ struct IterSmem {
 };
 __device__ __forceinline__ int perm_stage(int e) { return (e % kPP) * kStageQ + (e / kPP); }
 
-__global__ void __launch_bounds__(kPT)
+__global__ void __launch_bounds__(kPT, 1024 / kPT)
 ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                       uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
                       float4* __restrict__ node, uint32_t* __restrict__ isize,
@@ -233,13 +233,13 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
         return;
     }
     const uint32_t tiles = (n + kTileT - 1) / kTileT;
+    const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
+    uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
+    // tiles are handed out in start order, so the look-back below only ever waits on running tiles
     if (tid == 0) s.tile = atomicAdd(&cur->tile_counter, 1u);
     __syncthreads();
     const uint32_t tile = s.tile;
     if (tile >= tiles) return;
-
-    const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
-    uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
     const int t0 = (int)(tile * kTileT);
     const int base = t0 - 2 * kR;  // position of staged slot 0
 
@@ -470,47 +470,56 @@ __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t
     dst[2] = make_uint4(tri, left, right, slot);
 }
 
+// One inner cluster c at flat position p: writes its flat node, the flat nodes of its leaf children,
+// the positions of its inner children, and its child-pair record for the traversal kernels (both
+// children's boxes are on hand here, which saves re-reading the whole flat array afterwards).
 __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
                                             const float4* __restrict__ node,
                                             const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
-                                            rtr_node* __restrict__ flat) {
+                                            rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
     const uint32_t p = ipos[c - n_leaves];
     const Box bx_ = load_box(node, c); const float4 lo = bx_.lo, hi = bx_.hi;
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
-    const uint32_t size_l = L < n_leaves ? 1u : isize[L - n_leaves];
+    const bool lleaf = L < n_leaves, rleaf = R < n_leaves;
+    const Box bl = load_box(node, L), br = load_box(node, R);
+    const uint32_t size_l = lleaf ? 1u : isize[L - n_leaves];
     const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
     store_node(flat, p, lo, hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
-    if (L < n_leaves) {
-        const Box bl_ = load_box(node, L); const float4 llo = bl_.lo, lhi = bl_.hi;
-        store_node(flat, pos_l, llo, lhi, __float_as_uint(lhi.z), 0u, 0u, L);
-    } else {
-        ipos[L - n_leaves] = pos_l;
-    }
-    if (R < n_leaves) {
-        const Box br_ = load_box(node, R); const float4 rlo = br_.lo, rhi = br_.hi;
-        store_node(flat, pos_r, rlo, rhi, __float_as_uint(rhi.z), 0u, 0u, R);
-    } else {
-        ipos[R - n_leaves] = pos_r;
-    }
+    if (lleaf) store_node(flat, pos_l, bl.lo, bl.hi, __float_as_uint(bl.hi.z), 0u, 0u, L);
+    else ipos[L - n_leaves] = pos_l;
+    if (rleaf) store_node(flat, pos_r, br.lo, br.hi, __float_as_uint(br.hi.z), 0u, 0u, R);
+    else ipos[R - n_leaves] = pos_r;
+    // (L.min.xyz, L.max.x) (L.max.yz, R.min.xy) (R.min.z, R.max.xyz) (L.word, R.word, L.aux, R.aux)
+    float* dst = reinterpret_cast<float*>(pairs + (size_t)p * 4);
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(dst), "f"(bl.lo.x), "f"(bl.lo.y), "f"(bl.lo.z), "f"(bl.lo.w), "f"(bl.hi.x), "f"(bl.hi.y),
+                   "f"(br.lo.x), "f"(br.lo.y) : "memory");
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(dst + 8), "f"(br.lo.z), "f"(br.lo.w), "f"(br.hi.x), "f"(br.hi.y),
+                   "f"(__uint_as_float(lleaf ? (0x80000000u | pos_l) : pos_l)),
+                   "f"(__uint_as_float(rleaf ? (0x80000000u | pos_r) : pos_r)),
+                   "f"(__uint_as_float(lleaf ? L : 0u)), "f"(__uint_as_float(rleaf ? R : 0u)) : "memory");
 }
 
 __global__ void __launch_bounds__(256)
 flatten_level_kernel(uint32_t first, uint32_t count, uint32_t n_leaves,
                      const float4* __restrict__ node,
-                     const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat) {
+                     const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat,
+                     uint4* __restrict__ pairs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) flatten_one(first + i, n_leaves, node, isize, ipos, flat);
+    if (i < count) flatten_one(first + i, n_leaves, node, isize, ipos, flat, pairs);
 }
 
 // levels [it_lo, it_hi] processed last-first by one CTA (the top of the tree: many tiny levels)
 __global__ void __launch_bounds__(1024)
 flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_hi, int it_lo, uint32_t n_leaves,
                             const float4* __restrict__ node,
-                            const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat) {
+                            const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat,
+                            uint4* __restrict__ pairs) {
     for (int it = it_hi; it >= it_lo; --it) {
         const uint32_t first = iter_first_id[it], count = iter_first_id[it + 1] - first;
         for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
-            flatten_one(first + i, n_leaves, node, isize, ipos, flat);
+            flatten_one(first + i, n_leaves, node, isize, ipos, flat, pairs);
         __syncthreads();
     }
 }
@@ -698,7 +707,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             if (count > kSmall) {
                 RTR_PROF(ctx, "flatten_level_kernel");
                 flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node,
-                                                                                   b->isize, b->ipos, b->flat);
+                                                                                   b->isize, b->ipos, b->flat, b->pairs);
                 RTR_LAUNCH_CHECK(ctx);
                 --it;
             } else {
@@ -706,19 +715,13 @@ int rtr_bvh_run_build(rtr_bvh* b) {
                 while (lo - 1 >= 0 && b->h_first_id[lo] - b->h_first_id[lo - 1] <= kSmall) --lo;
                 RTR_PROF(ctx, "flatten_small_levels_kernel");
                 flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node,
-                                                                         b->isize, b->ipos, b->flat);
+                                                                         b->isize, b->ipos, b->flat, b->pairs);
                 RTR_LAUNCH_CHECK(ctx);
                 it = lo - 1;
             }
         }
     }
-    {   // child-pair records of the default traversal (part of the flatten stage time)
-        const uint32_t nc = 2 * n - 1;
-        RTR_PROF(ctx, "pack_pairs_kernel");
-        pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat, nc, 1u, b->pairs);
-        RTR_LAUNCH_CHECK(ctx);
-        b->pairs_view = b->pairs;
-    }
+    b->pairs_view = b->pairs;  // written by the flatten kernels
     RTR_CHECK(record(b, 5));
     b->flat_view = b->flat;
     b->wtri_view = b->wtri;
