@@ -1,0 +1,47 @@
+"""The C++ side of the boundary: the re-hosted tests/testsSortGPU executables and the cr::BVH shim
+(include/rtr_scene.hpp) compile with plain g++ against the C ABI (CPU check), and pass on a B200 (GPU check)."""
+import os
+import subprocess
+
+import pytest
+
+from realtimeraytracing_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "tests", "testsSortGPU")
+TESTS = ["testHistogramCreation", "testHistogramPrefixSum", "testRadixSort", "testBvhShim"]
+
+
+@pytest.fixture(scope="module")
+def executables():
+    build.build()
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    out = subprocess.run(["make", "-C", HARNESS, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return {t: os.path.join(HARNESS, "build", t) for t in TESTS}
+
+
+def test_cpp_harness_compiles_and_links(executables):
+    for t, path in executables.items():
+        assert os.path.exists(path), t
+        needed = subprocess.check_output(["readelf", "-d", path], text=True)
+        assert "librtr_b200.so" in needed, t  # bound to the C ABI library, nothing else of ours
+
+
+def test_cpp_harness_fails_loudly_without_a_device(executables):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    r = subprocess.run([executables["testHistogramCreation"]], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TESTS)
+def test_cpp_harness_passes_on_gpu(executables, name):
+    r = subprocess.run([executables[name]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

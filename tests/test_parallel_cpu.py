@@ -1,0 +1,102 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 (and 3) gloo process groups exercise exactly the partition
+/ broadcast / gather code of realtimeraytracing_b200.parallel that bench.py runs over NCCL:
+the build result is replicated by broadcast, image row blocks are dealt round-robin and all-gathered."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from realtimeraytracing_b200 import parallel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_row_blocks_tile_the_image():
+    for height, rpb in ((2160, 16), (1072, 16), (67, 16), (5, 8), (16, 16)):
+        blocks = parallel.row_blocks(height, rpb)
+        assert blocks[0][0] == 0 and blocks[-1][1] == height
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_every_row_has_exactly_one_owner(world):
+    height, rpb = 2160, 16
+    seen = np.zeros(height, dtype=np.int32)
+    for rank in range(world):
+        rows = parallel.rows_of_rank(height, rank, world, rpb)
+        seen[rows] += 1
+        assert parallel.pixels_of_rank(3840, height, rank, world, rpb) == rows.size * 3840
+    assert (seen == 1).all()
+    # same dealing as RowMap in csrc/trace.cu: block b -> rank b % world
+    for b, (r0, _) in enumerate(parallel.row_blocks(height, rpb)):
+        assert r0 in parallel.rows_of_rank(height, b % world, world, rpb)
+
+
+def test_balance_is_within_one_block():
+    for world in (2, 4, 8):
+        sizes = [parallel.rows_of_rank(2160, r, world, 16).size for r in range(world)]
+        assert max(sizes) - min(sizes) <= 16
+
+
+def test_bad_arguments():
+    with pytest.raises(ValueError):
+        parallel.row_blocks(0, 16)
+    with pytest.raises(ValueError):
+        parallel.blocks_of_rank(64, 2, 2, 16)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, height, width, rpb, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from realtimeraytracing_b200 import parallel as par
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. the build result exists on rank 0 only and is replicated by broadcast
+        n_nodes = 2 * 1000 - 1
+        flat = torch.zeros(n_nodes * 12, dtype=torch.int32)
+        tris = torch.zeros(1000 * 16, dtype=torch.int32)
+        if rank == 0:
+            flat = torch.arange(n_nodes * 12, dtype=torch.int32)
+            tris = torch.arange(1000 * 16, dtype=torch.int32) * 3
+        par.broadcast_arrays([flat, tris], src=0)
+        assert int(flat[-1]) == n_nodes * 12 - 1 and int(tris[5]) == 15
+        # 2. every rank "renders" its own row blocks into a full-size image (value = f(row, col, owner))
+        image = torch.full((height, width), -1.0)
+        for r0, r1 in par.blocks_of_rank(height, rank, world, rpb):
+            rows = torch.arange(r0, r1, dtype=torch.float32).unsqueeze(1)
+            cols = torch.arange(width, dtype=torch.float32).unsqueeze(0)
+            image[r0:r1] = rows * 1000.0 + cols + 0.25 * rank
+        # 3. all-gather of the row blocks: afterwards every rank holds the whole frame
+        par.gather_rows(image, height, rpb)
+        rows = torch.arange(height, dtype=torch.float32).unsqueeze(1)
+        cols = torch.arange(width, dtype=torch.float32).unsqueeze(0)
+        owner = torch.tensor([par.owner_of_block(r // rpb, world) for r in range(height)], dtype=torch.float32).unsqueeze(1)
+        assert torch.equal(image, rows * 1000.0 + cols + 0.25 * owner)
+        # 4. whole-job ray count = sum over ranks (what bench.py all-reduces)
+        mine = torch.tensor([par.pixels_of_rank(width, height, rank, world, rpb)], dtype=torch.int64)
+        dist.all_reduce(mine)
+        assert int(mine) == width * height
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height", [(2, 80), (2, 67), (3, 100)])
+def test_broadcast_and_row_gather_over_gloo(tmp_path, world, height):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, height, 24, 16, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
