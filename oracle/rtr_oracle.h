@@ -8,7 +8,7 @@
  *
  * Parity status: the build half (Morton codes, pair sort, PLOC topology,
  * flatten) is PINNED against the reference's own bvh.cpp/triangle.cpp compiled
- * unmodified into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_vs_ref.py)
+ * unmodified into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_golden_cpu.py)
  * and against the committed fixtures in tests/golden/ generated from that build.
  * The sort pre-pass helpers are pinned against the known-answer vectors of the
  * reference's tests/testsSortGPU.  The traversal half restates raytracer.glsl,

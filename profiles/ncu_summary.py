@@ -70,6 +70,48 @@ def summarise(path):
             if key in hdr:
                 i = hdr.index(key)
                 print("   %-24s %s %s" % (label, r[i], units[i]))
+        # warp-state sampling: share of each stall reason
+        pre = "smsp__pcsamp_warps_issue_stalled_"
+        samp = [(c[len(pre):], float(r[i])) for i, c in enumerate(hdr) if c.startswith(pre) and not c.endswith("not_issued")]
+        tot = sum(v for _, v in samp) or 1.0
+        print("   stall reasons (share of samples): " + ", ".join(
+            "%s %.1f%%" % (k, 100.0 * v / tot) for k, v in sorted(samp, key=lambda kv: -kv[1]) if v / tot > 0.03))
+
+
+def opcodes(path, top=14):
+    """stall samples and executed warp instructions by SASS opcode (first kernel of the report)"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, tab = None, []
+    for r in rows:
+        if "Source" in r and hdr is None:
+            hdr = r
+            continue
+        if hdr and "Source" in r:
+            break  # next kernel
+        if hdr and len(r) == len(hdr):
+            tab.append(r)
+    if not hdr:
+        return
+    si, ci, ii = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+
+    def num(x):
+        try:
+            return float(x.replace(",", ""))
+        except ValueError:
+            return 0.0
+    st, ins = {}, {}
+    for r in tab:
+        parts = r[si].split()
+        if not parts:
+            continue
+        op = (parts[1] if parts[0].startswith("@") and len(parts) > 1 else parts[0]).split(".")[0]
+        st[op] = st.get(op, 0.0) + num(r[ci])
+        ins[op] = ins.get(op, 0.0) + num(r[ii])
+    ts, ti = sum(st.values()) or 1.0, sum(ins.values()) or 1.0
+    print("   by opcode (stall-sample share / executed-instruction share), %d warp instructions:" % ti)
+    for op, v in sorted(st.items(), key=lambda kv: -kv[1])[:top]:
+        print("     %-8s %5.1f%% / %5.1f%%" % (op, 100.0 * v / ts, 100.0 * ins[op] / ti))
 
 
 def stalls(path, top=25):
@@ -107,5 +149,7 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     for p in args:
         summarise(p)
+        if "--ops" in sys.argv:
+            opcodes(p)
         if "--stalls" in sys.argv:
             stalls(p)
