@@ -19,7 +19,12 @@ struct TraceParams {
 };
 
 constexpr uint32_t kMaxPlocIterations = 1u << 16;
-constexpr int kPlocTile = 480;  // positions decided per CTA of ploc_iteration_kernel (ploc.cu)
+#ifndef RTR_PLOC_WARPS
+#define RTR_PLOC_WARPS 4
+#endif
+// positions decided per CTA of ploc_iteration_kernel (ploc.cu): every warp finds the nearest neighbour of
+// 112 positions, the first and last 16 of the CTA's range only serve the mutual-pair test of the others
+constexpr int kPlocTile = 112 * RTR_PLOC_WARPS - 32;
 
 struct rtr_bvh {
     rtr_ctx* ctx = nullptr;

@@ -12,34 +12,42 @@
 //   cin/cout   = active cluster ids in Morton order (the reference's C_In/C_Out)
 //
 // One kernel per PLOC iteration (ploc_iteration_kernel), NN search + merge + prefix scan + compaction
-// of the reference fused into one pass over the active list.  A CTA decides a tile of 480 positions;
-// it stages the ids and boxes of the tile plus a 32-position halo on each side in shared memory
-// (float4 + float2 per box, interleaved so that no access pattern below has bank conflicts), every
-// thread owns kPP consecutive positions whose boxes it keeps in registers, reads each neighbour box of
-// its +-16 window once and tries it against all of them: argmin of the merged surface area in
-// ascending j with strict '<', i.e. lowest j on ties (bvh.cpp:199-208), every fp32 op individually
-// rounded in the reference's order.  Mutual pairs are ranked with a CTA scan + decoupled look-back
-// across tiles: merged nodes go to id = total + rank (== the reference's serial counter, Q3) and
-// survivors are compacted in place order.  The iteration count is data dependent, so the loop state
-// lives on the device (PlocState, double buffered by launch parity) and launches that find
-// n_active <= kTailN are no-ops; a single-CTA tail kernel finishes the last <= 1024 clusters entirely
-// in shared memory (PLOC++ 4.4).
+// of the reference fused into one pass over the active list.  A CTA stages the ids and boxes of its tile
+// plus a 32-position halo on each side in shared memory (float4 + float2 per box, interleaved so that no
+// access pattern below has bank conflicts); every thread owns 4 consecutive positions whose boxes it keeps
+// in registers.  The merged surface area is symmetric, so each pair inside the +-16 window is evaluated
+// once, by the thread owning its lower position; the other end receives the column minima by warp shuffle
+// (see the kernel).  The result is the reference's argmin in ascending j with strict '<', i.e. lowest j on
+// ties (bvh.cpp:199-208), every fp32 op individually rounded in the reference's order.  Mutual pairs are
+// ranked with a CTA scan + decoupled look-back across tiles: merged nodes go to id = total + rank (== the
+// reference's serial counter, Q3) and survivors are compacted in place order.  The iteration count is data
+// dependent, so the loop state lives on the device (PlocState, double buffered by launch parity) and
+// launches that find n_active <= kTailN are no-ops; a single-CTA tail kernel finishes the last <= 1024
+// clusters entirely in shared memory (PLOC++ 4.4).
 #include "bvh.cuh"
 
 namespace {
 
 constexpr int kR = RTR_MAX_SEARCH_RADIUS;       // 16
-#ifndef RTR_PLOC_PP
-#define RTR_PLOC_PP 4
+constexpr int kPP = 4;                           // consecutive positions per thread
+constexpr int kHaloLanes = kR / kPP;             // lanes 0..3 of a warp repeat the last 16 positions of the warp before
+constexpr int kWarps = RTR_PLOC_WARPS;
+#ifndef RTR_PLOC_ROLL
+#define RTR_PLOC_ROLL 0   // 1: the three full 4x4 blocks of the pair matrix run as a loop (a third of the code)
 #endif
-constexpr int kPP = RTR_PLOC_PP;                 // positions per thread
-constexpr int kPT = 512 / kPP;                   // threads per CTA
-constexpr int kEval = kPT * kPP;                 // 512 positions whose nearest neighbour a CTA computes
-constexpr int kTileT = kPlocTile;                // 480 positions decided per CTA (= kEval - 2 kR)
-constexpr int kStage = kEval + 2 * kR;           // 544 positions staged (tile + 2 kR halo each side)
+#ifndef RTR_PLOC_MINB
+#define RTR_PLOC_MINB (768 / (32 * RTR_PLOC_WARPS))  // resident CTAs per SM the register budget is cut for
+#endif
+constexpr int kPT = 32 * kWarps;                 // threads per CTA
+constexpr int kWarpSpan = (32 - kHaloLanes) * kPP;  // 112 positions per warp get their nearest neighbour
+constexpr int kEval = kWarpSpan * kWarps;        // positions whose nearest neighbour a CTA computes: staged [kR, kR + kEval)
+constexpr int kTileT = kPlocTile;                // positions decided per CTA: staged [2 kR, kEval)
+constexpr int kStage = kEval + 2 * kR;           // positions staged (tile + 2 kR halo each side)
 constexpr int kStageQ = kStage / kPP;            // staged arrays are stored [e % kPP][e / kPP] (conflict free)
+constexpr int kStagePT = (kStage + kPT - 1) / kPT;  // staged positions gathered per thread
 constexpr uint32_t kTailN = 1024;
 constexpr int kChunk = 8;                        // iteration launches between host checks
+static_assert(kR % kPP == 0 && kR == 16 && kPP == 4, "search geometry is written for +-16 and 4 positions per thread");
 static_assert(kTileT == kEval - 2 * kR, "tile geometry");
 static_assert(kStage % kPP == 0, "staging layout");
 
@@ -213,7 +221,46 @@ struct IterSmem {
 };
 __device__ __forceinline__ int perm_stage(int e) { return (e % kPP) * kStageQ + (e / kPP); }
 
-__global__ void __launch_bounds__(kPT, 1024 / kPT)
+// One block of the pair matrix: own positions e0+a (a = 0..3) x the positions e0 + 4 dl + x of lane + dl.
+// LAST_LANE_BLOCK (dl = 4): only the pairs at distance 16 + x - a <= 16 exist.
+template <bool FULL, bool LAST_LANE_BLOCK, typename Smem>
+__device__ __forceinline__ void search_block(const Smem& s, int dl, int e0, int radius,
+                                             const float4 (&lo)[kPP], const float2 (&hi)[kPP],
+                                             float (&fbest)[kPP], int (&fj)[kPP], float (&bbest)[kPP], int (&bj)[kPP]) {
+    float4 xlo[kPP]; float2 xhi[kPP];
+    const int ex = e0 + kPP * dl;
+#pragma unroll
+    for (int x = 0; x < kPP; ++x) {
+        const int pe = x * kStageQ + ex / kPP;  // perm_stage(ex + x): ex is a multiple of kPP
+        xlo[x] = s.lo[pe];
+        xhi[x] = s.hi[pe];
+    }
+    float cv[kPP]; int ca[kPP];
+#pragma unroll
+    for (int x = kPP - 1; x >= 0; --x) {
+        cv[x] = INFINITY; ca[x] = 0;
+#pragma unroll
+        for (int a = 0; a < kPP; ++a) {
+            if (!LAST_LANE_BLOCK || x <= a) {
+                float d = pair_half_area(lo[a], hi[a], xlo[x], xhi[x]);
+                if (!FULL) d = (kPP * dl + x - a <= radius) ? d : INFINITY;
+                if (d <= fbest[a]) { fbest[a] = d; fj[a] = ex + x; }   // candidates above come in descending j
+                if (d < cv[x]) { cv[x] = d; ca[x] = a; }               // ascending a: lowest a among equal minima
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < kPP; ++x) {  // candidates below come in ascending j (dl descending)
+        const float rv = __shfl_up_sync(0xffffffffu, cv[x], dl);
+        const int ra = __shfl_up_sync(0xffffffffu, ca[x], dl);
+        if (rv < bbest[x]) { bbest[x] = rv; bj[x] = e0 - kPP * dl + ra; }
+    }
+}
+
+// FULL: radius == 16, the reference's PlocParams::_SEARCH_RADIUS (bvh.hpp:66); otherwise candidates farther
+// than `radius` positions away are masked out.
+template <bool FULL>
+__global__ void __launch_bounds__(kPT, RTR_PLOC_MINB)
 ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                       uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
                       float4* __restrict__ node, uint32_t* __restrict__ isize,
@@ -243,57 +290,94 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     const int t0 = (int)(tile * kTileT);
     const int base = t0 - 2 * kR;  // position of staged slot 0
 
-    // ---- stage ids + boxes of the tile and its halo (one 32-byte gather per position) ----
-    for (int e = tid; e < kStage; e += kPT) {
-        const int pos = base + e;
-        const int pe = perm_stage(e);
-        if (pos >= 0 && pos < (int)n) {
-            const uint32_t id = cin[pos];
-            const Box b = load_box(node, id);
-            s.id[pe] = id;
-            s.lo[pe] = b.lo;
-            s.hi[pe] = make_float2(b.hi.x, b.hi.y);
-        } else {
-            s.id[pe] = RTR_NONE;
+    // ---- stage ids + boxes of the tile and its halo (one 32-byte gather per position; all ids first, then
+    //      all boxes, so that a thread has its kStagePT gathers in flight together).  Slots outside the
+    //      active list get the box (-inf, +inf): every merged area with it is +inf, which never wins ----
+    {
+        uint32_t sid[kStagePT];
+#pragma unroll
+        for (int r = 0; r < kStagePT; ++r) {
+            const int e = tid + r * kPT, pos = base + e;
+            sid[r] = (e < kStage && pos >= 0 && pos < (int)n) ? cin[pos] : RTR_NONE;
+        }
+        Box sb[kStagePT];
+#pragma unroll
+        for (int r = 0; r < kStagePT; ++r) {
+            if (sid[r] != RTR_NONE) sb[r] = load_box(node, sid[r]);
+            else { sb[r].lo = make_float4(-INFINITY, -INFINITY, -INFINITY, INFINITY); sb[r].hi = make_float4(INFINITY, INFINITY, 0.f, 0.f); }
+        }
+#pragma unroll
+        for (int r = 0; r < kStagePT; ++r) {
+            const int e = tid + r * kPT;
+            if (e < kStage) {
+                const int pe = perm_stage(e);
+                s.id[pe] = sid[r];
+                s.lo[pe] = sb[r].lo;
+                s.hi[pe] = make_float2(sb[r].hi.x, sb[r].hi.y);
+            }
         }
     }
     __syncthreads();
 
-    // ---- nearest neighbour of the kPP positions this thread owns: staged e0 .. e0 + kPP - 1 ----
-    // Every neighbour box is read once and tried against all kPP own boxes; j ascending means
-    // ascending candidate position for each own position, strict '<' keeps the lowest on ties.
-    const int e0 = kR + kPP * tid;  // staged index; positions [t0 - kR, t0 + kTileT + kR)
-    float4 lo[kPP]; float2 hi[kPP]; bool ok[kPP];
+    // ---- nearest neighbour (plocNearestNeighborSearch, bvh.cpp:193-210) of the kPP positions this thread
+    //      owns, staged e0 .. e0+3.  The merged area is symmetric, so every pair is evaluated ONCE, by the
+    //      thread that owns its lower position: block dl = own 4 positions x the 4 positions of lane + dl
+    //      (dl = 4..1; dl = 4 only holds the 10 pairs at distance <= 16).  Row minima serve the own
+    //      positions (their candidates above), column minima go to lane + dl by shuffle (its candidates
+    //      below).  The reference scans j ascending with strict '<', i.e. it returns the LOWEST j among the
+    //      minima: candidates above arrive in descending j and replace on '<=', candidates below arrive in
+    //      ascending j and replace on '<', and the lower side wins a tie between the two.  Lanes 0..3 of a
+    //      warp own the same positions as lanes 28..31 of the warp before (no candidates from below reach
+    //      them): they only produce column minima. ----
+    const int lane = tid & 31, warp = tid >> 5;
+    const int e0 = kWarpSpan * warp + kPP * lane;  // staged index of the first own position
+    float4 lo[kPP]; float2 hi[kPP];
 #pragma unroll
     for (int i = 0; i < kPP; ++i) {
         const int pe = perm_stage(e0 + i);
         lo[i] = s.lo[pe];
         hi[i] = s.hi[pe];
-        const int pos = base + e0 + i;
-        ok[i] = pos >= 0 && pos < (int)n;
     }
-    float best[kPP]; int bj[kPP];
+    float fbest[kPP], bbest[kPP]; int fj[kPP], bj[kPP];  // best candidate above / below
 #pragma unroll
-    for (int i = 0; i < kPP; ++i) { best[i] = INFINITY; bj[i] = -1; }
+    for (int i = 0; i < kPP; ++i) { fbest[i] = bbest[i] = INFINITY; fj[i] = bj[i] = -1; }
+    search_block<FULL, true>(s, kHaloLanes, e0, radius, lo, hi, fbest, fj, bbest, bj);
+#if RTR_PLOC_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
-    for (int j = -kR; j < kPP + kR; ++j) {  // neighbour at staged position e0 + j
-        float4 xlo; float2 xhi;
-        if (j >= 0 && j < kPP) { xlo = lo[j]; xhi = hi[j]; }
-        else { const int pe = perm_stage(e0 + j); xlo = s.lo[pe]; xhi = s.hi[pe]; }
-        const int xpos = base + e0 + j;
-        const bool xok = xpos >= 0 && xpos < (int)n;
+#endif
+    for (int dl = kHaloLanes - 1; dl >= 1; --dl)
+        search_block<FULL, false>(s, dl, e0, radius, lo, hi, fbest, fj, bbest, bj);
+    {   // the 6 pairs inside the thread
+        float dloc[kPP][kPP];
+#pragma unroll
+        for (int a = 0; a < kPP; ++a)
+#pragma unroll
+            for (int x = a + 1; x < kPP; ++x) {
+                float d = pair_half_area(lo[a], hi[a], lo[x], hi[x]);
+                if (!FULL) d = (x - a <= radius) ? d : INFINITY;
+                dloc[a][x] = d;
+            }
+#pragma unroll
+        for (int a = 0; a < kPP; ++a)
+#pragma unroll
+            for (int x = kPP - 1; x > a; --x)
+                if (dloc[a][x] <= fbest[a]) { fbest[a] = dloc[a][x]; fj[a] = e0 + x; }
+#pragma unroll
+        for (int x = 1; x < kPP; ++x)
+#pragma unroll
+            for (int a = 0; a < x; ++a)
+                if (dloc[a][x] < bbest[x]) { bbest[x] = dloc[a][x]; bj[x] = e0 + a; }
+    }
+    if (lane >= kHaloLanes) {
 #pragma unroll
         for (int i = 0; i < kPP; ++i) {
-            const int k = j - i;
-            if (k != 0 && k >= -kR && k <= kR) {
-                const float d = pair_half_area(lo[i], hi[i], xlo, xhi);
-                const bool cand = xok && (k < 0 ? -k : k) <= radius;
-                if (cand && d < best[i]) { best[i] = d; bj[i] = e0 + j; }
-            }
+            const bool below = bbest[i] <= fbest[i];
+            const float best = below ? bbest[i] : fbest[i];
+            s.nn[e0 + i - kR] = (best < INFINITY) ? (below ? bj[i] : fj[i]) : -1;  // all inf/NaN: no neighbour (Q4)
         }
     }
-#pragma unroll
-    for (int i = 0; i < kPP; ++i) s.nn[kPP * tid + i] = ok[i] ? bj[i] : -1;
     __syncthreads();
 
     // ---- mutual pairs (plocMerging, bvh.cpp:159-165): lo = lower partner, hi = removed partner ----
@@ -303,7 +387,7 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     for (int i = 0; i < kPP; ++i) {
         const int q = e0 + i;  // staged index
         is_lo[i] = is_hi[i] = false; partner[i] = -1;
-        const bool in_tile = q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
+        const bool in_tile = lane >= kHaloLanes && q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
         if (in_tile) {
             const int j = s.nn[q - kR];
             if (j >= 0 && s.nn[j - kR] == q) { is_lo[i] = q < j; is_hi[i] = q > j; partner[i] = j; }
@@ -350,7 +434,7 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
 #pragma unroll
     for (int i = 0; i < kPP; ++i) {
         const int q = e0 + i;
-        const bool in_tile = q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
+        const bool in_tile = lane >= kHaloLanes && q >= 2 * kR && q < 2 * kR + kTileT && (base + q) < (int)n;
         if (in_tile) {
             uint32_t out_id = s.id[perm_stage(q)];
             if (is_lo[i]) {
@@ -654,7 +738,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         const uint32_t tiles = (bound_n + kTileT - 1) / kTileT;
         for (int k = 0; k < kChunk; ++k) {
             RTR_PROF(ctx, "ploc_iteration_kernel");
-            ploc_iteration_kernel<<<tiles, kPT, 0, ctx->stream>>>(
+            auto kern = (radius == kR) ? ploc_iteration_kernel<true> : ploc_iteration_kernel<false>;
+            kern<<<tiles, kPT, 0, ctx->stream>>>(
                 launch_idx, n, radius, b->cin, b->cout, b->node, b->isize, b->state, b->tile_status,
                 b->trace_active, b->trace_merges, b->iter_first_id);
             RTR_LAUNCH_CHECK(ctx);

@@ -26,6 +26,9 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr uint32_t kFlagAgg = 1u << 30;   // tile aggregate available
 constexpr uint32_t kFlagIncl = 2u << 30;  // inclusive prefix available
 constexpr uint32_t kValueMask = (1u << 30) - 1;
+#ifndef RTR_SORT_MINB
+#define RTR_SORT_MINB 2   // resident CTAs per SM the register budget is cut for
+#endif
 #ifndef RTR_SORT_LOOKBATCH
 #define RTR_SORT_LOOKBATCH 16
 #endif
@@ -136,23 +139,51 @@ radix_scan_kernel(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ gba
 // ---------------------------------------------------------------------------------------
 // one Onesweep digit pass
 // ---------------------------------------------------------------------------------------
+// (u32 key, u32 payload) pairs travel through the in-tile reorder as one 64-bit shared-memory slot
+template <typename KeyT, bool PAIRS> struct SortPacked { static constexpr bool value = PAIRS && sizeof(KeyT) == 4; };
+
 template <typename KeyT, bool PAIRS, int BLOCK, int IPT>
 struct OnesweepSmem {
     static constexpr int TILE = BLOCK * IPT;
     static constexpr int WARPS = BLOCK / 32;
-    alignas(128) KeyT keys[TILE];
-    alignas(128) uint32_t vals_in[PAIRS ? TILE : 4];   // payload as loaded (TMA destination)
-    alignas(128) uint32_t vals[PAIRS ? TILE : 4];      // payload in tile-sorted order
-    uint32_t whist[WARPS][kRadix];  // per-warp digit counts, then warp-exclusive offsets
-    uint32_t cta_ofs[kRadix];       // first tile-local slot of each digit
-    uint32_t gofs[kRadix];          // global slot of digit's first key of this tile, minus cta_ofs
+    static constexpr bool PACKED = SortPacked<KeyT, PAIRS>::value;
+    // keys as loaded (TMA destination, first TILE entries), later keys -- or (key, payload) slots when
+    // PACKED -- in tile-sorted order
+    alignas(128) KeyT keys[PACKED ? 2 * TILE : TILE];
+    alignas(128) uint32_t vals_in[PAIRS ? TILE : 4];              // payload as loaded (TMA destination)
+    alignas(128) uint32_t vals[(PAIRS && !PACKED) ? TILE : 4];    // payload in tile-sorted order
+    uint32_t whist[WARPS][kRadix];  // per-warp running digit counts, then first tile-local slot of (warp, digit)
+    uint32_t gofs[kRadix];          // global slot of the digit's first key of this tile, minus its tile-local slot
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t mbar;
     uint32_t tile;
 };
 
+// lanes of the warp holding the same 8-bit digit as the caller: one ballot per digit bit, each narrowing
+// the set (R2P + 8 VOTE + 16 predicated LOP3 in SASS; MATCH.ANY is ~10x slower on sm_100)
+__device__ __forceinline__ uint32_t digit_peers8(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit < kRadixBits; ++bit) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, b, nb;\n\t"
+                     "and.b32 t, %1, %2;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+                     "not.b32 nb, b;\n\t"
+                     "@p and.b32 %0, %0, b;\n\t"
+                     "@!p and.b32 %0, %0, nb;\n\t}"
+                     : "+r"(peers) : "r"(d), "r"(1u << bit));
+    }
+    return peers;
+}
+__device__ __forceinline__ uint32_t lanemask_gt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+    return m;
+}
+
 template <typename KeyT, bool PAIRS, int BLOCK, int IPT, bool TMA>
-__global__ void __launch_bounds__(BLOCK, (BLOCK <= 256 ? 1024 : 1024) / BLOCK)
+__global__ void __launch_bounds__(BLOCK, RTR_SORT_MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 uint32_t n, uint32_t num_tiles, int shift, uint32_t mask,
@@ -162,9 +193,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     using Smem = OnesweepSmem<KeyT, PAIRS, BLOCK, IPT>;
     constexpr int TILE = Smem::TILE;
     constexpr int WARPS = Smem::WARPS;
-    constexpr int DPT = kRadix / BLOCK > 0 ? kRadix / BLOCK : 1;  // digits handled per thread when BLOCK < 256
-    static_assert(BLOCK >= kRadix || kRadix % BLOCK == 0, "digits map onto threads");
-    static_assert(IPT % 4 == 0, "items are ranked in batches of 4");
+    constexpr bool PACKED = Smem::PACKED;
+    static_assert(BLOCK >= kRadix && BLOCK % 32 == 0, "one thread per digit");
+    static_assert(TILE < (1 << 16), "tile-local slots are kept in 16 bits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -204,144 +235,134 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         }
     }
 
-    // ---- rank inside the warp: ballots of equal digits for all items first, then per item
-    //      one shared-memory atomic by the group leader for the running warp count ----
+    // ---- rank inside the warp.  peers = lanes with the same digit; the key's slot among the warp's keys of
+    //      that digit = running count of the earlier items (shared memory, bumped by the highest peer lane)
+    //      + peers below.  rank[k] ends as (digit << 16 | slot) ----
     uint32_t rank[IPT];
     uint32_t* wh = s.whist[warp];
-    const uint32_t lt = lanemask_lt();
-    // peers of a lane = lanes holding the same digit: intersection of one ballot per digit bit
-    // (MATCH.ANY is an order of magnitude slower than 8 VOTEs on this part, profiles/r01_ncu_v3_onesweep.txt)
-    const int digit_bits = 32 - __clz(mask);  // warp-uniform; 8 except for a last partial digit
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
-        uint32_t peers = 0xffffffffu;
-        if (digit_bits == kRadixBits) {
-#pragma unroll
-            for (int bit = 0; bit < kRadixBits; ++bit) {
-                const uint32_t sel = 0u - ((d >> bit) & 1u);  // all ones iff the bit is set
-                peers &= ~(__ballot_sync(0xffffffffu, sel != 0u) ^ sel);
-            }
-        } else {
-            for (int bit = 0; bit < digit_bits; ++bit) {
-                const uint32_t sel = 0u - ((d >> bit) & 1u);
-                peers &= ~(__ballot_sync(0xffffffffu, sel != 0u) ^ sel);
-            }
-        }
-        rank[k] = peers;
-    }
+    const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
 #pragma unroll
     for (int k0 = 0; k0 < IPT; k0 += 4) {
-        uint32_t prev[4];
+        uint32_t peers[4], dg[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t peers = rank[k0 + j];
-            prev[j] = 0;
-            if (lane == 31u - __clz(peers))
-                prev[j] = atomicAdd(&wh[digit_of<KeyT>(key[k0 + j], shift, mask)], (uint32_t)__popc(peers));
-            __syncwarp();  // item k's update is ordered before item k+1's
+            dg[j] = digit_of<KeyT>(key[k0 + j], shift, mask);
+            peers[j] = digit_peers8(dg[j]);  // bits above a last partial digit are 0 in every lane: their ballots narrow nothing
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t peers = rank[k0 + j];
-            rank[k0 + j] = __shfl_sync(0xffffffffu, prev[j], 31 - __clz(peers)) + __popc(peers & lt);
+            const uint32_t below = __popc(peers[j] & lt);
+            const uint32_t cnt = wh[dg[j]];                              // every peer reads the same word ...
+            if ((peers[j] & gt) == 0u) wh[dg[j]] = cnt + below + 1u;     // ... before the last one bumps it
+            __syncwarp();                                                // item k's bump is ordered before item k+1's read
+            rank[k0 + j] = (dg[j] << 16) | (cnt + below);
         }
     }
-    __syncthreads();  // all keys are in registers; s.keys / s.vals may be overwritten from here on
+    __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
 
-    // ---- per digit: exclusive offsets across warps, tile total, publish aggregate ----
-    uint32_t total[DPT], incl[DPT];
+    // ---- per digit (threads 0..255): counts of the warps -> tile total -> published aggregate; exclusive scan
+    //      over digits -> first tile-local slot of every (warp, digit); decoupled look-back ----
+    uint32_t total = 0, x = 0;
+    uint32_t cw[WARPS];
+    if (tid < kRadix) {
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const uint32_t d = tid * DPT + q;
-        total[q] = 0; incl[q] = 0;
-        if (d < kRadix) {
-#pragma unroll 4
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = s.whist[w][d];
-                s.whist[w][d] = total[q];
-                total[q] += c;
-            }
-            st_relaxed_u32(&status[(size_t)tile * kRadix + d], (tile == 0 ? kFlagIncl : kFlagAgg) | total[q]);
-        }
-    }
-    // scan of the 256 totals -> first tile-local slot of each digit
-    {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int q = 0; q < DPT; ++q) { incl[q] = mine + total[q]; mine = incl[q]; }  // thread-local inclusive
-        uint32_t x = mine;
+        for (int w = 0; w < WARPS; ++w) { cw[w] = s.whist[w][tid]; total += cw[w]; }
+        st_relaxed_u32(&status[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagIncl : kFlagAgg) | total);
+        x = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= (uint32_t)o) x += y;
         }
-        if (lane == 31 && warp < kRadix / 32) s.scan_warp[warp] = x;
-        __syncthreads();
-        if (tid * DPT < kRadix) {
-            uint32_t base = x - mine;
-            for (uint32_t i = 0; i < warp; ++i) base += s.scan_warp[i];
+        if (lane == 31) s.scan_warp[warp] = x;
+    }
+    __syncthreads();
+    if (tid < kRadix) {
+        uint32_t cta_ofs = x - total;
+        for (uint32_t i = 0; i < warp; ++i) cta_ofs += s.scan_warp[i];
+        uint32_t run = cta_ofs;
 #pragma unroll
-            for (int q = 0; q < DPT; ++q) s.cta_ofs[tid * DPT + q] = base + incl[q] - total[q];
+        for (int w = 0; w < WARPS; ++w) { s.whist[w][tid] = run; run += cw[w]; }
+        // look-back: kLookBatch predecessors in flight per round.  Done before the reorder so that the
+        // window between "aggregate published" and "inclusive published" -- which is what later tiles
+        // have to walk through -- is as short as possible
+        uint32_t before = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[kLookBatch];
+#pragma unroll
+                for (int j = 0; j < kLookBatch; ++j)
+                    v[j] = (t - j >= 0) ? ld_relaxed_u32(&status[(size_t)(t - j) * kRadix + tid]) : kFlagIncl;
+                int adv = 0;
+#pragma unroll
+                for (int j = 0; j < kLookBatch; ++j) {
+                    if (!done && adv == j) {
+                        const uint32_t flag = v[j] & ~kValueMask;
+                        if (flag != 0) {  // published
+                            before += v[j] & kValueMask;
+                            ++adv;
+                            if (flag == kFlagIncl) done = true;
+                        }
+                    }
+                }
+                t -= adv;
+            }
+            st_relaxed_u32(&status[(size_t)tile * kRadix + tid], kFlagIncl | (before + total));
         }
+        s.gofs[tid] = gbase[tid] + before - cta_ofs;
     }
     __syncthreads();
 
-    // ---- decoupled look-back: one thread per digit, kLookBatch predecessors in flight per round.  Done before
-    //      the reorder so that the window between "aggregate published" and "inclusive published" --
-    //      which is what later tiles have to walk through -- is as short as possible ----
-#pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const uint32_t d = tid * DPT + q;
-        if (d < kRadix) {
-            uint32_t before = 0;
-            if (tile > 0) {
-                int t = (int)tile - 1;
-                bool done = false;
-                while (!done) {
-                    uint32_t v[kLookBatch];
-#pragma unroll
-                    for (int j = 0; j < kLookBatch; ++j)
-                        v[j] = (t - j >= 0) ? ld_relaxed_u32(&status[(size_t)(t - j) * kRadix + d]) : kFlagIncl;
-                    int adv = 0;
-#pragma unroll
-                    for (int j = 0; j < kLookBatch; ++j) {
-                        if (!done && adv == j) {
-                            const uint32_t flag = v[j] & ~kValueMask;
-                            if (flag != 0) {  // published
-                                before += v[j] & kValueMask;
-                                ++adv;
-                                if (flag == kFlagIncl) done = true;
-                            }
-                        }
-                    }
-                    t -= adv;
-                }
-                st_relaxed_u32(&status[(size_t)tile * kRadix + d], kFlagIncl | (before + total[q]));
-            }
-            s.gofs[d] = gbase[d] + before - s.cta_ofs[d];
-        }
-    }
-
     // ---- reorder keys (and payload) inside the tile through shared memory ----
+    uint2* kv = reinterpret_cast<uint2*>(s.keys);
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-        const uint32_t d = digit_of<KeyT>(key[k], shift, mask);
-        const uint32_t pos = s.cta_ofs[d] + wh[d] + rank[k];
-        s.keys[pos] = key[k];
-        if (PAIRS) s.vals[pos] = s.vals_in[warp_base + k * 32 + lane];
+        const uint32_t pos = wh[rank[k] >> 16] + (rank[k] & 0xFFFFu);
+        if constexpr (PACKED) {
+            kv[pos] = make_uint2((uint32_t)key[k], s.vals_in[warp_base + k * 32 + lane]);
+        } else {
+            s.keys[pos] = key[k];
+            if (PAIRS) s.vals[pos] = s.vals_in[warp_base + k * 32 + lane];
+        }
     }
     __syncthreads();
 
     // ---- coalesced scatter: consecutive threads write runs of equal digits ----
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const uint32_t i = k * BLOCK + tid;
-        if (i < valid) {
-            const KeyT kk = s.keys[i];
-            const uint32_t dst = s.gofs[digit_of<KeyT>(kk, shift, mask)] + i;
-            keys_out[dst] = kk;
-            if (PAIRS) vals_out[dst] = s.vals[i];
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t i = k * BLOCK + tid;
+            if constexpr (PACKED) {
+                const uint2 e = kv[i];
+                const uint32_t dst = s.gofs[digit_of<KeyT>((KeyT)e.x, shift, mask)] + i;
+                keys_out[dst] = (KeyT)e.x;
+                vals_out[dst] = e.y;
+            } else {
+                const KeyT kk = s.keys[i];
+                const uint32_t dst = s.gofs[digit_of<KeyT>(kk, shift, mask)] + i;
+                keys_out[dst] = kk;
+                if (PAIRS) vals_out[dst] = s.vals[i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t i = k * BLOCK + tid;
+            if (i < valid) {
+                if constexpr (PACKED) {
+                    const uint2 e = kv[i];
+                    const uint32_t dst = s.gofs[digit_of<KeyT>((KeyT)e.x, shift, mask)] + i;
+                    keys_out[dst] = (KeyT)e.x;
+                    vals_out[dst] = e.y;
+                } else {
+                    const KeyT kk = s.keys[i];
+                    const uint32_t dst = s.gofs[digit_of<KeyT>(kk, shift, mask)] + i;
+                    keys_out[dst] = kk;
+                    if (PAIRS) vals_out[dst] = s.vals[i];
+                }
+            }
         }
     }
 }
