@@ -5,6 +5,10 @@
 #include <new>
 
 #include "bvh.cuh"
+#include <stdlib.h>
+#ifndef RTR_L2_FETCH_DEFAULT
+#define RTR_L2_FETCH_DEFAULT 0
+#endif
 
 static thread_local std::string g_create_error;
 
@@ -60,12 +64,12 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 }
 
 void bvh_free_arrays(rtr_bvh* b) {
-    void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->cin, b->cout, b->tile_status,
+    void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->order, b->cin, b->cout, b->tile_status,
                     b->state, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
                     b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    b->codes = b->tri_idx = b->isize = b->ipos = b->cin = b->cout = nullptr;
+    b->codes = b->tri_idx = b->isize = b->ipos = b->order = b->cin = b->cout = nullptr;
     b->node = nullptr;
     b->tile_status = nullptr; b->state = nullptr;
     b->trace_active = b->trace_merges = b->iter_first_id = nullptr;
@@ -94,6 +98,7 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     RTR_CHECK(dev_alloc(ctx, &b->node, 2 * nc));
     RTR_CHECK(dev_alloc(ctx, &b->isize, cap));
     RTR_CHECK(dev_alloc(ctx, &b->ipos, cap));
+    RTR_CHECK(dev_alloc(ctx, &b->order, nc));
     RTR_CHECK(dev_alloc(ctx, &b->cin, cap));
     RTR_CHECK(dev_alloc(ctx, &b->cout, cap));
     RTR_CHECK(dev_alloc(ctx, &b->tile_status, tiles));
@@ -256,6 +261,15 @@ int rtr_ctx_create(int device, rtr_ctx** out) {
     if (!ctx) return RTR_E_NOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    // The build gathers 32-byte cluster records and the traversal 64-byte child-pair records at random: a
+    // smaller L2 fetch granularity keeps DRAM from delivering neighbours nobody asked for.  (A hint; the
+    // streaming kernels touch whole lines anyway.)  RTR_L2_FETCH=0 leaves the device default.
+    {
+        const char* env = getenv("RTR_L2_FETCH");
+        const long gran = env ? atol(env) : RTR_L2_FETCH_DEFAULT;
+        if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        cudaGetLastError();  // a hint: never fatal
+    }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return rtr_set_error(nullptr, RTR_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));

@@ -20,7 +20,7 @@ struct TraceParams {
 
 constexpr uint32_t kMaxPlocIterations = 1u << 16;
 #ifndef RTR_PLOC_WARPS
-#define RTR_PLOC_WARPS 4
+#define RTR_PLOC_WARPS 8
 #endif
 // positions decided per CTA of ploc_iteration_kernel (ploc.cu): every warp finds the nearest neighbour of
 // 112 positions, the first and last 16 of the CTA's range only serve the mutual-pair test of the others
@@ -48,6 +48,7 @@ struct rtr_bvh {
     float4* node = nullptr;        // [2*(2cap-1)] by cluster id, 32 B records: (min.xyz, max.x)(max.y, max.z, bits(left | triangle id), bits(right | NONE))
     uint32_t* isize = nullptr;     // [cap] nodes in the subtree of internal cluster (id - n)
     uint32_t* ipos = nullptr;      // [cap] DFS pre-order position of internal cluster (id - n)
+    uint32_t* order = nullptr;     // [2cap-1] cluster id at every DFS pre-order position (flatten pass 1)
     uint32_t* cin = nullptr;       // [cap] active list, ping
     uint32_t* cout = nullptr;      // [cap] active list, pong
     uint64_t* tile_status = nullptr;  // [ceil(cap/tile)] decoupled look-back words

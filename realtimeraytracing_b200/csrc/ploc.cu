@@ -36,7 +36,7 @@ constexpr int kWarps = RTR_PLOC_WARPS;
 #define RTR_PLOC_ROLL 0   // 1: the three full 4x4 blocks of the pair matrix run as a loop (a third of the code)
 #endif
 #ifndef RTR_PLOC_MINB
-#define RTR_PLOC_MINB (768 / (32 * RTR_PLOC_WARPS))  // resident CTAs per SM the register budget is cut for
+#define RTR_PLOC_MINB (1024 / (32 * RTR_PLOC_WARPS))  // resident CTAs per SM the register budget is cut for (64 registers)
 #endif
 constexpr int kPT = 32 * kWarps;                 // threads per CTA
 constexpr int kWarpSpan = (32 - kHaloLanes) * kPP;  // 112 positions per warp get their nearest neighbour
@@ -142,6 +142,27 @@ __device__ __forceinline__ uint32_t block_scan_incl(uint32_t v, uint32_t* s_warp
     return base + x;
 }
 
+// Longest squared triangle edge of the launch (conservative traversal pruning bound, see trace.cu): warp
+// shuffle -> CTA -> at most one atomic per CTA, and only while the CTA still raises the global value
+// (one same-address atomic per warp kept leaf_init_kernel waiting on a single L2 slice).
+__device__ __forceinline__ void publish_edge_bound(float e2, TraceParams* __restrict__ tparams) {
+    __shared__ float s_e2[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o));
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps = (blockDim.x + 31u) >> 5;
+    if (lane == 0) s_e2[warp] = e2;
+    __syncthreads();
+    if (warp == 0) {
+        e2 = lane < warps ? s_e2[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o));
+        if (lane == 0 && e2 > 0.f) {
+            const uint32_t mine = float_to_ordered(e2);
+            if (mine > ld_relaxed_u32(&tparams->emax2_ordered)) atomicMax(&tparams->emax2_ordered, mine);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // leaf initialisation: plocPreprocessing (bvh.cpp:29-42) + AABB::buildFromTriangle (:383-399)
 // ---------------------------------------------------------------------------------------
@@ -173,9 +194,7 @@ leaf_init_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restri
         e2 = fmaxf(abx * abx + aby * aby + abz * abz,
                    fmaxf(acx * acx + acy * acy + acz * acz, bcx * bcx + bcy * bcy + bcz * bcz));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o));
-    if (lane_id() == 0 && e2 > 0.f) atomicMax(&tparams->emax2_ordered, float_to_ordered(e2));
+    publish_edge_bound(e2, tparams);
 }
 
 // adopted node arrays: same cache, indexed by triangle id
@@ -197,9 +216,7 @@ edge_bound_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restr
         e2 = fmaxf(abx * abx + aby * aby + abz * abz,
                    fmaxf(acx * acx + acy * acy + acz * acz, bcx * bcx + bcy * bcy + bcz * bcz));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o));
-    if (lane_id() == 0 && e2 > 0.f) atomicMax(&tparams->emax2_ordered, float_to_ordered(e2));
+    publish_edge_bound(e2, tparams);
 }
 
 __global__ void ploc_state_init_kernel(PlocState* state, uint32_t n, uint32_t* iter_first_id) {
@@ -280,13 +297,15 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
         return;
     }
     const uint32_t tiles = (n + kTileT - 1) / kTileT;
+    // the grid is sized for an upper bound of n that the host refreshes every kChunk launches: surplus CTAs
+    // leave without touching the tile counter
+    if (blockIdx.x >= tiles) return;
     const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
     uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
     // tiles are handed out in start order, so the look-back below only ever waits on running tiles
     if (tid == 0) s.tile = atomicAdd(&cur->tile_counter, 1u);
     __syncthreads();
-    const uint32_t tile = s.tile;
-    if (tile >= tiles) return;
+    const uint32_t tile = s.tile;  // < tiles: exactly `tiles` CTAs draw a number
     const int t0 = (int)(tile * kTileT);
     const int base = t0 - 2 * kR;  // position of staged slot 0
 
@@ -399,31 +418,50 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     uint32_t ex_lo_local = (incl & 0xFFFFu) - (packed & 0xFFFFu);
     uint32_t ex_hi_local = (incl >> 16) - (packed >> 16);
 
-    // ---- decoupled look-back over tiles (plocPrefixScan, bvh.cpp:125-148, as a single pass) ----
-    if (tid == 0) {
+    // ---- decoupled look-back over tiles (plocPrefixScan, bvh.cpp:125-148, as a single pass).  Warp 0 reads
+    //      the status words of 32 predecessors per round: the run of published words nearest to this tile,
+    //      up to and including the first inclusive one, is summed with shuffles.  (One predecessor per
+    //      round made the walk of the first wave of CTAs -- which all publish their aggregates at the same
+    //      moment -- the critical path of the whole launch.) ----
+    if (warp == 0) {
         const uint32_t agg_lo = cta_total & 0xFFFFu, agg_hi = cta_total >> 16;
         const uint32_t tag = iter + 1u;
         uint32_t ex_lo = 0, ex_hi = 0;
         if (tile > 0) {
-            st_relaxed_u64(&tile_status[tile], lb_pack(tag, kLbAgg, agg_lo, agg_hi));
-            int t = (int)tile - 1;
+            if (lane == 0) st_relaxed_u64(&tile_status[tile], lb_pack(tag, kLbAgg, agg_lo, agg_hi));
+            int t = (int)tile - 1;  // nearest predecessor not yet accounted for
             while (true) {
-                const uint64_t w = ld_relaxed_u64(&tile_status[t]);
-                const uint64_t flag = (w >> 54) & 3ull;
-                if ((uint32_t)(w >> 56) != (tag & 0xFFu) || flag == 0) continue;
-                ex_lo += (uint32_t)(w & kCntMask);
-                ex_hi += (uint32_t)((w >> 27) & kCntMask);
-                if (flag == kLbIncl) break;
-                --t;
+                const int tt = t - lane;
+                uint64_t w = lb_pack(tag, kLbIncl, 0u, 0u);  // before tile 0: an inclusive prefix of nothing
+                if (tt >= 0) w = ld_relaxed_u64(&tile_status[tt]);
+                const uint32_t flag = ((uint32_t)(w >> 56) == (tag & 0xFFu)) ? (uint32_t)((w >> 54) & 3ull) : 0u;
+                const uint32_t m_incl = __ballot_sync(0xffffffffu, flag == (uint32_t)kLbIncl);
+                const uint32_t m_none = __ballot_sync(0xffffffffu, flag == 0u);
+                const int first_incl = m_incl ? __ffs(m_incl) - 1 : 32;
+                const int first_none = m_none ? __ffs(m_none) - 1 : 32;
+                const bool closed = first_incl < first_none;          // the run ends with an inclusive prefix
+                const int take = closed ? first_incl + 1 : first_none;  // lanes [0, take) are consumed
+                uint32_t c_lo = lane < take ? (uint32_t)(w & kCntMask) : 0u;
+                uint32_t c_hi = lane < take ? (uint32_t)((w >> 27) & kCntMask) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o);
+                    c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o);
+                }
+                ex_lo += c_lo; ex_hi += c_hi;
+                if (closed) break;
+                t -= take;
             }
         }
-        st_relaxed_u64(&tile_status[tile], lb_pack(tag, kLbIncl, ex_lo + agg_lo, ex_hi + agg_hi));
-        s.ex_lo = ex_lo; s.ex_hi = ex_hi;
-        if (tile == tiles - 1) {  // bvh.cpp:105-113
-            const uint32_t merges = ex_lo + agg_lo, removed = ex_hi + agg_hi;
-            nxt->n_active = n - removed; nxt->total = total + merges; nxt->iter = iter + 1; nxt->tile_counter = 0;
-            if (iter < kMaxPlocIterations) {
-                trace_active[iter] = n; trace_merges[iter] = merges; iter_first_id[iter + 1] = total + merges;
+        if (lane == 0) {
+            st_relaxed_u64(&tile_status[tile], lb_pack(tag, kLbIncl, ex_lo + agg_lo, ex_hi + agg_hi));
+            s.ex_lo = ex_lo; s.ex_hi = ex_hi;
+            if (tile == tiles - 1) {  // bvh.cpp:105-113
+                const uint32_t merges = ex_lo + agg_lo, removed = ex_hi + agg_hi;
+                nxt->n_active = n - removed; nxt->total = total + merges; nxt->iter = iter + 1; nxt->tile_counter = 0;
+                if (iter < kMaxPlocIterations) {
+                    trace_active[iter] = n; trace_merges[iter] = merges; iter_first_id[iter + 1] = total + merges;
+                }
             }
         }
     }
@@ -554,25 +592,75 @@ __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t
     dst[2] = make_uint4(tri, left, right, slot);
 }
 
-// One inner cluster c at flat position p: writes its flat node, the flat nodes of its leaf children,
-// the positions of its inner children, and its child-pair record for the traversal kernels (both
-// children's boxes are on hand here, which saves re-reading the whole flat array afterwards).
-__device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
-                                            const float4* __restrict__ node,
-                                            const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
-                                            rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
+// Pass 1 (top-down over creation levels, last iteration first): DFS pre-order position of every cluster.
+// One inner cluster c at position p places its children -- left at p + 1, right behind the left subtree
+// (scene.cpp:189-199) -- and records which cluster sits at each position.  Only 4-byte arrays are touched
+// (order 8 B/triangle, ipos and isize 4 B/triangle), which the 126 MB L2 absorbs.
+__device__ __forceinline__ void place_children(uint32_t c, uint32_t n_leaves, const float4* __restrict__ node,
+                                               const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
+                                               uint32_t* __restrict__ order) {
     const uint32_t p = ipos[c - n_leaves];
-    const Box bx_ = load_box(node, c); const float4 lo = bx_.lo, hi = bx_.hi;
+    const float4 hi = __ldg(node + 2 * (size_t)c + 1);
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
+    const uint32_t size_l = L < n_leaves ? 1u : isize[L - n_leaves];
+    const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
+    order[pos_l] = L;
+    order[pos_r] = R;
+    if (L >= n_leaves) ipos[L - n_leaves] = pos_l;
+    if (R >= n_leaves) ipos[R - n_leaves] = pos_r;
+}
+
+__global__ void __launch_bounds__(256)
+flatten_level_kernel(uint32_t first, uint32_t count, uint32_t n_leaves, const float4* __restrict__ node,
+                     const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) place_children(first + i, n_leaves, node, isize, ipos, order);
+}
+
+// levels [it_lo, it_hi] processed last-first by one CTA (the top of the tree: many tiny levels)
+__global__ void __launch_bounds__(1024)
+flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_hi, int it_lo, uint32_t n_leaves,
+                            const float4* __restrict__ node, const uint32_t* __restrict__ isize,
+                            uint32_t* __restrict__ ipos, uint32_t* __restrict__ order) {
+    for (int it = it_hi; it >= it_lo; --it) {
+        const uint32_t first = iter_first_id[it], count = iter_first_id[it + 1] - first;
+        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
+            place_children(first + i, n_leaves, node, isize, ipos, order);
+        __syncthreads();
+    }
+}
+
+// Pass 2, one thread per flat position p: gathers the 32-byte record of the cluster placed there and
+// streams out the reference's 48-byte node (scene.cpp:189-208) and, for inner nodes, the 64-byte child-pair
+// record of the traversal kernels.  All stores of a warp are contiguous; the left child's record is the
+// next lane's own (position p + 1).
+__global__ void __launch_bounds__(256)
+flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __restrict__ order,
+                    const float4* __restrict__ node, const uint32_t* __restrict__ isize,
+                    rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < nb_nodes;
+    const uint32_t c = live ? order[p] : 0u;
+    const Box me = load_box(node, c);
+    // the next position's record (the left child of an inner node), through the warp
+    Box nx;
+    nx.lo.x = __shfl_down_sync(0xffffffffu, me.lo.x, 1); nx.lo.y = __shfl_down_sync(0xffffffffu, me.lo.y, 1);
+    nx.lo.z = __shfl_down_sync(0xffffffffu, me.lo.z, 1); nx.lo.w = __shfl_down_sync(0xffffffffu, me.lo.w, 1);
+    nx.hi.x = __shfl_down_sync(0xffffffffu, me.hi.x, 1); nx.hi.y = __shfl_down_sync(0xffffffffu, me.hi.y, 1);
+    nx.hi.z = __shfl_down_sync(0xffffffffu, me.hi.z, 1); nx.hi.w = __shfl_down_sync(0xffffffffu, me.hi.w, 1);
+    if (!live) return;
+    const bool leaf = c < n_leaves;
+    const uint32_t L = __float_as_uint(me.hi.z), R = __float_as_uint(me.hi.w);
+    if (leaf) {  // leaves keep 0/0 and their triangle id; the wtri slot (= cluster id) rides in the padding word
+        store_node(flat, p, me.lo, me.hi, L, 0u, 0u, c);
+        return;
+    }
     const bool lleaf = L < n_leaves, rleaf = R < n_leaves;
-    const Box bl = load_box(node, L), br = load_box(node, R);
     const uint32_t size_l = lleaf ? 1u : isize[L - n_leaves];
     const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
-    store_node(flat, p, lo, hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
-    if (lleaf) store_node(flat, pos_l, bl.lo, bl.hi, __float_as_uint(bl.hi.z), 0u, 0u, L);
-    else ipos[L - n_leaves] = pos_l;
-    if (rleaf) store_node(flat, pos_r, br.lo, br.hi, __float_as_uint(br.hi.z), 0u, 0u, R);
-    else ipos[R - n_leaves] = pos_r;
+    const Box br = load_box(node, R);
+    const Box bl = (lane_id() < 31u) ? nx : load_box(node, L);
+    store_node(flat, p, me.lo, me.hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
     // (L.min.xyz, L.max.x) (L.max.yz, R.min.xy) (R.min.z, R.max.xyz) (L.word, R.word, L.aux, R.aux)
     float* dst = reinterpret_cast<float*>(pairs + (size_t)p * 4);
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -585,28 +673,7 @@ __device__ __forceinline__ void flatten_one(uint32_t c, uint32_t n_leaves,
                    "f"(__uint_as_float(lleaf ? L : 0u)), "f"(__uint_as_float(rleaf ? R : 0u)) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
-flatten_level_kernel(uint32_t first, uint32_t count, uint32_t n_leaves,
-                     const float4* __restrict__ node,
-                     const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat,
-                     uint4* __restrict__ pairs) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) flatten_one(first + i, n_leaves, node, isize, ipos, flat, pairs);
-}
-
-// levels [it_lo, it_hi] processed last-first by one CTA (the top of the tree: many tiny levels)
-__global__ void __launch_bounds__(1024)
-flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_hi, int it_lo, uint32_t n_leaves,
-                            const float4* __restrict__ node,
-                            const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, rtr_node* __restrict__ flat,
-                            uint4* __restrict__ pairs) {
-    for (int it = it_hi; it >= it_lo; --it) {
-        const uint32_t first = iter_first_id[it], count = iter_first_id[it + 1] - first;
-        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
-            flatten_one(first + i, n_leaves, node, isize, ipos, flat, pairs);
-        __syncthreads();
-    }
-}
+__global__ void flatten_root_kernel(uint32_t* order, uint32_t root) { order[0] = root; }
 
 __global__ void flatten_single_leaf_kernel(const float4* node, rtr_node* flat) {
     const Box bx_ = load_box(node, 0); const float4 lo = bx_.lo, hi = bx_.hi;
@@ -784,7 +851,10 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node, b->flat);
         RTR_LAUNCH_CHECK(ctx);
     } else {
+        uint32_t* order = b->order;
         RTR_CUDA(ctx, cudaMemsetAsync(b->ipos + (n - 2), 0, sizeof(uint32_t), ctx->stream));  // root 2n-2 -> position 0
+        flatten_root_kernel<<<1, 1, 0, ctx->stream>>>(order, 2 * n - 2);
+        RTR_LAUNCH_CHECK(ctx);
         const uint32_t kSmall = 4096;
         int it = (int)b->iterations - 1;
         while (it >= 0) {
@@ -792,7 +862,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             if (count > kSmall) {
                 RTR_PROF(ctx, "flatten_level_kernel");
                 flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node,
-                                                                                   b->isize, b->ipos, b->flat, b->pairs);
+                                                                                   b->isize, b->ipos, order);
                 RTR_LAUNCH_CHECK(ctx);
                 --it;
             } else {
@@ -800,11 +870,15 @@ int rtr_bvh_run_build(rtr_bvh* b) {
                 while (lo - 1 >= 0 && b->h_first_id[lo] - b->h_first_id[lo - 1] <= kSmall) --lo;
                 RTR_PROF(ctx, "flatten_small_levels_kernel");
                 flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node,
-                                                                         b->isize, b->ipos, b->flat, b->pairs);
+                                                                         b->isize, b->ipos, order);
                 RTR_LAUNCH_CHECK(ctx);
                 it = lo - 1;
             }
         }
+        const uint32_t nc = 2 * n - 1;
+        RTR_PROF(ctx, "flatten_emit_kernel");
+        flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, n, order, b->node, b->isize, b->flat, b->pairs);
+        RTR_LAUNCH_CHECK(ctx);
     }
     b->pairs_view = b->pairs;  // written by the flatten kernels
     RTR_CHECK(record(b, 5));

@@ -30,8 +30,12 @@ constexpr uint32_t kValueMask = (1u << 30) - 1;
 #define RTR_SORT_MINB 2   // resident CTAs per SM the register budget is cut for
 #endif
 #ifndef RTR_SORT_LOOKBATCH
-#define RTR_SORT_LOOKBATCH 16
+#define RTR_SORT_LOOKBATCH 4
 #endif
+#ifndef RTR_SORT_PREFETCH
+#define RTR_SORT_PREFETCH 296   // tiles ahead whose keys are pulled into L2 (two CTAs on each of the 148 SMs)
+#endif
+constexpr uint32_t kPrefetchTiles = RTR_SORT_PREFETCH;
 constexpr int kLookBatch = RTR_SORT_LOOKBATCH;  // predecessors whose status words one look-back round has in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -54,6 +58,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -154,6 +161,7 @@ struct OnesweepSmem {
     alignas(128) uint32_t vals[(PAIRS && !PACKED) ? TILE : 4];    // payload in tile-sorted order
     uint32_t whist[WARPS][kRadix];  // per-warp running digit counts, then first tile-local slot of (warp, digit)
     uint32_t gofs[kRadix];          // global slot of the digit's first key of this tile, minus its tile-local slot
+    uint32_t cta_hist[kRadix];      // digit counts of the tile
     uint32_t scan_warp[kRadix / 32];
     alignas(8) uint64_t mbar;
     uint32_t tile;
@@ -207,6 +215,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         if (TMA) { mbar_init(&s.mbar, 1); mbar_fence_init(); }
     }
     for (uint32_t i = lane; i < kRadix; i += 32) s.whist[warp][i] = 0;
+    if (tid < kRadix) s.cta_hist[tid] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint32_t tile_base = tile * (uint32_t)TILE;
@@ -214,7 +223,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const bool full = (valid == (uint32_t)TILE);
 
     // ---- load: warp-striped so that (item, lane) order == memory order (stability).  Full tiles
-    //      arrive as TMA bulk copies (keys and payload in flight together, one mbarrier) ----
+    //      arrive as TMA bulk copies (keys and payload in flight together, one mbarrier); the tile the
+    //      CTA after next on this SM will want is pulled into L2 meanwhile ----
     KeyT key[IPT];
     const uint32_t warp_base = warp * 32u * IPT;
     if (TMA && full) {
@@ -222,6 +232,11 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
             mbar_expect_tx(&s.mbar, TILE * (sizeof(KeyT) + (PAIRS ? 4u : 0u)));
             tma_bulk_g2s(s.keys, keys_in + tile_base, TILE * sizeof(KeyT), &s.mbar);
             if (PAIRS) tma_bulk_g2s(s.vals_in, vals_in + tile_base, TILE * 4u, &s.mbar);
+            const uint32_t ahead = tile + kPrefetchTiles;
+            if (kPrefetchTiles > 0 && (uint64_t)(ahead + 1u) * TILE <= n) {
+                l2_prefetch_bulk(keys_in + (size_t)ahead * TILE, TILE * sizeof(KeyT));
+                if (PAIRS) l2_prefetch_bulk(vals_in + (size_t)ahead * TILE, TILE * 4u);
+            }
         }
         mbar_wait(&s.mbar, 0);
 #pragma unroll
@@ -235,6 +250,51 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         }
     }
 
+    // ---- digit counts of the tile first (one shared-memory reduction per key): the aggregate other tiles
+    //      look back at is published BEFORE the expensive ranking, and this tile's own look-back runs
+    //      interleaved with the ranking instead of after it ----
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) atomicAdd(&s.cta_hist[digit_of<KeyT>(key[k], shift, mask)], 1u);
+    __syncthreads();
+    uint32_t total = 0, x = 0;
+    if (tid < kRadix) {
+        total = s.cta_hist[tid];
+        st_relaxed_u32(&status[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagIncl : kFlagAgg) | total);
+        x = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) s.scan_warp[warp] = x;
+    }
+    // decoupled look-back, one thread per digit, kLookBatch predecessors in flight; issued/consumed in steps
+    uint32_t before = 0;
+    int lb_t = (int)tile - 1;
+    bool lb_done = !(tid < kRadix) || tile == 0;
+    uint32_t lb_v[kLookBatch];
+    auto lb_issue = [&]() {
+#pragma unroll
+        for (int j = 0; j < kLookBatch; ++j)
+            lb_v[j] = (lb_t - j >= 0) ? ld_relaxed_u32(&status[(size_t)(lb_t - j) * kRadix + tid]) : kFlagIncl;
+    };
+    auto lb_consume = [&]() {
+        int adv = 0;
+#pragma unroll
+        for (int j = 0; j < kLookBatch; ++j) {
+            if (!lb_done && adv == j) {
+                const uint32_t flag = lb_v[j] & ~kValueMask;
+                if (flag != 0) {  // published
+                    before += lb_v[j] & kValueMask;
+                    ++adv;
+                    if (flag == kFlagIncl) lb_done = true;
+                }
+            }
+        }
+        lb_t -= adv;
+        if (lb_done) st_relaxed_u32(&status[(size_t)tile * kRadix + tid], kFlagIncl | (before + total));
+    };
+
     // ---- rank inside the warp.  peers = lanes with the same digit; the key's slot among the warp's keys of
     //      that digit = running count of the earlier items (shared memory, bumped by the highest peer lane)
     //      + peers below.  rank[k] ends as (digit << 16 | slot) ----
@@ -243,6 +303,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
 #pragma unroll
     for (int k0 = 0; k0 < IPT; k0 += 4) {
+        const bool lb_step = !lb_done;
+        if (lb_step) lb_issue();
         uint32_t peers[4], dg[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -257,60 +319,18 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
             __syncwarp();                                                // item k's bump is ordered before item k+1's read
             rank[k0 + j] = (dg[j] << 16) | (cnt + below);
         }
+        if (lb_step) lb_consume();
     }
+    while (!lb_done) { lb_issue(); lb_consume(); }
     __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
 
-    // ---- per digit (threads 0..255): counts of the warps -> tile total -> published aggregate; exclusive scan
-    //      over digits -> first tile-local slot of every (warp, digit); decoupled look-back ----
-    uint32_t total = 0, x = 0;
-    uint32_t cw[WARPS];
-    if (tid < kRadix) {
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) { cw[w] = s.whist[w][tid]; total += cw[w]; }
-        st_relaxed_u32(&status[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagIncl : kFlagAgg) | total);
-        x = total;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (uint32_t)o) x += y;
-        }
-        if (lane == 31) s.scan_warp[warp] = x;
-    }
-    __syncthreads();
+    // ---- per digit (threads 0..255): first tile-local slot of every (warp, digit) ----
     if (tid < kRadix) {
         uint32_t cta_ofs = x - total;
         for (uint32_t i = 0; i < warp; ++i) cta_ofs += s.scan_warp[i];
         uint32_t run = cta_ofs;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) { s.whist[w][tid] = run; run += cw[w]; }
-        // look-back: kLookBatch predecessors in flight per round.  Done before the reorder so that the
-        // window between "aggregate published" and "inclusive published" -- which is what later tiles
-        // have to walk through -- is as short as possible
-        uint32_t before = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            bool done = false;
-            while (!done) {
-                uint32_t v[kLookBatch];
-#pragma unroll
-                for (int j = 0; j < kLookBatch; ++j)
-                    v[j] = (t - j >= 0) ? ld_relaxed_u32(&status[(size_t)(t - j) * kRadix + tid]) : kFlagIncl;
-                int adv = 0;
-#pragma unroll
-                for (int j = 0; j < kLookBatch; ++j) {
-                    if (!done && adv == j) {
-                        const uint32_t flag = v[j] & ~kValueMask;
-                        if (flag != 0) {  // published
-                            before += v[j] & kValueMask;
-                            ++adv;
-                            if (flag == kFlagIncl) done = true;
-                        }
-                    }
-                }
-                t -= adv;
-            }
-            st_relaxed_u32(&status[(size_t)tile * kRadix + tid], kFlagIncl | (before + total));
-        }
+        for (int w = 0; w < WARPS; ++w) { const uint32_t c = s.whist[w][tid]; s.whist[w][tid] = run; run += c; }
         s.gofs[tid] = gbase[tid] + before - cta_ofs;
     }
     __syncthreads();

@@ -501,16 +501,17 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 #define RTR_FIN_BATCH 4
 #endif
 #ifndef RTR_TRACE_MIN_CTAS
-#define RTR_TRACE_MIN_CTAS 6
+#define RTR_TRACE_MIN_CTAS 8
 #endif
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDry = 0xFFFFFFFFu;  // stack ran dry (also the state of an idle lane)
 #ifndef RTR_SMEM_STACK
-#define RTR_SMEM_STACK 12
+#define RTR_SMEM_STACK 8
 #endif
 constexpr int kSmemStack = RTR_SMEM_STACK;
+static_assert((kSmemStack & (kSmemStack - 1)) == 0, "the shared-memory stack window is indexed modulo a power of two");
 
 struct JobDesc {
     uint32_t kind;   // 0: pixels (render / primary), 1: explicit rays
@@ -567,7 +568,8 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     int sp = 0;
     uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen
     float L = 0.f;
-    float stack_t[kStack - kSmemStack];
+    int win_lo = 0;                 // first stack entry held in shared memory
+    float stack_t[kStack - kSmemStack];   // entries below the window (index < kStack - kSmemStack always)
     uint32_t stack_a[kStack - kSmemStack], stack_b[kStack - kSmemStack];
 
     auto limit_of = [&](float t) -> float {
@@ -578,7 +580,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     // begin walking ray r: root test (raytracer.glsl:255-262 pops node 0 first)
     auto start_ray = [&](bool any, float tm) {
         st = (st & 0xFFFFu) | (any ? 0x10000u : 0u) | (st & 0x20000u);
-        best_t = tm; best_node = RTR_NONE; sp = 0; pend_node = RTR_NONE;
+        best_t = tm; best_node = RTR_NONE; sp = 0; win_lo = 0; pend_node = RTR_NONE;
         limit = any ? limit_of(tm) : INFINITY;
         const NodeRec root = load_node(A.nodes, 0u);
         float te;
@@ -588,16 +590,34 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             else a = 0u;
         }
     };
+    // Stack entries [win_lo, sp) live in shared memory at slot (index % kSmemStack) -- a window that follows the
+    // top of the stack, where a depth-first walk does nearly all of its pushes and pops -- entries [0, win_lo)
+    // in local memory.  A push into a full window moves its oldest entry out; a pop below the window reads
+    // local memory directly.
+    auto push_far = [&](float tf, uint32_t fa, uint32_t fb) {
+        if (sp >= kStack) { st |= 0x20000u; return; }
+        const int slot = sp & (kSmemStack - 1);
+        if (sp - win_lo == kSmemStack) {  // slot holds entry win_lo: spill it
+            stack_t[win_lo] = __uint_as_float(s_stack[0][slot][threadIdx.x]);
+            stack_a[win_lo] = s_stack[1][slot][threadIdx.x];
+            stack_b[win_lo] = s_stack[2][slot][threadIdx.x];
+            ++win_lo;
+        }
+        s_stack[0][slot][threadIdx.x] = __float_as_uint(tf); s_stack[1][slot][threadIdx.x] = fa; s_stack[2][slot][threadIdx.x] = fb;
+        ++sp;
+    };
     auto pop_next = [&]() {
         a = kDry;
         while (sp > 0) {
             --sp;
-            if (sp < kSmemStack) {
-                if (__uint_as_float(s_stack[0][sp][threadIdx.x]) > limit) continue;
-                a = s_stack[1][sp][threadIdx.x]; b = s_stack[2][sp][threadIdx.x];
+            if (sp >= win_lo) {
+                const int slot = sp & (kSmemStack - 1);
+                if (__uint_as_float(s_stack[0][slot][threadIdx.x]) > limit) continue;
+                a = s_stack[1][slot][threadIdx.x]; b = s_stack[2][slot][threadIdx.x];
             } else {
-                if (stack_t[sp - kSmemStack] > limit) continue;
-                a = stack_a[sp - kSmemStack]; b = stack_b[sp - kSmemStack];
+                win_lo = sp;
+                if (stack_t[sp] > limit) continue;
+                a = stack_a[sp]; b = stack_b[sp];
             }
             break;
         }
@@ -678,13 +698,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         const bool left_first = tl <= tr;
                         const float tf = left_first ? tr : tl;
                         const uint32_t fa = left_first ? c3.y : c3.x, fb = left_first ? c3.w : c3.z;  // far child -> stack
-                        if (sp < kSmemStack) {
-                            s_stack[0][sp][threadIdx.x] = __float_as_uint(tf); s_stack[1][sp][threadIdx.x] = fa; s_stack[2][sp][threadIdx.x] = fb;
-                            ++sp;
-                        } else if (sp < kStack) {
-                            stack_t[sp - kSmemStack] = tf; stack_a[sp - kSmemStack] = fa; stack_b[sp - kSmemStack] = fb;
-                            ++sp;
-                        } else st |= 0x20000u;
+                        push_far(tf, fa, fb);
                         a = left_first ? c3.x : c3.y; b = left_first ? c3.z : c3.w;
                     } else if (hl) { a = c3.x; b = c3.z; }
                     else if (hr) { a = c3.y; b = c3.w; }
@@ -705,7 +719,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     Hit h;
                     if (ray_triangle(r, A.wtri, pend_slot, 0u, h)) {
                         if (st & 0x10000u) {
-                            if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; }
+                            if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; win_lo = 0; }
                         } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
                             best_t = h.t; best_node = pend_node;
                             limit = limit_of(h.t);
