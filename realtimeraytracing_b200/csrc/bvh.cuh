@@ -15,7 +15,7 @@ struct TraceParams {
     uint32_t emax2_ordered;  // max squared edge length over all triangles, ordered-uint encoded
     uint32_t stack_overflows;
     uint32_t job_counter;    // next 32-job tile of the persistent traversal launch in flight
-    uint32_t pad1;
+    uint32_t bad_layout;     // pack_pairs_kernel: inner nodes whose left child is not at index + 1 (not DFS pre-order)
 };
 
 constexpr uint32_t kMaxPlocIterations = 1u << 16;
@@ -71,11 +71,7 @@ struct rtr_bvh {
     size_t wtri_own_cap = 0;            // triangles wtri_own was sized for
     const float4* wtri_view = nullptr;  // what traversal reads
     bool wtri_by_rank = true;
-    // child-pair records read by the default traversal: one 64-byte record per inner node of the flat array
-    // (indexed by flat index; leaf entries unused) = both children's boxes + their links, copied bit for
-    // bit from the flat nodes by pack_pairs_kernel:
-    //   (L.min.xyz, L.max.x) (L.max.yz, R.min.xy) (R.min.z, R.max.xyz) (L.word, R.word, L.aux, R.aux)
-    //   word = child flat index, or 0x80000000 | index for a leaf whose aux is its wtri slot
+    // traversal records read by the default traversal, 64 bytes per flat index (layout: TravRec below)
     uint4* pairs = nullptr;        // [4*(2cap-1)]
     uint4* pairs_own = nullptr;    // adopted / received BVHs
     size_t pairs_own_cap = 0;      // triangles pairs_own was sized for
@@ -88,6 +84,85 @@ struct rtr_bvh {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
 };
+
+// ---------------------------------------------------------------------------------------
+// Traversal records: the default traversal's private copy of the flat array, 64 bytes per flat index.
+//
+//   inner node p (first 32 bytes, one 256-bit load):
+//     w0..w2  origin = min corner of the node's own box (fp32)
+//     w3      bytes (Ex, Ey, Ez, flags): grid step of axis k = 2^(Ek - 127);
+//             flags bit0 / bit1: left / right child is a leaf, bit2: no culling at this node (box outside
+//             the supported range)
+//     w4..w6  per axis k the byte quadruple (Llo, Lhi, Rlo, Rhi): child plane = origin_k + byte * step_k,
+//             min planes rounded down, max planes rounded up -- a SUPERSET of the child's exact box
+//     w7      flat index of the right child (the left child is p + 1: DFS pre-order, scene.cpp:189-199)
+//   leaf p (64 bytes, two 256-bit loads):
+//     exact box min.xyz, max.xyz | world-space vertices P0, P1, P2 (host naming) | triangle id
+//
+// Why a superset is enough: the reference tests a leaf's triangle iff the slab test passes on the leaf's own
+// box (merged boxes are exact unions and the slab test is monotone in the box).  The leaf
+// record keeps that box exactly and the leaf's test is the reference's; inner records only decide which
+// leaves get there, so they may err on the side of visiting -- never on the side of skipping.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int trav_ilogb(double x) {  // floor(log2 x) of a positive normal double
+    return (int)((__double_as_longlong(x) >> 52) & 0x7FF) - 1023;
+}
+__device__ __forceinline__ double trav_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+
+// One axis: grid step 2^e with origin + 255 * step >= hi, then the four plane bytes.  Everything is checked
+// in double, where origin + byte * step is exact (the step is kept within 2^-40 of the origin's magnitude).
+__device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
+                                                 uint32_t& ebyte, uint32_t& quad, bool& ok) {
+    const double lo = nlo_f, hi = nhi_f;
+    const double ext = hi - lo;
+    int e = -100;
+    if (ext > 0.0 && ext < 1e300) {
+        e = trav_ilogb(ext) - 7;              // 256 * 2^e > ext
+        if (255.0 * trav_pow2(e) < ext) ++e;  // smallest e with 255 * 2^e >= ext
+    }
+    if (lo != 0.0) {
+        const int eo = trav_ilogb(fabs(lo)) + 1;
+        if (e < eo - 40) e = eo - 40;
+    }
+    if (e < -100) e = -100;
+    if (!(ext >= 0.0) || e > 30 || !(fabs(lo) < 1e15)) { ok = false; e = 0; }
+    const double step = trav_pow2(e), inv_step = trav_pow2(-e);
+    auto down = [&](float x) -> uint32_t {
+        const double t = fmin(fmax(((double)x - lo) * inv_step, 0.0), 255.0);
+        int q = __double2int_rd(t);
+        if (q > 0 && lo + (double)q * step > (double)x) --q;
+        return (uint32_t)q;
+    };
+    auto up = [&](float x) -> uint32_t {
+        const double t = fmin(fmax(((double)x - lo) * inv_step, 0.0), 255.0);
+        int q = __double2int_ru(t);
+        if (q < 255 && lo + (double)q * step < (double)x) ++q;
+        return (uint32_t)q;
+    };
+    ebyte = (uint32_t)(e + 127);
+    quad = down(llo) | (up(lhi) << 8) | (down(rlo) << 16) | (up(rhi) << 24);
+    // the bytes must really bound the children (they always do for the exact unions a PLOC tree holds)
+    const double l0 = lo + (double)(quad & 0xFFu) * step, l1 = lo + (double)((quad >> 8) & 0xFFu) * step;
+    const double r0 = lo + (double)((quad >> 16) & 0xFFu) * step, r1 = lo + (double)(quad >> 24) * step;
+    if (!(l0 <= (double)llo && l1 >= (double)lhi && r0 <= (double)rlo && r1 >= (double)rhi)) ok = false;
+}
+
+// node box n, child boxes l and r as (min.xyz, max.x)(max.y, max.z) float4 + float2
+__device__ __forceinline__ void trav_encode_inner(const float4 nlo, const float2 nhi, const float4 llo, const float2 lhi,
+                                                  const float4 rlo, const float2 rhi, bool lleaf, bool rleaf,
+                                                  uint32_t right, uint4& o0, uint4& o1) {
+    uint32_t ex, ey, ez, qx, qy, qz;
+    bool ok = true;
+    trav_encode_axis(nlo.x, nlo.w, llo.x, llo.w, rlo.x, rlo.w, ex, qx, ok);
+    trav_encode_axis(nlo.y, nhi.x, llo.y, lhi.x, rlo.y, rhi.x, ey, qy, ok);
+    trav_encode_axis(nlo.z, nhi.y, llo.z, lhi.y, rlo.z, rhi.y, ez, qz, ok);
+    const uint32_t flags = (lleaf ? 1u : 0u) | (rleaf ? 2u : 0u) | (ok ? 0u : 4u);
+    o0 = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z),
+                    ex | (ey << 8) | (ez << 16) | (flags << 24));
+    o1 = make_uint4(qx, qy, qz, right);
+}
+#endif
 
 // ploc.cu
 int rtr_bvh_run_build(rtr_bvh* b);

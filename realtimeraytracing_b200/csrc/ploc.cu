@@ -630,14 +630,31 @@ flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_h
     }
 }
 
+// leaf traversal record (bvh.cuh): exact box | P0 P1 P2 | triangle id.  wt = the triangle's wtri slot.
+__device__ __forceinline__ void store_leaf_record(uint4* __restrict__ pairs, uint32_t p, const float4 lo, const float4 hi,
+                                                  const float4* __restrict__ wt, uint32_t tri) {
+    const float4 a = __ldg(wt), b = __ldg(wt + 1), c = __ldg(wt + 2);  // (P0.xyz,P1.x)(P1.yz,P2.xy)(P2.z,-,-,-)
+    float* dst = reinterpret_cast<float*>(pairs + (size_t)p * 4);
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(dst), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(a.x), "f"(a.y) : "memory");
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(dst + 8), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x),
+                   "f"(__uint_as_float(tri)) : "memory");
+}
+__device__ __forceinline__ void store_inner_record(uint4* __restrict__ pairs, uint32_t p, const uint4 o0, const uint4 o1) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(pairs + (size_t)p * 4), "r"(o0.x), "r"(o0.y), "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
+                 : "memory");
+}
+
 // Pass 2, one thread per flat position p: gathers the 32-byte record of the cluster placed there and
-// streams out the reference's 48-byte node (scene.cpp:189-208) and, for inner nodes, the 64-byte child-pair
-// record of the traversal kernels.  All stores of a warp are contiguous; the left child's record is the
-// next lane's own (position p + 1).
+// streams out the reference's 48-byte node (scene.cpp:189-208) and the traversal record of the position
+// (bvh.cuh: the compressed child pair of an inner node, box + world-space vertices of a leaf).  All stores of
+// a warp are contiguous; the left child's record is the next lane's own (position p + 1).
 __global__ void __launch_bounds__(256)
 flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __restrict__ order,
                     const float4* __restrict__ node, const uint32_t* __restrict__ isize,
-                    rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
+                    const float4* __restrict__ wtri, rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < nb_nodes;
     const uint32_t c = live ? order[p] : 0u;
@@ -653,6 +670,7 @@ flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __rest
     const uint32_t L = __float_as_uint(me.hi.z), R = __float_as_uint(me.hi.w);
     if (leaf) {  // leaves keep 0/0 and their triangle id; the wtri slot (= cluster id) rides in the padding word
         store_node(flat, p, me.lo, me.hi, L, 0u, 0u, c);
+        store_leaf_record(pairs, p, me.lo, me.hi, wtri + 3 * (size_t)c, L);
         return;
     }
     const bool lleaf = L < n_leaves, rleaf = R < n_leaves;
@@ -661,43 +679,48 @@ flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __rest
     const Box br = load_box(node, R);
     const Box bl = (lane_id() < 31u) ? nx : load_box(node, L);
     store_node(flat, p, me.lo, me.hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
-    // (L.min.xyz, L.max.x) (L.max.yz, R.min.xy) (R.min.z, R.max.xyz) (L.word, R.word, L.aux, R.aux)
-    float* dst = reinterpret_cast<float*>(pairs + (size_t)p * 4);
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"l"(dst), "f"(bl.lo.x), "f"(bl.lo.y), "f"(bl.lo.z), "f"(bl.lo.w), "f"(bl.hi.x), "f"(bl.hi.y),
-                   "f"(br.lo.x), "f"(br.lo.y) : "memory");
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"l"(dst + 8), "f"(br.lo.z), "f"(br.lo.w), "f"(br.hi.x), "f"(br.hi.y),
-                   "f"(__uint_as_float(lleaf ? (0x80000000u | pos_l) : pos_l)),
-                   "f"(__uint_as_float(rleaf ? (0x80000000u | pos_r) : pos_r)),
-                   "f"(__uint_as_float(lleaf ? L : 0u)), "f"(__uint_as_float(rleaf ? R : 0u)) : "memory");
+    uint4 o0, o1;
+    trav_encode_inner(me.lo, make_float2(me.hi.x, me.hi.y), bl.lo, make_float2(bl.hi.x, bl.hi.y),
+                      br.lo, make_float2(br.hi.x, br.hi.y), lleaf, rleaf, pos_r, o0, o1);
+    store_inner_record(pairs, p, o0, o1);
 }
 
 __global__ void flatten_root_kernel(uint32_t* order, uint32_t root) { order[0] = root; }
 
-__global__ void flatten_single_leaf_kernel(const float4* node, rtr_node* flat) {
+__global__ void flatten_single_leaf_kernel(const float4* node, const float4* wtri, rtr_node* flat, uint4* pairs) {
     const Box bx_ = load_box(node, 0); const float4 lo = bx_.lo, hi = bx_.hi;
     store_node(flat, 0, lo, hi, __float_as_uint(hi.z), 0u, 0u, 0u);
+    store_leaf_record(pairs, 0, lo, hi, wtri, __float_as_uint(hi.z));
 }
 
-// child-pair records for the traversal kernels (layout in bvh.cuh): pure repacking of the flat array
+// traversal records (bvh.cuh) of an adopted / received flat array
 __global__ void __launch_bounds__(256)
-pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t by_rank, uint4* __restrict__ pairs) {
+pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t by_rank, const float4* __restrict__ wtri,
+                  uint4* __restrict__ pairs, TraceParams* __restrict__ tparams) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_nodes) return;
-    const uint4 links = __ldg(reinterpret_cast<const uint4*>(flat + i) + 2);
-    if (links.y == 0u && links.z == 0u) return;  // leaf: no record
+    const uint4* me = reinterpret_cast<const uint4*>(flat + i);
+    const uint4 m0 = __ldg(me), m1 = __ldg(me + 1), links = __ldg(me + 2);
+    const float4 nlo = make_float4(__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z), __uint_as_float(m1.x));
+    const float4 nhi = make_float4(__uint_as_float(m1.y), __uint_as_float(m1.z), 0.f, 0.f);
+    if (links.y == 0u && links.z == 0u) {
+        const uint32_t slot = by_rank ? links.w : links.x;
+        store_leaf_record(pairs, i, nlo, nhi, wtri + 3 * (size_t)slot, links.x);
+        return;
+    }
+    if (links.y != i + 1u) atomicAdd(&tparams->bad_layout, 1u);  // not the DFS pre-order of scene.cpp:189-208
     const uint4* l = reinterpret_cast<const uint4*>(flat + links.y);
     const uint4* r = reinterpret_cast<const uint4*>(flat + links.z);
     const uint4 l0 = __ldg(l), l1 = __ldg(l + 1), l2 = __ldg(l + 2);
     const uint4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
     const bool lleaf = l2.y == 0u && l2.z == 0u, rleaf = r2.y == 0u && r2.z == 0u;
-    uint4* dst = pairs + (size_t)i * 4;
-    dst[0] = make_uint4(l0.x, l0.y, l0.z, l1.x);
-    dst[1] = make_uint4(l1.y, l1.z, r0.x, r0.y);
-    dst[2] = make_uint4(r0.z, r1.x, r1.y, r1.z);
-    dst[3] = make_uint4(lleaf ? (0x80000000u | links.y) : links.y, rleaf ? (0x80000000u | links.z) : links.z,
-                        lleaf ? (by_rank ? l2.w : l2.x) : 0u, rleaf ? (by_rank ? r2.w : r2.x) : 0u);
+    uint4 o0, o1;
+    trav_encode_inner(nlo, make_float2(nhi.x, nhi.y),
+                      make_float4(__uint_as_float(l0.x), __uint_as_float(l0.y), __uint_as_float(l0.z), __uint_as_float(l1.x)),
+                      make_float2(__uint_as_float(l1.y), __uint_as_float(l1.z)),
+                      make_float4(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r1.x)),
+                      make_float2(__uint_as_float(r1.y), __uint_as_float(r1.z)), lleaf, rleaf, links.z, o0, o1);
+    store_inner_record(pairs, i, o0, o1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -740,7 +763,15 @@ int rtr_bvh_compute_trace_params(rtr_bvh* b) {
     }
     b->wtri_view = b->wtri_own;
     b->wtri_by_rank = false;
-    return rtr_bvh_pack_pairs_own(b);
+    RTR_CHECK(rtr_bvh_pack_pairs_own(b));
+    // the traversal records rely on the left child sitting at index + 1 (scene.cpp:189-199 always produces that)
+    TraceParams* h = static_cast<TraceParams*>(ctx->pinned);
+    RTR_CUDA(ctx, cudaMemcpyAsync(h, b->tparams, sizeof(TraceParams), cudaMemcpyDeviceToHost, ctx->stream));
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h->bad_layout)
+        return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "adopted node array is not in DFS pre-order: %u inner nodes have Left != index + 1",
+                             h->bad_layout);
+    return RTR_OK;
 }
 
 int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
@@ -753,7 +784,8 @@ int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
         b->pairs_own_cap = b->n;
     }
     const uint32_t nc = 2 * b->n - 1;
-    pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->pairs_own);
+    pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->wtri_view,
+                                                                 b->pairs_own, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
     b->pairs_view = b->pairs_own;
     return RTR_OK;
@@ -848,7 +880,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
 
     // 5. flatten, last creation level first
     if (n == 1) {
-        flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node, b->flat);
+        flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node, b->wtri, b->flat, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     } else {
         uint32_t* order = b->order;
@@ -877,7 +909,7 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         }
         const uint32_t nc = 2 * n - 1;
         RTR_PROF(ctx, "flatten_emit_kernel");
-        flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, n, order, b->node, b->isize, b->flat, b->pairs);
+        flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, n, order, b->node, b->isize, b->wtri, b->flat, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     }
     b->pairs_view = b->pairs;  // written by the flatten kernels

@@ -52,7 +52,7 @@ __device__ __forceinline__ Hit no_hit() {
 struct Accel {
     const rtr_node* __restrict__ nodes;
     const float4* __restrict__ wtri;
-    const uint4* __restrict__ pairs;  // child-pair records (bvh.cuh), default traversal only
+    const uint4* __restrict__ pairs;  // traversal records (bvh.cuh: TravRec), default traversal only
     uint32_t by_rank;  // 1: wtri slot = leaf's third padding word (built here); 0: slot = triangle id (adopted nodes)
 };
 
@@ -114,19 +114,33 @@ __device__ __forceinline__ TriWorld shader_vertices(const float4* __restrict__ w
     return w;
 }
 
-// raytracer.glsl:102-147
-__device__ __forceinline__ bool ray_triangle(const Ray& r, const float4* __restrict__ wtri, uint32_t slot,
-                                             uint32_t tri, Hit& hit) {
-    const TriWorld w = shader_vertices(wtri, slot);
+// raytracer.glsl:102-147 on world-space vertices in shader naming
+__device__ __forceinline__ bool ray_triangle_w(const Ray& r, const TriWorld& w, uint32_t slot, uint32_t tri, Hit& hit) {
     const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
     const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
     float nx, ny, nz;
     cross3(e1x, e1y, e1z, e0x, e0y, e0z, nx, ny, nz);
-    normalize3(nx, ny, nz);
     float qx, qy, qz;
     cross3(r.dx, r.dy, r.dz, e1x, e1y, e1z, qx, qy, qz);
     const float a = dot3(e0x, e0y, e0z, qx, qy, qz);
-    if (dot3(nx, ny, nz, r.dx, r.dy, r.dz) >= 0.f || fabsf(a) < 1e-4f) return false;
+    if (fabsf(a) < 1e-4f) return false;  // the shader's "facing away || |a| < 1e-4" has no side effects: order is free
+    // Facing test dot(normalize(n), d) >= 0 (raytracer.glsl:112-119).  Only its sign matters, and with
+    // D = n.d the normalised value differs from D/|n| by less than 4.3u|d| while the plain fp32
+    // dot3(n, d) differs from D by less than 3.1u|n||d|: beyond |dot3(n, d)| > 2e-6 |n||d| both have D's
+    // sign, and the square root and three divisions are skipped.  Closer to zero (or out of fp32's
+    // normal range) the shader's own expression decides.
+    {
+        const float sd = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
+        const float n2 = dot3(nx, ny, nz, nx, ny, nz);
+        const float d2 = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+        const float bound = 4.1e-12f * n2 * d2;
+        if (n2 > 1e-30f && n2 < 1e30f && d2 > 1e-30f && d2 < 1e30f && sd * sd > bound) {
+            if (sd > 0.f) return false;
+        } else {
+            normalize3(nx, ny, nz);
+            if (dot3(nx, ny, nz, r.dx, r.dy, r.dz) >= 0.f) return false;
+        }
+    }
     const float sx = __fdiv_rn(__fsub_rn(r.ox, w.p0.x), a);
     const float sy = __fdiv_rn(__fsub_rn(r.oy, w.p0.y), a);
     const float sz = __fdiv_rn(__fsub_rn(r.oz, w.p0.z), a);
@@ -140,6 +154,10 @@ __device__ __forceinline__ bool ray_triangle(const Ray& r, const float4* __restr
     if (t < 0.f) return false;
     hit.b0 = bx; hit.b1 = by; hit.b2 = bz; hit.t = t; hit.did_hit = 1u; hit.tri = tri; hit.slot = slot;
     return true;
+}
+__device__ __forceinline__ bool ray_triangle(const Ray& r, const float4* __restrict__ wtri, uint32_t slot,
+                                             uint32_t tri, Hit& hit) {
+    return ray_triangle_w(r, shader_vertices(wtri, slot), slot, tri, hit);
 }
 
 // raytracer.glsl:182-237 (edge code 2 folded into "hit"); IEEE fminf/fmaxf (Q11)
@@ -334,16 +352,19 @@ __device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, c
 }
 
 // hit frame shared by both secondary rays: unit front normal and offset origin h + n*1e-3
-__device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const Accel& A, float& nx, float& ny, float& nz,
-                                          float& ox, float& oy, float& oz) {
-    const TriWorld w = shader_vertices(A.wtri, h.slot);
+__device__ __forceinline__ void hit_frame_w(const Ray& r, float t, const TriWorld& w, float& nx, float& ny, float& nz,
+                                            float& ox, float& oy, float& oz) {
     const float e0x = __fsub_rn(w.p1.x, w.p0.x), e0y = __fsub_rn(w.p1.y, w.p0.y), e0z = __fsub_rn(w.p1.z, w.p0.z);
     const float e1x = __fsub_rn(w.p2.x, w.p0.x), e1y = __fsub_rn(w.p2.y, w.p0.y), e1z = __fsub_rn(w.p2.z, w.p0.z);
     cross3(e1x, e1y, e1z, e0x, e0y, e0z, nx, ny, nz);
     normalize3(nx, ny, nz);
-    ox = __fadd_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, h.t)), __fmul_rn(nx, 1e-3f));
-    oy = __fadd_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, h.t)), __fmul_rn(ny, 1e-3f));
-    oz = __fadd_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, h.t)), __fmul_rn(nz, 1e-3f));
+    ox = __fadd_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, t)), __fmul_rn(nx, 1e-3f));
+    oy = __fadd_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, t)), __fmul_rn(ny, 1e-3f));
+    oz = __fadd_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, t)), __fmul_rn(nz, 1e-3f));
+}
+__device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const Accel& A, float& nx, float& ny, float& nz,
+                                          float& ox, float& oy, float& oz) {
+    hit_frame_w(r, h.t, shader_vertices(A.wtri, h.slot), nx, ny, nz, ox, oy, oz);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -505,6 +526,10 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 #endif
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
+#ifndef RTR_BLOCK_BATCH
+#define RTR_BLOCK_BATCH 2
+#endif
+constexpr uint32_t kBlockBatch = RTR_BLOCK_BATCH;  // ... or once this many lanes wait on a second leaf
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDry = 0xFFFFFFFFu;  // stack ran dry (also the state of an idle lane)
 #ifndef RTR_SMEM_STACK
@@ -531,18 +556,34 @@ struct JobDesc {
     int want_any;
 };
 
-// Lane state is kept small (occupancy hides the node-fetch latency): the node being expanded is the pair
-// (a, b) = (left, right) of an inner node or (kLeafBit | index, wtri slot) of a leaf, stack entries carry
-// the same pair plus the entry distance so a pop needs no global load, and the best hit is (t, leaf index)
-// only -- its barycentrics and triangle id are regenerated by one more ray_triangle when the ray finishes.
+// Lane state is kept small (occupancy hides the node-fetch latency): the node being expanded is one word --
+// an inner flat index, or kLeafBit | index for a leaf -- stack entries carry that word plus the entry
+// distance, and the best hit is (t, leaf index) only: its barycentrics and triangle id are regenerated by one
+// more ray_triangle when the ray finishes.
+//
+// Inner nodes are expanded from the 32-byte compressed record (bvh.cuh) -- ONE 256-bit load per lane where
+// two 48-byte nodes took six 128-bit loads and the uncompressed pair two 256-bit ones; the kernel is bound by
+// L1 wavefronts of exactly these divergent loads.  The compressed child boxes are supersets, evaluated here
+// with an error margin that also covers the rounding of the reference's own slab test, so that
+//     reference slab test passes on the exact box  ==>  compressed test passes            (*)
+// and the entry distance computed here is a lower bound of the reference's.  With the node origin c, grid
+// step s = 2^e, plane byte q and the ray (o, inv = 1/d), per axis
+//     a = s*inv (exact), b = fl(fl(c - o)*inv), x = 2^23 + q (exact, built by PRMT),
+//     t = fl(x*a + fl(fl(b -+ m) - 2^23*a))
+// differs from the real (c + q*s - o)*inv by at most |a|/2 + 5u(|b| + 256|a|), the reference's
+// fl(fl(X - o)*inv) from its real value by at most 2.01u(|b| + 256|a|) (u = 2^-24): the margin
+// m = 0.52|a| + 2e-6|b| + 1e-30 covers both with room.  A ray with an |inv| not below 2^64 (d = 0, where
+// the reference's inf/NaN arithmetic decides, or so small that a product could overflow) takes the
+// reference's slab test on the decoded superset boxes instead (monotone in the box, hence (*) again).  A
+// leaf is then tested exactly as in the reference: slab test on its own exact box, ray/triangle on its vertices, both
+// from its 64-byte record.
 __global__ void __launch_bounds__(kTraceBlock, RTR_TRACE_MIN_CTAS)
 trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDesc jd,
                         unsigned long long* __restrict__ rays_traced) {
-    // Traversal stack: the top kSmemStack entries of every thread live in shared memory, laid out
+    // Traversal stack: a window of kSmemStack entries of every thread lives in shared memory, laid out
     // [word][depth][thread] so that any mix of depths across a warp is bank-conflict free (bank = lane);
-    // a divergent local-memory access would cost one L1 tag lookup per lane instead.  Deeper entries
-    // spill to local memory.
-    __shared__ uint32_t s_stack[3][kSmemStack][kTraceBlock];
+    // a divergent local-memory access would cost one L1 wavefront per lane instead.
+    __shared__ uint32_t s_stack[2][kSmemStack][kTraceBlock];
     __shared__ float s_pb[2];                   // pruning bound constants k, k*Emax (negative k: disabled)
     __shared__ float s_stash[6][kTraceBlock];   // normal + incoming direction while a shadow ray is out
     if (threadIdx.x == 0) {
@@ -563,14 +604,15 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     float best_t = INFINITY;        // closest hit so far; for an any-hit ray: its t_max
     uint32_t best_node = RTR_NONE;  // leaf of the best hit
     float limit = INFINITY;
-    uint32_t a = kDry, b = 0u;      // node being expanded: inner flat index, or kLeafBit | index with b = wtri slot
-    uint32_t pend_node = RTR_NONE, pend_slot = 0u;
+    uint32_t a = kDry;              // node being expanded: inner flat index, or kLeafBit | index
+    uint32_t pend_node = RTR_NONE;  // parked leaf
     int sp = 0;
-    uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen
+    uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen,
+                                    // bit 18 ray with a (nearly) zero direction component
     float L = 0.f;
     int win_lo = 0;                 // first stack entry held in shared memory
     float stack_t[kStack - kSmemStack];   // entries below the window (index < kStack - kSmemStack always)
-    uint32_t stack_a[kStack - kSmemStack], stack_b[kStack - kSmemStack];
+    uint32_t stack_a[kStack - kSmemStack];
 
     auto limit_of = [&](float t) -> float {
         const float k = s_pb[0];
@@ -579,31 +621,29 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
 
     // begin walking ray r: root test (raytracer.glsl:255-262 pops node 0 first)
     auto start_ray = [&](bool any, float tm) {
-        st = (st & 0xFFFFu) | (any ? 0x10000u : 0u) | (st & 0x20000u);
+        st = (st & 0xFFFFu) | (any ? 0x10000u : 0u) | (st & 0x20000u);  // clears bit 18
         best_t = tm; best_node = RTR_NONE; sp = 0; win_lo = 0; pend_node = RTR_NONE;
         limit = any ? limit_of(tm) : INFINITY;
+        // the compressed test needs every |1/d| below 2^64 (false for inf and NaN too)
+        if (!(fabsf(r.ix) < 1.8e19f && fabsf(r.iy) < 1.8e19f && fabsf(r.iz) < 1.8e19f)) st |= 0x40000u;
         const NodeRec root = load_node(A.nodes, 0u);
         float te;
         a = kDry;
-        if (intersect_box(r, root.lo, root.hi, te) && !(te > limit)) {
-            if (is_leaf(root.links)) { a = kLeafBit; b = slot_of(A, root.links); }
-            else a = 0u;
-        }
+        if (intersect_box(r, root.lo, root.hi, te) && !(te > limit)) a = is_leaf(root.links) ? kLeafBit : 0u;
     };
     // Stack entries [win_lo, sp) live in shared memory at slot (index % kSmemStack) -- a window that follows the
     // top of the stack, where a depth-first walk does nearly all of its pushes and pops -- entries [0, win_lo)
     // in local memory.  A push into a full window moves its oldest entry out; a pop below the window reads
     // local memory directly.
-    auto push_far = [&](float tf, uint32_t fa, uint32_t fb) {
+    auto push_far = [&](float tf, uint32_t fa) {
         if (sp >= kStack) { st |= 0x20000u; return; }
         const int slot = sp & (kSmemStack - 1);
         if (sp - win_lo == kSmemStack) {  // slot holds entry win_lo: spill it
             stack_t[win_lo] = __uint_as_float(s_stack[0][slot][threadIdx.x]);
             stack_a[win_lo] = s_stack[1][slot][threadIdx.x];
-            stack_b[win_lo] = s_stack[2][slot][threadIdx.x];
             ++win_lo;
         }
-        s_stack[0][slot][threadIdx.x] = __float_as_uint(tf); s_stack[1][slot][threadIdx.x] = fa; s_stack[2][slot][threadIdx.x] = fb;
+        s_stack[0][slot][threadIdx.x] = __float_as_uint(tf); s_stack[1][slot][threadIdx.x] = fa;
         ++sp;
     };
     auto pop_next = [&]() {
@@ -613,14 +653,40 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             if (sp >= win_lo) {
                 const int slot = sp & (kSmemStack - 1);
                 if (__uint_as_float(s_stack[0][slot][threadIdx.x]) > limit) continue;
-                a = s_stack[1][slot][threadIdx.x]; b = s_stack[2][slot][threadIdx.x];
+                a = s_stack[1][slot][threadIdx.x];
             } else {
                 win_lo = sp;
                 if (stack_t[sp] > limit) continue;
-                a = stack_a[sp]; b = stack_b[sp];
+                a = stack_a[sp];
             }
             break;
         }
+    };
+    // one axis of the compressed pair test: updates (near, far) of the left and of the right child
+    auto axis_planes = [&](float c, uint32_t ebyte, uint32_t quad, float o, float j,
+                           float& tnl, float& tfl, float& tnr, float& tfr) {
+        const float step = __uint_as_float(ebyte << 23);
+        const float sa = __fmul_rn(step, j);
+        const float sb = __fmul_rn(__fsub_rn(c, o), j);
+        const float m = __fmaf_rn(fabsf(sa), 0.52f, __fmaf_rn(fabsf(sb), 2e-6f, 1e-30f));
+        const float bn = __fmaf_rn(-8388608.f, sa, __fsub_rn(sb, m));
+        const float bf = __fmaf_rn(-8388608.f, sa, __fadd_rn(sb, m));
+        // bytes (Llo, Lhi, Rlo, Rhi) -> (Lnear, Lfar, Rnear, Rfar)
+        const uint32_t w = __byte_perm(quad, quad, j < 0.f ? 0x2301u : 0x3210u);
+        const float x0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u));
+        const float x1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651u));
+        const float x2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652u));
+        const float x3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653u));
+        tnl = fmaxf(tnl, __fmaf_rn(x0, sa, bn)); tfl = fminf(tfl, __fmaf_rn(x1, sa, bf));
+        tnr = fmaxf(tnr, __fmaf_rn(x2, sa, bn)); tfr = fminf(tfr, __fmaf_rn(x3, sa, bf));
+    };
+    // decoded planes of one axis, rounded outwards: min planes down, max planes up
+    auto decode_axis = [&](float c, uint32_t ebyte, uint32_t quad, float& llo, float& lhi, float& rlo, float& rhi) {
+        const float step = __uint_as_float(ebyte << 23);
+        llo = __fadd_rd(c, __fmul_rn(__uint2float_rn(quad & 0xFFu), step));
+        lhi = __fadd_ru(c, __fmul_rn(__uint2float_rn((quad >> 8) & 0xFFu), step));
+        rlo = __fadd_rd(c, __fmul_rn(__uint2float_rn((quad >> 16) & 0xFFu), step));
+        rhi = __fadd_ru(c, __fmul_rn(__uint2float_rn(quad >> 24), step));
     };
     auto job_pixel = [&](uint32_t j, uint32_t& x, uint32_t& y, uint32_t& out_row) -> bool {
         const uint32_t tiles_x = (jd.width + 7u) / 8u;
@@ -675,36 +741,52 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
 
         // ---- walk: one step per iteration for every lane that can move (idle lanes keep a == 0) ----
         while (true) {
+            bool need_pop = false;
             if (a != kDry) {
                 if (a & kLeafBit) {
                     if (pend_node == RTR_NONE) {  // park the leaf and keep walking
-                        pend_node = a & ~kLeafBit; pend_slot = b;
-                        pop_next();
+                        pend_node = a & ~kLeafBit;
+                        need_pop = true;
                     }
                 } else {
-                    // one 64-byte record = two 256-bit loads (LDG.E.256, sm_100+): one L1 data-pipe pass per
-                    // 32-byte sector instead of two
-                    uint4 c0, c1, c2, c3;
+                    // compressed child pair: one 256-bit load (LDG.E.256, sm_100+)
+                    uint4 c0, c1;
                     ld_nc_256(A.pairs + (size_t)a * 4, c0, c1);
-                    ld_nc_256(A.pairs + (size_t)a * 4 + 2, c2, c3);
-                    const float4 llo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
-                    const float4 lhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
-                    const float4 rlo = make_float4(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x), 0.f);
-                    const float4 rhi = make_float4(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w), 0.f);
-                    float tl, tr;
-                    const bool hl = intersect_box(r, llo, lhi, tl) && !(tl > limit);
-                    const bool hr = intersect_box(r, rlo, rhi, tr) && !(tr > limit);
+                    float tl = -INFINITY, fl = INFINITY, tr = -INFINITY, fr = INFINITY;
+                    const uint32_t flags = c0.w >> 24;
+                    bool hl, hr;
+                    if (st & 0x40000u) {
+                        // a direction component is 0 (or nearly): the reference's own slab test -- it is what defines
+                        // the outcome for a ray parallel to a slab (Q11) -- on the decoded superset boxes
+                        float4 llo, lhi, rlo, rhi;
+                        decode_axis(__uint_as_float(c0.x), c0.w & 0xFFu, c1.x, llo.x, lhi.x, rlo.x, rhi.x);
+                        decode_axis(__uint_as_float(c0.y), (c0.w >> 8) & 0xFFu, c1.y, llo.y, lhi.y, rlo.y, rhi.y);
+                        decode_axis(__uint_as_float(c0.z), (c0.w >> 16) & 0xFFu, c1.z, llo.z, lhi.z, rlo.z, rhi.z);
+                        hl = intersect_box(r, llo, lhi, tl);
+                        hr = intersect_box(r, rlo, rhi, tr);
+                        if (flags & 4u) { hl = hr = true; tl = tr = -INFINITY; }
+                        hl = hl && !(tl > limit);
+                        hr = hr && !(tr > limit);
+                    } else {
+                        axis_planes(__uint_as_float(c0.x), c0.w & 0xFFu, c1.x, r.ox, r.ix, tl, fl, tr, fr);
+                        axis_planes(__uint_as_float(c0.y), (c0.w >> 8) & 0xFFu, c1.y, r.oy, r.iy, tl, fl, tr, fr);
+                        axis_planes(__uint_as_float(c0.z), (c0.w >> 16) & 0xFFu, c1.z, r.oz, r.iz, tl, fl, tr, fr);
+                        if (flags & 4u) { tl = tr = -INFINITY; fl = fr = INFINITY; }  // box outside the encodable range
+                        hl = fl >= 0.f && tl <= fl && !(tl > limit);
+                        hr = fr >= 0.f && tr <= fr && !(tr > limit);
+                    }
+                    const uint32_t lw = (a + 1u) | ((flags & 1u) ? kLeafBit : 0u);
+                    const uint32_t rw = c1.w | ((flags & 2u) ? kLeafBit : 0u);
                     if (hl && hr) {
                         const bool left_first = tl <= tr;
-                        const float tf = left_first ? tr : tl;
-                        const uint32_t fa = left_first ? c3.y : c3.x, fb = left_first ? c3.w : c3.z;  // far child -> stack
-                        push_far(tf, fa, fb);
-                        a = left_first ? c3.x : c3.y; b = left_first ? c3.z : c3.w;
-                    } else if (hl) { a = c3.x; b = c3.z; }
-                    else if (hr) { a = c3.y; b = c3.w; }
-                    else pop_next();
+                        push_far(left_first ? tr : tl, left_first ? rw : lw);
+                        a = left_first ? lw : rw;
+                    } else if (hl) a = lw;
+                    else if (hr) a = rw;
+                    else need_pop = true;
                 }
             }
+            if (need_pop) pop_next();  // one site: lanes coming from a parked leaf and from a double miss pop together
             const bool busy = job != RTR_NONE;
             const bool blocked = a != kDry && (a & kLeafBit) != 0u && pend_node != RTR_NONE;
             const uint32_t m_blocked = __ballot_sync(0xffffffffu, blocked);
@@ -713,16 +795,29 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             const uint32_t m_dry = __ballot_sync(0xffffffffu, busy && a == kDry);
             const uint32_t movable = m_walk & ~m_blocked;
             const bool want_fin = m_dry != 0u && ((uint32_t)__popc(m_dry) >= kFinBatch || (uint32_t)__popc(m_walk) < 16u);
-            if (m_blocked != 0u || (uint32_t)__popc(m_pend) >= kLeafBatch || movable == 0u || (want_fin && (m_dry & m_pend) != 0u)) {
-                // ---- triangle step: every parked leaf of the warp ----
+            if ((uint32_t)__popc(m_blocked) >= kBlockBatch || (uint32_t)__popc(m_pend) >= kLeafBatch || movable == 0u || (want_fin && (m_dry & m_pend) != 0u)) {
+                // ---- leaf step: every parked leaf of the warp.  The reference's own two tests, on the exact
+                //      box and the vertices of the 64-byte leaf record ----
                 if (pend_node != RTR_NONE) {
-                    Hit h;
-                    if (ray_triangle(r, A.wtri, pend_slot, 0u, h)) {
-                        if (st & 0x10000u) {
-                            if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; win_lo = 0; }
-                        } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
-                            best_t = h.t; best_node = pend_node;
-                            limit = limit_of(h.t);
+                    uint4 c0, c1, c2, c3;
+                    ld_nc_256(A.pairs + (size_t)pend_node * 4, c0, c1);
+                    ld_nc_256(A.pairs + (size_t)pend_node * 4 + 2, c2, c3);
+                    const float4 blo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
+                    const float4 bhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
+                    float te;
+                    if (intersect_box(r, blo, bhi, te) && !(te > limit)) {
+                        TriWorld w;  // shader naming (Q8): _P1 = host P2, _P2 = host P1
+                        w.p0 = make_float3(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x));
+                        w.p2 = make_float3(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w));
+                        w.p1 = make_float3(__uint_as_float(c3.x), __uint_as_float(c3.y), __uint_as_float(c3.z));
+                        Hit h;
+                        if (ray_triangle_w(r, w, 0u, 0u, h)) {
+                            if (st & 0x10000u) {
+                                if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; win_lo = 0; }
+                            } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
+                                best_t = h.t; best_node = pend_node;
+                                limit = limit_of(h.t);
+                            }
                         }
                     }
                     pend_node = RTR_NONE;
@@ -738,11 +833,18 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             const bool any_mode = (st & 0x10000u) != 0u;
             // regenerate the record of the best hit (same inputs, same ops => same bits)
             Hit best = no_hit();
+            TriWorld bw;
+            bw.p0 = bw.p1 = bw.p2 = make_float3(0.f, 0.f, 0.f);
             if (best_node != RTR_NONE) {
                 if (any_mode) best.did_hit = 1u;
                 else {
-                    const uint4 bl = load_links(A.nodes, best_node);
-                    ray_triangle(r, A.wtri, slot_of(A, bl), bl.x, best);
+                    uint4 c0, c1, c2, c3;
+                    ld_nc_256(A.pairs + (size_t)best_node * 4, c0, c1);
+                    ld_nc_256(A.pairs + (size_t)best_node * 4 + 2, c2, c3);
+                    bw.p0 = make_float3(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x));
+                    bw.p2 = make_float3(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w));
+                    bw.p1 = make_float3(__uint_as_float(c3.x), __uint_as_float(c3.y), __uint_as_float(c3.z));
+                    ray_triangle_w(r, bw, 0u, c3.w, best);
                 }
             }
             if (jd.kind != 0u) {
@@ -760,7 +862,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     if (!best.did_hit) {
                         path_done = true;
                     } else {
-                        hit_frame(r, best, A, nx, ny, nz, ox, oy, oz);
+                        hit_frame_w(r, best.t, bw, nx, ny, nz, ox, oy, oz);
                         dx = r.dx; dy = r.dy; dz = r.dz;
                         if (jd.shadow) {
                             const float sx = __fsub_rn(jd.lx, ox), sy = __fsub_rn(jd.ly, oy), sz = __fsub_rn(jd.lz, oz);
