@@ -46,6 +46,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-kernel side measurements")
     p.add_argument("--reference-order", action="store_true", help="trace in the shader's exact visiting order (no pruning)")
+    p.add_argument("--reserve-sms", type=int, default=16,
+                   help="N>1: SMs the traversal leaves free for the NCCL kernels of the broadcast in flight")
+    p.add_argument("--no-pipeline", action="store_true", help="N>1: rebuild, broadcast, render and gather strictly in sequence")
     return p.parse_args()
 
 
@@ -300,7 +303,9 @@ def main():
             fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        return reduce_timing(e0.elapsed_time(e1), launches0)
+
+    def reduce_timing(ms, launches0):
         launches = ctx.launch_count - launches0
         rays = int(d_rays.item())
         if world > 1:
@@ -312,21 +317,109 @@ def main():
             rays, launches = int(r[0].item()), int(r[1].item())
         return ms, rays, launches
 
+    # ---- N > 1: pipelined frames.  Rank 0 rebuilds and broadcasts frame f+1 (stream B) while every rank traces
+    #      its rows of frame f (stream R); two BVHs alternate.  The row blocks are dealt with weights so that the
+    #      rebuilding rank, which has less time left for rays, gets fewer of them (parallel.stripe_layout). ----
+    pipelined = world > 1 and not args.no_pipeline
+    layout = [1] * world
+    if pipelined:
+        stream_b = torch.cuda.Stream(device=dev)
+        stream_r = stream
+        bvhs = [bvh, capi.Bvh(ctx)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]       # BVH k rebuilt and received
+        released = [torch.cuda.Event(), torch.cuda.Event()]    # the rays of the frame that used BVH k are done
+        ctx.reserve_sms(args.reserve_sms)
+
+        def submit_build(f, e2e):
+            k = f % 2
+            ctx.switch_stream(stream_b.cuda_stream)
+            stream_b.wait_event(released[k])
+            if rank == 0:
+                if e2e:
+                    bvhs[k].build(tris_pinned.numpy().view(TRIANGLE), meshes_np)
+                else:
+                    bvhs[k].build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            bvhs[k].broadcast(0)
+            ready[k].record(stream_b)
+
+        def submit_render(f, e2e):
+            k = f % 2
+            ctx.switch_stream(stream_r.cuda_stream)
+            stream_r.wait_event(ready[k])
+            bvhs[k].render_stripes_dev(cam, W, H, d_rgba.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
+                                       bounces=bounces, flags=flags)
+            released[k].record(stream_r)
+            ctx.allgather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, layout)
+            if e2e and rank == 0:
+                ctx.download(rgba_pinned.numpy(), d_rgba.data_ptr())      # D2H of the frame (synchronises stream R)
+
+        def run_pipelined(steps, e2e):
+            submit_build(0, e2e)
+            for f in range(steps):
+                if f + 1 < steps:
+                    submit_build(f + 1, e2e)   # enqueued before the rays of frame f: runs beside them
+                submit_render(f, e2e)
+
+        def timed_pipelined(steps, e2e):
+            barrier(); stream_b.synchronize()
+            with torch.cuda.stream(stream_r):
+                d_rays.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            launches0 = ctx.launch_count
+            stream_r.synchronize()
+            e0.record(stream_r)
+            stream_b.wait_event(e0)            # the first rebuild starts inside the timed region
+            run_pipelined(steps, e2e)
+            stream_r.wait_stream(stream_b)
+            e1.record(stream_r)
+            barrier(); stream_b.synchronize()
+            ctx.switch_stream(stream_r.cuda_stream)
+            return reduce_timing(e0.elapsed_time(e1), launches0)
+
+        # weights from this box's own timings: rebuild + broadcast on rank 0, a full frame of rays on one GPU
+        for _ in range(2):
+            frame_device()
+        barrier()
+        t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t0.record(stream)
+        if rank == 0:
+            bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+        bvh.broadcast(0)
+        t1.record(stream)
+        bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, bounces=bounces, flags=flags)
+        t2.record(stream)
+        barrier()
+        tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2)], dtype=torch.float64, device=dev)
+        dist.broadcast(tt, src=0)
+        serial_ms, render_ms = float(tt[0].item()), float(tt[1].item())
+        layout = parallel.stripe_layout(world, parallel.builder_share_for(serial_ms, render_ms, world))
+        barrier()
+
     # ---- warm-up, then the timed region ----
-    for _ in range(max(3, args.warmup)):
-        frame_device()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms, rays, launches = timed(frame_device, args.steps)
+    if pipelined:
+        run_pipelined(max(3, args.warmup), False)
+        if rank == 0:
+            sampler.start()
+        ms, rays, launches = timed_pipelined(args.steps, False)
+    else:
+        for _ in range(max(3, args.warmup)):
+            frame_device()
+        if rank == 0:
+            sampler.start()
+        ms, rays, launches = timed(frame_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = rays / (ms * 1e-3) / 1e6
 
     # ---- end to end through the host-pointer ABI ----
-    for _ in range(2):
-        frame_e2e()
     e2e_steps = args.steps
-    e2e_ms, e2e_rays, _ = timed(frame_e2e, e2e_steps)
+    if pipelined:
+        run_pipelined(2, True)
+        e2e_ms, e2e_rays, _ = timed_pipelined(e2e_steps, True)
+    else:
+        for _ in range(2):
+            frame_e2e()
+        e2e_ms, e2e_rays, _ = timed(frame_e2e, e2e_steps)
     e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
     h2d = n * TRIANGLE.itemsize + MESH.itemsize + 284
     d2h = H * W * 16
@@ -419,7 +512,9 @@ def main():
                        "triangles": n, "image": [W, H], "traced_pixels": [dw, dh], "bounces": bounces,
                        "rays_per_step": rays // args.steps, "search_radius": 16,
                        "trace_order": "reference" if args.reference_order else "pruned (identical records)",
-                       "parallelism": "build on rank 0 + NCCL broadcast + %d-row blocks dealt to %d rank(s)" % (rpb, world),
+                       "parallelism": ("build on rank 0 + NCCL broadcast + %d-row blocks dealt to %d rank(s)" % (rpb, world)) +
+                                      ((", frames pipelined (rebuild+broadcast of f+1 beside the rays of f), stripes per rank %s, %d SMs left to NCCL"
+                                        % (layout, args.reserve_sms)) if pipelined else ""),
                        "l2": "inputs larger than L2 (640 MB of triangles + 960 MB of nodes per step), no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -431,6 +526,8 @@ def main():
         line.update(extras)
         print(json.dumps(line, default=float))
 
+    if pipelined:
+        bvhs[1].close()
     bvh.close()
     if comm:
         comm.close()

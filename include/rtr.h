@@ -107,6 +107,13 @@ const char* rtr_last_error(const rtr_ctx* ctx);
 int rtr_ctx_sync(rtr_ctx* ctx);
 void* rtr_ctx_stream(rtr_ctx* ctx);                 /* cudaStream_t the ctx launches on */
 int rtr_ctx_set_stream(rtr_ctx* ctx, void* stream); /* adopt a caller-owned cudaStream_t */
+/* Pipelined frames: later calls on this ctx are enqueued on `stream` (borrowed); unlike rtr_ctx_set_stream the
+ * work already enqueued is not waited for, so a caller can alternate between two streams -- rebuild + broadcast
+ * of frame f+1 on one, rays of frame f on the other -- and order them with its own events
+ * (SURVEY.md 8b "build + trace may overlap on different streams"). */
+int rtr_ctx_switch_stream(rtr_ctx* ctx, void* cuda_stream);
+/* the persistent traversal kernel leaves `sms` SMs free, e.g. for the NCCL kernels of a broadcast in flight */
+int rtr_ctx_reserve_sms(rtr_ctx* ctx, uint32_t sms);
 int rtr_ctx_device(const rtr_ctx* ctx);
 int rtr_ctx_sm_count(const rtr_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
@@ -245,6 +252,17 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* c
                            uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
                            float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
+/* weighted dealing: rank r owns stripes_of_rank[r] stripes (host array of nranks entries, at most
+ * RTR_MAX_STRIPES_PER_RANK each, 255 in total; 0 = renders nothing, e.g. a rank busy rebuilding); block b belongs to
+ * stripe b % sum(stripes_of_rank) and the stripes of a cycle are handed out round by round: round k to every rank
+ * with more than k stripes, in rank order.  rtr_render_sharded_dev is the case of one stripe per rank. */
+#define RTR_MAX_STRIPES_PER_RANK 16
+int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
+                           uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
+                           uint32_t rows_per_block, const uint32_t* stripes_of_rank, uint32_t nranks, uint32_t rank,
+                           uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
+                           float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
+
 /* ---- multi-GPU (one process per GPU; NCCL resolved at run time with dlopen("libnccl.so.2"),
  * so inside a torch process it is the very library torch.distributed already loaded) ---- */
 #define RTR_NCCL_UNIQUE_ID_BYTES 128
@@ -256,6 +274,10 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root);
 /* rows of the image are dealt to ranks in blocks of `rows_per_block`, block b -> rank b % nranks */
 int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
                        uint32_t rows_per_block);
+
+/* the same for the weighted dealing of rtr_render_stripes_dev (stripes_of_rank: host array of nranks entries) */
+int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                          uint32_t rows_per_block, const uint32_t* stripes_of_rank);
 
 #ifdef __cplusplus
 }

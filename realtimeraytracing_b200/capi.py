@@ -33,6 +33,7 @@ SYMBOLS = [
     "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
+    "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms",
 ]
 
 
@@ -127,6 +128,10 @@ def load_library():
     L.rtr_comm_destroy.argtypes = [vp]
     L.rtr_bvh_broadcast.argtypes = [vp, pp, i32]
     L.rtr_allgather_rows.argtypes = [vp, vp, u32, u32, u32, u32]
+    L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
+    L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+    L.rtr_ctx_switch_stream.argtypes = [vp, vp]
+    L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     _lib = L
     return L
 
@@ -328,8 +333,22 @@ class Context:
     def comm_destroy(self):
         self.check(self.lib.rtr_comm_destroy(self.handle))
 
+    def switch_stream(self, cuda_stream: int):
+        """Enqueue later calls on `cuda_stream` without waiting for the work already enqueued (pipelined frames)."""
+        self.check(self.lib.rtr_ctx_switch_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def reserve_sms(self, sms: int):
+        self.check(self.lib.rtr_ctx_reserve_sms(self.handle, sms))
+
     def allgather_rows(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int):
         self.check(self.lib.rtr_allgather_rows(self.handle, C.c_void_p(image_dev), width, height, bytes_per_pixel, rows_per_block))
+
+    def allgather_stripes(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int,
+                          stripes_of_rank):
+        """Gathers the blocks of a weighted dealing (parallel.stripe_layout)."""
+        st = np.ascontiguousarray(stripes_of_rank, dtype=np.uint32)
+        self.check(self.lib.rtr_allgather_stripes(self.handle, C.c_void_p(image_dev), width, height, bytes_per_pixel,
+                                                  rows_per_block, _ptr(st)))
 
 
 class Bvh:
@@ -481,6 +500,18 @@ class Bvh:
         self.ctx.check(self.lib.rtr_render_sharded_dev(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w,
                                                        denom_h, rows_per_block, shard_rank, shard_count, bounces,
                                                        1 if shadow else 0, _ptr(light), flags, _ptr(rgba_dev),
+                                                       _ptr(hits_dev), _ptr(rays_dev)))
+
+    def render_stripes_dev(self, camera, width, height, rgba_dev, rows_per_block, stripes_of_rank, rank,
+                           hits_dev=None, rays_dev=None, denom_w=0, denom_h=0, bounces=0, shadow=False,
+                           light=(0.0, 0.0, 0.0), flags=0):
+        """Row blocks dealt with weights (parallel.stripe_layout): this rank renders the blocks of its stripes."""
+        camera = _as(camera, CAMERA)
+        light = np.asarray(light, dtype=np.float32)
+        st = np.ascontiguousarray(stripes_of_rank, dtype=np.uint32)
+        self.ctx.check(self.lib.rtr_render_stripes_dev(self.ctx.handle, self.handle, _ptr(camera), width, height, denom_w,
+                                                       denom_h, rows_per_block, _ptr(st), st.size, rank,
+                                                       bounces, 1 if shadow else 0, _ptr(light), flags, _ptr(rgba_dev),
                                                        _ptr(hits_dev), _ptr(rays_dev)))
 
     def render_dev(self, camera, width, height, rgba_dev, hits_dev=None, rays_dev=None, denom_w=0, denom_h=0, row0=0,

@@ -314,6 +314,22 @@ int rtr_ctx_set_stream(rtr_ctx* ctx, void* stream) {
     ctx->owns_stream = false;
     return RTR_OK;
 }
+int rtr_ctx_switch_stream(rtr_ctx* ctx, void* stream) {
+    if (!ctx) return RTR_E_INVALID;
+    if (ctx->owns_stream && ctx->stream) {  // the ctx's own stream is retired first (this once, with a sync)
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->owns_stream = false;
+    return RTR_OK;
+}
+int rtr_ctx_reserve_sms(rtr_ctx* ctx, uint32_t sms) {
+    if (!ctx) return RTR_E_INVALID;
+    if ((int)sms >= ctx->sm_count) return rtr_set_error(ctx, RTR_E_INVALID, "reserve_sms: %u of %d SMs", sms, ctx->sm_count);
+    ctx->reserved_sms = (int)sms;
+    return RTR_OK;
+}
 int rtr_ctx_device(const rtr_ctx* ctx) { return ctx ? ctx->device : -1; }
 int rtr_ctx_sm_count(const rtr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t rtr_ctx_launch_count(const rtr_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -757,9 +773,35 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam
                            float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
-    if (shard_count == 0) return rtr_set_error(ctx, RTR_E_INVALID, "render: shard_count == 0");
+    if (shard_count == 0 || shard_rank >= shard_count || shard_count > 255)
+        return rtr_set_error(ctx, RTR_E_INVALID, "render: bad shard %u of %u", shard_rank, shard_count);
+    const uint8_t off = (uint8_t)shard_rank;
     return rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, bounces, shadow, light_pos, flags,
-                             rgba_dev, hits_dev, rays_dev, rows_per_block, shard_rank, shard_count);
+                             rgba_dev, hits_dev, rays_dev, rows_per_block, shard_count, 1u, &off);
+}
+
+int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
+                           uint32_t denom_w, uint32_t denom_h, uint32_t rows_per_block, const uint32_t* stripes_of_rank,
+                           uint32_t nranks, uint32_t rank, uint32_t bounces, int shadow, const float light_pos[3],
+                           uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
+    RTR_CHECK(trace_args_ok(ctx, b, cam));
+    if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
+    if (!stripes_of_rank || nranks == 0 || rank >= nranks)
+        return rtr_set_error(ctx, RTR_E_INVALID, "render: bad stripe layout (rank %u of %u)", rank, nranks);
+    const std::vector<int> owner = rtr_stripe_owners(stripes_of_rank, (int)nranks);
+    if (owner.empty() || owner.size() > 255) return rtr_set_error(ctx, RTR_E_INVALID, "render: %zu stripes (1..255)", owner.size());
+    if (stripes_of_rank[rank] > RTR_MAX_STRIPES_PER_RANK)
+        return rtr_set_error(ctx, RTR_E_INVALID, "render: more than %d stripes for one rank", RTR_MAX_STRIPES_PER_RANK);
+    if (owner.size() == 1)  // a single stripe: the whole image (or nothing)
+        return stripes_of_rank[rank] ? rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, bounces, shadow,
+                                                         light_pos, flags, rgba_dev, hits_dev, rays_dev)
+                                     : RTR_OK;
+    uint8_t off[RTR_MAX_STRIPES_PER_RANK];
+    uint32_t mine = 0;
+    for (size_t v = 0; v < owner.size(); ++v)
+        if (owner[v] == (int)rank) off[mine++] = (uint8_t)v;
+    return rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, bounces, shadow, light_pos, flags,
+                             rgba_dev, hits_dev, rays_dev, rows_per_block, (uint32_t)owner.size(), mine, off);
 }
 
 int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height, uint32_t denom_w,

@@ -180,4 +180,5 @@ int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays_de
 int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
                       uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
                       const float light[3], uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev,
-                      uint32_t rows_per_block = 0, uint32_t shard_rank = 0, uint32_t shard_count = 1);
+                      uint32_t rows_per_block = 0, uint32_t total_stripes = 1, uint32_t nb_stripes = 1,
+                      const uint8_t* stripe_offsets = nullptr);

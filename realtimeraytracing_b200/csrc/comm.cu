@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include "bvh.cuh"
+#include <vector>
 
 namespace {
 
@@ -208,6 +209,29 @@ int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t h
         const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
         char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
         RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, (int)(blk % (uint32_t)ctx->nranks),
+                                       ctx->nccl_comm, ctx->stream));
+    }
+    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    return RTR_OK;
+}
+
+int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                          uint32_t rows_per_block, const uint32_t* stripes_of_rank) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!image_dev || width == 0 || height == 0 || bytes_per_pixel == 0 || rows_per_block == 0 || !stripes_of_rank)
+        return rtr_set_error(ctx, RTR_E_INVALID, "allgather_stripes: bad argument");
+    if (ctx->nranks == 1) return RTR_OK;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "allgather_stripes: rtr_comm_init has not been called");
+    const std::vector<int> owner = rtr_stripe_owners(stripes_of_rank, ctx->nranks);  // stripe -> rank
+    if (owner.empty()) return rtr_set_error(ctx, RTR_E_INVALID, "allgather_stripes: no stripes");
+    const size_t row_bytes = (size_t)width * bytes_per_pixel;
+    const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    for (uint32_t blk = 0; blk < blocks; ++blk) {
+        const uint32_t r0 = blk * rows_per_block;
+        const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
+        char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
+        RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, owner[blk % owner.size()],
                                        ctx->nccl_comm, ctx->stream));
     }
     RTR_NCCL(ctx, g_nccl.GroupEnd());

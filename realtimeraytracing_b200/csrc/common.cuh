@@ -20,6 +20,7 @@
 struct rtr_ctx {
     int device = 0;
     int sm_count = RTR_SM_COUNT_B200;
+    int reserved_sms = 0;  // SMs the persistent traversal leaves free (rtr_ctx_reserve_sms)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     uint64_t launches = 0;
@@ -76,6 +77,20 @@ void rtr_prof_end(rtr_ctx* ctx);
     } while (0)
 
 static inline size_t rtr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Weighted dealing of image row blocks (rtr_render_stripes_dev / rtr_allgather_stripes): block b belongs to
+// stripe b % V, V = sum of stripes_of_rank; the stripes of one cycle are handed out round by round -- round k
+// goes to every rank with more than k stripes, in rank order -- so that the ranks' blocks interleave and a
+// partial last cycle cannot favour anyone by more than a block.  Returns the owner of every stripe.
+static inline std::vector<int> rtr_stripe_owners(const uint32_t* stripes_of_rank, int nranks) {
+    std::vector<int> owner;
+    uint32_t most = 0;
+    for (int r = 0; r < nranks; ++r) most = stripes_of_rank[r] > most ? stripes_of_rank[r] : most;
+    for (uint32_t k = 0; k < most; ++k)
+        for (int r = 0; r < nranks; ++r)
+            if (stripes_of_rank[r] > k) owner.push_back(r);
+    return owner;
+}
 
 // ---------------------------------------------------------------------------------------
 // device helpers

@@ -371,15 +371,18 @@ __device__ __forceinline__ void hit_frame(const Ray& r, const Hit& h, const Acce
 // kernels
 // ---------------------------------------------------------------------------------------
 // Which image rows a launch covers: a contiguous range [row0, row0+rows) written at local row
-// indices, or (count > 1) the row blocks dealt to one rank -- block b of rows_per_block rows belongs
-// to rank b % count -- written at their global rows of the full image.
+// indices, or (count > 1) the row blocks dealt to one rank -- block b of rows_per_block rows belongs to
+// stripe b % count, the rank owns the `span` stripes off[0..span) -- written at their global rows of the
+// full image.  (span == 1, off[0] = rank: block b -> rank b % count.)
 struct RowMap {
     uint32_t row0, rows, height;
-    uint32_t rpb, rank, count;
+    uint32_t rpb, count, span;
+    uint8_t off[RTR_MAX_STRIPES_PER_RANK];
 };
 __device__ __forceinline__ bool map_row(const RowMap& m, uint32_t y_local, uint32_t& y, uint32_t& out_row) {
     if (m.count <= 1) { y = m.row0 + y_local; out_row = y_local; return true; }
-    y = (m.rank + (y_local / m.rpb) * m.count) * m.rpb + (y_local % m.rpb);
+    const uint32_t blk = y_local / m.rpb;  // local block: cycle blk / span, stripe off[blk % span]
+    y = ((blk / m.span) * m.count + m.off[blk % m.span]) * m.rpb + (y_local % m.rpb);
     out_row = y;
     return y < m.height;
 }
@@ -526,17 +529,20 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 #endif
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
+#ifndef RTR_WALK_STEPS
+#define RTR_WALK_STEPS 4
+#endif
+constexpr int kWalkSteps = RTR_WALK_STEPS;
 #ifndef RTR_BLOCK_BATCH
-#define RTR_BLOCK_BATCH 2
+#define RTR_BLOCK_BATCH 4
 #endif
 constexpr uint32_t kBlockBatch = RTR_BLOCK_BATCH;  // ... or once this many lanes wait on a second leaf
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDry = 0xFFFFFFFFu;  // stack ran dry (also the state of an idle lane)
 #ifndef RTR_SMEM_STACK
-#define RTR_SMEM_STACK 8
+#define RTR_SMEM_STACK 20
 #endif
 constexpr int kSmemStack = RTR_SMEM_STACK;
-static_assert((kSmemStack & (kSmemStack - 1)) == 0, "the shared-memory stack window is indexed modulo a power of two");
 
 struct JobDesc {
     uint32_t kind;   // 0: pixels (render / primary), 1: explicit rays
@@ -580,7 +586,7 @@ struct JobDesc {
 __global__ void __launch_bounds__(kTraceBlock, RTR_TRACE_MIN_CTAS)
 trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDesc jd,
                         unsigned long long* __restrict__ rays_traced) {
-    // Traversal stack: a window of kSmemStack entries of every thread lives in shared memory, laid out
+    // Traversal stack: the first kSmemStack entries of every thread live in shared memory, laid out
     // [word][depth][thread] so that any mix of depths across a warp is bank-conflict free (bank = lane);
     // a divergent local-memory access would cost one L1 wavefront per lane instead.
     __shared__ uint32_t s_stack[2][kSmemStack][kTraceBlock];
@@ -610,8 +616,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen,
                                     // bit 18 ray with a (nearly) zero direction component
     float L = 0.f;
-    int win_lo = 0;                 // first stack entry held in shared memory
-    float stack_t[kStack - kSmemStack];   // entries below the window (index < kStack - kSmemStack always)
+    float stack_t[kStack - kSmemStack];   // entries the shared-memory part has no room for
     uint32_t stack_a[kStack - kSmemStack];
 
     auto limit_of = [&](float t) -> float {
@@ -622,7 +627,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     // begin walking ray r: root test (raytracer.glsl:255-262 pops node 0 first)
     auto start_ray = [&](bool any, float tm) {
         st = (st & 0xFFFFu) | (any ? 0x10000u : 0u) | (st & 0x20000u);  // clears bit 18
-        best_t = tm; best_node = RTR_NONE; sp = 0; win_lo = 0; pend_node = RTR_NONE;
+        best_t = tm; best_node = RTR_NONE; sp = 0; pend_node = RTR_NONE;
         limit = any ? limit_of(tm) : INFINITY;
         // the compressed test needs every |1/d| below 2^64 (false for inf and NaN too)
         if (!(fabsf(r.ix) < 1.8e19f && fabsf(r.iy) < 1.8e19f && fabsf(r.iz) < 1.8e19f)) st |= 0x40000u;
@@ -631,34 +636,25 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
         a = kDry;
         if (intersect_box(r, root.lo, root.hi, te) && !(te > limit)) a = is_leaf(root.links) ? kLeafBit : 0u;
     };
-    // Stack entries [win_lo, sp) live in shared memory at slot (index % kSmemStack) -- a window that follows the
-    // top of the stack, where a depth-first walk does nearly all of its pushes and pops -- entries [0, win_lo)
-    // in local memory.  A push into a full window moves its oldest entry out; a pop below the window reads
-    // local memory directly.
+    // Stack: entries below kSmemStack in shared memory, deeper ones (rare) in local memory.
     auto push_far = [&](float tf, uint32_t fa) {
-        if (sp >= kStack) { st |= 0x20000u; return; }
-        const int slot = sp & (kSmemStack - 1);
-        if (sp - win_lo == kSmemStack) {  // slot holds entry win_lo: spill it
-            stack_t[win_lo] = __uint_as_float(s_stack[0][slot][threadIdx.x]);
-            stack_a[win_lo] = s_stack[1][slot][threadIdx.x];
-            ++win_lo;
-        }
-        s_stack[0][slot][threadIdx.x] = __float_as_uint(tf); s_stack[1][slot][threadIdx.x] = fa;
-        ++sp;
+        if (sp < kSmemStack) {
+            s_stack[0][sp][threadIdx.x] = __float_as_uint(tf); s_stack[1][sp][threadIdx.x] = fa;
+            ++sp;
+        } else if (sp < kStack) {
+            stack_t[sp - kSmemStack] = tf; stack_a[sp - kSmemStack] = fa;
+            ++sp;
+        } else st |= 0x20000u;
     };
     auto pop_next = [&]() {
         a = kDry;
         while (sp > 0) {
             --sp;
-            if (sp >= win_lo) {
-                const int slot = sp & (kSmemStack - 1);
-                if (__uint_as_float(s_stack[0][slot][threadIdx.x]) > limit) continue;
-                a = s_stack[1][slot][threadIdx.x];
-            } else {
-                win_lo = sp;
-                if (stack_t[sp] > limit) continue;
-                a = stack_a[sp];
-            }
+            float te; uint32_t w;
+            if (sp < kSmemStack) { te = __uint_as_float(s_stack[0][sp][threadIdx.x]); w = s_stack[1][sp][threadIdx.x]; }
+            else { te = stack_t[sp - kSmemStack]; w = stack_a[sp - kSmemStack]; }
+            if (te > limit) continue;
+            a = w;
             break;
         }
     };
@@ -741,6 +737,8 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
 
         // ---- walk: one step per iteration for every lane that can move (idle lanes keep a == 0) ----
         while (true) {
+#pragma unroll 1
+          for (int rep = 0; rep < kWalkSteps; ++rep) {  // the warp-wide bookkeeping below runs once per kWalkSteps steps
             bool need_pop = false;
             if (a != kDry) {
                 if (a & kLeafBit) {
@@ -787,6 +785,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                 }
             }
             if (need_pop) pop_next();  // one site: lanes coming from a parked leaf and from a double miss pop together
+          }
             const bool busy = job != RTR_NONE;
             const bool blocked = a != kDry && (a & kLeafBit) != 0u && pend_node != RTR_NONE;
             const uint32_t m_blocked = __ballot_sync(0xffffffffu, blocked);
@@ -813,7 +812,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         Hit h;
                         if (ray_triangle_w(r, w, 0u, 0u, h)) {
                             if (st & 0x10000u) {
-                                if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; win_lo = 0; }
+                                if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; }
                             } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
                                 best_t = h.t; best_node = pend_node;
                                 limit = limit_of(h.t);
@@ -924,7 +923,7 @@ int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const uint32_t need = (jd.total + kTraceBlock - 1) / kTraceBlock;
-    uint32_t grid = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    uint32_t grid = (uint32_t)((ctx->sm_count - ctx->reserved_sms) * ctas_per_sm);
     if (grid > need) grid = need;
     if (grid == 0) return RTR_OK;
     RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->job_counter, 0, sizeof(uint32_t), ctx->stream));
@@ -973,7 +972,7 @@ int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& c
         return RTR_OK;
     }
     RowMap rm;
-    rm.row0 = row0; rm.rows = rows; rm.height = height; rm.rpb = 1; rm.rank = 0; rm.count = 1;
+    rm.row0 = row0; rm.rows = rows; rm.height = height; rm.rpb = 1; rm.count = 1; rm.span = 1; rm.off[0] = 0;
     return launch_persistent(ctx, b, pixel_jobs(cam, width, denom_w, denom_h, rm, 0u, 0, nullptr, nullptr, hits), nullptr);
 }
 
@@ -997,21 +996,32 @@ int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, u
 int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
                       uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
                       const float light[3], uint32_t flags, float* rgba, rtr_hit* hits, uint64_t* rays,
-                      uint32_t rows_per_block, uint32_t shard_rank, uint32_t shard_count) {
+                      uint32_t rows_per_block, uint32_t total_stripes, uint32_t nb_stripes, const uint8_t* stripe_offsets) {
     resolve_denoms(width, height, denom_w, denom_h);
     if (row1 == 0) row1 = height;
     if (width == 0 || row0 >= row1 || row1 > height || denom_w == 0 || denom_h == 0)
         return rtr_set_error(ctx, RTR_E_INVALID, "render: bad image geometry %ux%u rows [%u,%u) denom %ux%u", width,
                              height, row0, row1, denom_w, denom_h);
     RowMap rm;
-    rm.row0 = row0; rm.rows = row1 - row0; rm.height = height; rm.rpb = 1; rm.rank = 0; rm.count = 1;
-    if (shard_count > 1) {
-        if (rows_per_block == 0 || shard_rank >= shard_count)
-            return rtr_set_error(ctx, RTR_E_INVALID, "render: bad shard %u/%u rows_per_block %u", shard_rank, shard_count, rows_per_block);
+    memset(&rm, 0, sizeof(rm));
+    rm.row0 = row0; rm.rows = row1 - row0; rm.height = height; rm.rpb = 1; rm.count = 1; rm.span = 1; rm.off[0] = 0;
+    if (total_stripes > 1) {
+        if (nb_stripes == 0) return RTR_OK;  // a rank that owns no stripes (e.g. the one that rebuilds the BVH)
+        if (rows_per_block == 0 || nb_stripes > RTR_MAX_STRIPES_PER_RANK || total_stripes > 255 || !stripe_offsets)
+            return rtr_set_error(ctx, RTR_E_INVALID, "render: bad stripes %u of %u, rows_per_block %u", nb_stripes,
+                                 total_stripes, rows_per_block);
+        uint32_t first = total_stripes;
+        for (uint32_t i = 0; i < nb_stripes; ++i) {
+            if (stripe_offsets[i] >= total_stripes) return rtr_set_error(ctx, RTR_E_INVALID, "render: stripe offset out of range");
+            rm.off[i] = stripe_offsets[i];
+            if (stripe_offsets[i] < first) first = stripe_offsets[i];
+        }
         const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
-        const uint32_t mine = blocks > shard_rank ? (blocks - shard_rank + shard_count - 1) / shard_count : 0;
-        if (mine == 0) return RTR_OK;
-        rm.row0 = 0; rm.rows = mine * rows_per_block; rm.rpb = rows_per_block; rm.rank = shard_rank; rm.count = shard_count;
+        // local blocks are enumerated cycle by cycle: up to the last cycle that still holds one of this rank's blocks
+        const uint32_t cycles = blocks > first ? (blocks - first + total_stripes - 1) / total_stripes : 0;
+        if (cycles == 0) return RTR_OK;
+        rm.row0 = 0; rm.rows = cycles * nb_stripes * rows_per_block; rm.rpb = rows_per_block;
+        rm.count = total_stripes; rm.span = nb_stripes;
     }
     if ((uint64_t)((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u >= 0xFFFFFF00ull)
         return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "render: image too large");

@@ -46,6 +46,69 @@ def pixels_of_rank(width: int, height: int, rank: int, world: int, rows_per_bloc
     return int(rows_of_rank(height, rank, world, rows_per_block).size) * width
 
 
+# ---- weighted dealing: the rank that rebuilds the BVH renders fewer rows ------------------------------------
+def stripe_layout(world: int, builder_share: float = 1.0, stripes_per_rank: int = 8) -> List[int]:
+    """Stripes owned by each rank.  Block b of the image belongs to stripe b % sum(layout); rank r owns
+    layout[r] of them (see stripe_owners).  Every rank but the builder (rank 0) gets
+    `stripes_per_rank`; the builder gets round(builder_share * stripes_per_rank), possibly 0 --
+    builder_share is the fraction of a full share of rendering it can take next to the rebuild
+    (1.0: plain dealing, the layout of rtr_render_sharded_dev with stripes_per_rank == 1)."""
+    if world <= 0 or stripes_per_rank <= 0:
+        raise ValueError("world and stripes_per_rank must be positive")
+    if world == 1:
+        return [1]
+    share = min(1.0, max(0.0, float(builder_share)))
+    return [int(round(share * stripes_per_rank))] + [stripes_per_rank] * (world - 1)
+
+
+def stripe_owners(layout: List[int]) -> List[int]:
+    """Owner of every stripe of a cycle (rtr_stripe_owners in csrc/common.cuh): round k hands one stripe to every
+    rank with more than k stripes, in rank order, so the ranks' blocks interleave."""
+    owners = []
+    for k in range(max(layout)):
+        owners += [r for r, n in enumerate(layout) if n > k]
+    return owners
+
+
+def owner_of_block_striped(block: int, layout: List[int]) -> int:
+    owners = stripe_owners(layout)
+    return owners[block % len(owners)]
+
+
+def blocks_of_rank_striped(height: int, rank: int, layout: List[int], rows_per_block: int = DEFAULT_ROWS_PER_BLOCK):
+    """Row ranges rendered by `rank` under a stripe layout (the mapping of RowMap with span > 1 in csrc/trace.cu)."""
+    return [rb for b, rb in enumerate(row_blocks(height, rows_per_block)) if owner_of_block_striped(b, layout) == rank]
+
+
+def builder_share_for(build_ms: float, render_ms: float, world: int) -> float:
+    """Share of a full rendering slice the building rank can take so that all ranks finish together:
+    with per-frame work B (rebuild, rank 0 only) and R (rendering, divisible), every rank should be busy
+    (B + R) / world; rank 0 renders (B + R) / world - B of it, a full share is what the others render."""
+    if world <= 1:
+        return 1.0
+    t = (build_ms + render_ms) / world
+    mine = t - build_ms
+    if mine <= 0.0:
+        return 0.0
+    others = (render_ms - mine) / (world - 1)
+    return max(0.0, min(1.0, mine / others))
+
+
+def gather_rows_striped(image, height: int, layout: List[int], rows_per_block: int = DEFAULT_ROWS_PER_BLOCK, group=None):
+    """gather_rows for a stripe layout (same schedule as rtr_allgather_stripes)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return image
+    works = []
+    for b, (r0, r1) in enumerate(row_blocks(height, rows_per_block)):
+        src = owner_of_block_striped(b, layout)
+        works.append(dist.broadcast(image[r0:r1], src=dist.get_global_rank(group, src) if group else src, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return image
+
+
 def gather_rows(image, height: int, rows_per_block: int = DEFAULT_ROWS_PER_BLOCK, group=None):
     """All-gather the row blocks of a full-size image tensor [height, ...] in place: after the call
     every rank holds every block.  Each block is broadcast by its owner (same schedule as

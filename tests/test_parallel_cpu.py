@@ -100,3 +100,81 @@ def test_broadcast_and_row_gather_over_gloo(tmp_path, world, height):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, height, 24, 16, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+# ---- weighted dealing (the rank that rebuilds the BVH renders fewer rows) --------------------------------
+def _rowmap_rows(height, rpb, offsets, total):
+    """The rows RowMap (csrc/trace.cu) enumerates for a rank owning the stripes `offsets` of `total`."""
+    if not offsets:
+        return []
+    blocks = (height + rpb - 1) // rpb
+    first, span = min(offsets), len(offsets)
+    cycles = (blocks - first + total - 1) // total if blocks > first else 0
+    rows = []
+    for y_local in range(cycles * span * rpb):
+        blk = y_local // rpb
+        y = ((blk // span) * total + offsets[blk % span]) * rpb + (y_local % rpb)
+        if y < height:
+            rows.append(y)
+    return rows
+
+
+@pytest.mark.parametrize("world,share", [(1, 1.0), (2, 0.75), (2, 0.0), (4, 0.5), (8, 0.2), (8, 1.0)])
+def test_stripe_layout_partitions_the_image(world, share):
+    height, rpb = 2160, 16
+    layout = parallel.stripe_layout(world, share)
+    assert len(layout) == world and sum(layout) >= 1
+    seen = np.zeros(height, dtype=np.int32)
+    for rank in range(world):
+        rows = [r for a, b in parallel.blocks_of_rank_striped(height, rank, layout, rpb) for r in range(a, b)]
+        seen[rows] += 1
+        # the device-side enumeration visits exactly these rows
+        offsets = [v for v, r in enumerate(parallel.stripe_owners(layout)) if r == rank]
+        assert sorted(_rowmap_rows(height, rpb, offsets, sum(layout))) == rows
+    assert (seen == 1).all()
+    if world > 1:
+        sizes = [len(parallel.blocks_of_rank_striped(height, r, layout, rpb)) for r in range(world)]
+        assert sizes[0] <= min(sizes[1:]) + 1  # the builder never renders more than the others
+        assert max(sizes[1:]) - min(sizes[1:]) <= 1
+
+
+def test_stripe_layout_with_full_share_is_plain_dealing():
+    assert parallel.stripe_layout(4, 1.0, stripes_per_rank=1) == [1, 1, 1, 1]
+    for b in range(40):
+        assert parallel.owner_of_block_striped(b, [1, 1, 1, 1]) == parallel.owner_of_block(b, 4)
+
+
+def test_builder_share():
+    assert parallel.builder_share_for(5.0, 40.0, 1) == 1.0
+    assert parallel.builder_share_for(5.0, 40.0, 8) == pytest.approx((45.0 / 8 - 5.0) / ((40.0 - (45.0 / 8 - 5.0)) / 7))
+    assert parallel.builder_share_for(10.0, 20.0, 4) == 0.0      # the rebuild alone fills the builder's frame
+    assert 0.0 < parallel.builder_share_for(4.4, 40.0, 2) < 1.0
+
+
+def _striped_worker(rank, world, port, height, width, rpb, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from realtimeraytracing_b200 import parallel as par
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        layout = par.stripe_layout(world, 0.5, stripes_per_rank=4)
+        image = torch.full((height, width), -1.0)
+        for r0, r1 in par.blocks_of_rank_striped(height, rank, layout, rpb):
+            image[r0:r1] = float(rank)
+        par.gather_rows_striped(image, height, layout, rpb)
+        owner = torch.tensor([par.owner_of_block_striped(r // rpb, layout) for r in range(height)], dtype=torch.float32)
+        assert torch.equal(image, owner.unsqueeze(1).expand(height, width))
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height", [(2, 200), (3, 333)])
+def test_striped_gather_over_gloo(tmp_path, world, height):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_striped_worker, args=(world, port, height, 8, 16, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
