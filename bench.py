@@ -46,7 +46,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-kernel side measurements")
     p.add_argument("--reference-order", action="store_true", help="trace in the shader's exact visiting order (no pruning)")
-    p.add_argument("--reserve-sms", type=int, default=16,
+    p.add_argument("--reserve-sms", type=int, default=8,
                    help="N>1: SMs the traversal leaves free for the NCCL kernels of the broadcast in flight")
     p.add_argument("--no-pipeline", action="store_true", help="N>1: rebuild, broadcast, render and gather strictly in sequence")
     return p.parse_args()
@@ -224,6 +224,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if not args.no_pipeline:
+            # the broadcast of the next frame's BVH runs beside the rays of the current one on --reserve-sms SMs:
+            # NCCL gets as many channels (one CTA each) as there are SMs left to it
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, args.reserve_sms)))
         dist.init_process_group("nccl", device_id=dev)
     rbuild.build()
 
@@ -328,6 +332,8 @@ def main():
         bvhs = [bvh, capi.Bvh(ctx)]
         ready = [torch.cuda.Event(), torch.cuda.Event()]       # BVH k rebuilt and received
         released = [torch.cuda.Event(), torch.cuda.Event()]    # the rays of the frame that used BVH k are done
+        built = [torch.cuda.Event(), torch.cuda.Event()]       # rank 0: BVH k rebuilt (not yet broadcast)
+        total_frames = [0]
         ctx.reserve_sms(args.reserve_sms)
 
         def submit_build(f, e2e):
@@ -339,21 +345,40 @@ def main():
                     bvhs[k].build(tris_pinned.numpy().view(TRIANGLE), meshes_np)
                 else:
                     bvhs[k].build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
-            bvhs[k].broadcast(0)
+            built[k].record(stream_b)
+            mark("built", f, stream_b)
+            bvhs[k].broadcast(0, traversal_only=not args.reference_order, expected_triangles=n)   # 64 B*(2n-1), enqueue only
             ready[k].record(stream_b)
+            mark("bcast", f, stream_b)
 
         def submit_render(f, e2e):
             k = f % 2
             ctx.switch_stream(stream_r.cuda_stream)
             stream_r.wait_event(ready[k])
+            if rank == 0 and f + 1 < total_frames[0]:
+                # the persistent traversal kernel would hold the SMs the next rebuild needs: on the building rank
+                # the rays of frame f start once the rebuild of f+1 is through (its broadcast runs beside them)
+                stream_r.wait_event(built[(f + 1) % 2])
+            mark("rays0", f, stream_r)
             bvhs[k].render_stripes_dev(cam, W, H, d_rgba.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
                                        bounces=bounces, flags=flags)
             released[k].record(stream_r)
+            mark("rays1", f, stream_r)
             ctx.allgather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, layout)
+            mark("gather", f, stream_r)
             if e2e and rank == 0:
                 ctx.download(rgba_pinned.numpy(), d_rgba.data_ptr())      # D2H of the frame (synchronises stream R)
 
+        marks = []
+
+        def mark(what, f, st):
+            if os.environ.get("RTR_BENCH_TRACE"):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(st)
+                marks.append((what, f, e))
+
         def run_pipelined(steps, e2e):
+            total_frames[0] = steps
             submit_build(0, e2e)
             for f in range(steps):
                 if f + 1 < steps:
@@ -362,6 +387,7 @@ def main():
 
         def timed_pipelined(steps, e2e):
             barrier(); stream_b.synchronize()
+            del marks[:]
             with torch.cuda.stream(stream_r):
                 d_rays.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,25 +400,34 @@ def main():
             e1.record(stream_r)
             barrier(); stream_b.synchronize()
             ctx.switch_stream(stream_r.cuda_stream)
+            if marks:  # RTR_BENCH_TRACE=1: when each phase of each frame ended, ms after the start of the timed region
+                sys.stderr.write("rank %d: " % rank + "  ".join("%s%d@%.1f" % (w, f, e0.elapsed_time(e)) for w, f, e in marks) + "\n")
+                del marks[:]
             return reduce_timing(e0.elapsed_time(e1), launches0)
 
         # weights from this box's own timings: rebuild + broadcast on rank 0, a full frame of rays on one GPU
         for _ in range(2):
             frame_device()
         barrier()
-        t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t0, t1, t2, t3, t4 = (torch.cuda.Event(enable_timing=True) for _ in range(5))
         t0.record(stream)
         if rank == 0:
             bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
-        bvh.broadcast(0)
-        t1.record(stream)
-        bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, bounces=bounces, flags=flags)
+        t1.record(stream)   # the broadcast runs beside the rays: only the rebuild is serial on rank 0
+        bvh.broadcast(0, traversal_only=not args.reference_order, expected_triangles=n)
         t2.record(stream)
+        bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, bounces=bounces, flags=flags)
+        t3.record(stream)
+        ctx.allgather_rows(d_rgba.data_ptr(), W, H, 16, rpb)
+        t4.record(stream)
         barrier()
-        tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2)], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2), t2.elapsed_time(t3), t3.elapsed_time(t4)],
+                          dtype=torch.float64, device=dev)
         dist.broadcast(tt, src=0)
-        serial_ms, render_ms = float(tt[0].item()), float(tt[1].item())
+        serial_ms, bcast_ms, render_ms, gather_ms = (float(x) for x in tt.tolist())
         layout = parallel.stripe_layout(world, parallel.builder_share_for(serial_ms, render_ms, world))
+        phases = {"rebuild_ms": serial_ms, "broadcast_ms": bcast_ms, "full_frame_rays_ms_one_gpu": render_ms,
+                  "gather_ms": gather_ms, "stripes_of_rank": layout}
         barrier()
 
     # ---- warm-up, then the timed region ----
@@ -523,6 +558,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        if pipelined:
+            line["multi_gpu"] = phases
         line.update(extras)
         print(json.dumps(line, default=float))
 

@@ -271,6 +271,12 @@ int rtr_comm_init(rtr_ctx* ctx, const void* unique_id, int rank, int nranks);
 int rtr_comm_destroy(rtr_ctx* ctx);
 /* root: sends flat nodes + triangles + meshes of *bvh; others: receive into a BVH they own */
 int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root);
+/* lighter replica for ranks that only trace in the default order: the 64-byte traversal records, node 0 and the
+ * trace constants (64 B*(2n-1) instead of ~208 B per triangle).  Receivers cannot use RTR_TRACE_REFERENCE_ORDER,
+ * the node/triangle accessors or re-broadcast (RTR_E_STATE).  expected_triangles: 0 = the root announces the size
+ * first (one host round trip on every rank); otherwise every rank passes the same triangle count and the call
+ * only enqueues -- a receiver can then post it ahead of the root's rebuild (pipelined frames). */
+int rtr_bvh_broadcast_traversal(rtr_ctx* ctx, rtr_bvh** bvh, int root, uint32_t expected_triangles);
 /* rows of the image are dealt to ranks in blocks of `rows_per_block`, block b -> rank b % nranks */
 int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
                        uint32_t rows_per_block);

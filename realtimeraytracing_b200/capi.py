@@ -33,7 +33,7 @@ SYMBOLS = [
     "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
-    "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms",
+    "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
 ]
 
 
@@ -127,6 +127,7 @@ def load_library():
     L.rtr_comm_init.argtypes = [vp, vp, i32, i32]
     L.rtr_comm_destroy.argtypes = [vp]
     L.rtr_bvh_broadcast.argtypes = [vp, pp, i32]
+    L.rtr_bvh_broadcast_traversal.argtypes = [vp, pp, i32, u32]
     L.rtr_allgather_rows.argtypes = [vp, vp, u32, u32, u32, u32]
     L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
@@ -377,8 +378,13 @@ class Bvh:
                                                   C.c_void_p(meshes_dev), nb_meshes, C.byref(self.handle)))
         return self
 
-    def broadcast(self, root: int = 0):
-        self.ctx.check(self.lib.rtr_bvh_broadcast(self.ctx.handle, C.byref(self.handle), root))
+    def broadcast(self, root: int = 0, traversal_only: bool = False, expected_triangles: int = 0):
+        """Replicates the root's BVH on every rank; traversal_only sends just what the default traversal reads
+        (and with expected_triangles set on every rank the call only enqueues)."""
+        if traversal_only:
+            self.ctx.check(self.lib.rtr_bvh_broadcast_traversal(self.ctx.handle, C.byref(self.handle), root, expected_triangles))
+        else:
+            self.ctx.check(self.lib.rtr_bvh_broadcast(self.ctx.handle, C.byref(self.handle), root))
         return self
 
     def close(self):

@@ -90,7 +90,7 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     b->tris_own = nullptr; b->meshes_own = nullptr;
     bvh_free_arrays(b);  // also drops a broadcast receive buffer
     b->tris_own = keep_t; b->tris_own_cap = keep_tc; b->meshes_own = keep_m; b->meshes_own_cap = keep_mc;
-    b->adopted = false;
+    b->adopted = false; b->trav_only = false;
     const size_t cap = n, nc = 2 * (size_t)n - 1;
     const size_t tiles = (cap + kPlocTile - 1) / kPlocTile + 1;
     RTR_CHECK(dev_alloc(ctx, &b->codes, cap));
@@ -589,7 +589,7 @@ int rtr_bvh_adopt_dev(rtr_ctx* ctx, const rtr_node* nodes_dev, uint32_t nb_trian
         b->built = false;
         b->n = nb_triangles; b->array_len = nb_triangles; b->nb_meshes = nb_meshes;
         b->tris = tris_dev; b->meshes = meshes_dev; b->flat_view = nodes_dev;
-        b->adopted = true;
+        b->adopted = true; b->trav_only = false;
         RTR_CHECK(rtr_bvh_compute_trace_params(b));
         b->built = true;
         return RTR_OK;
@@ -685,10 +685,11 @@ int rtr_bvh_clusters(rtr_bvh* b, rtr_node* clusters, uint32_t* parent, uint32_t*
 int rtr_bvh_flat_nodes(rtr_bvh* b, rtr_node* out) {
     return with_bvh(b, false, [&]() -> int {
         if (!out) return rtr_set_error(b->ctx, RTR_E_INVALID, "NULL out");
+        if (b->trav_only) return rtr_set_error(b->ctx, RTR_E_STATE, "this BVH holds traversal records only (rtr_bvh_broadcast_traversal)");
         return rtr_dev_download(b->ctx, out, b->flat_view, (2 * (size_t)b->n - 1) * sizeof(rtr_node));
     });
 }
-const rtr_node* rtr_bvh_device_nodes(const rtr_bvh* b) { return (b && b->built) ? b->flat_view : nullptr; }
+const rtr_node* rtr_bvh_device_nodes(const rtr_bvh* b) { return (b && b->built && !b->trav_only) ? b->flat_view : nullptr; }
 const rtr_triangle* rtr_bvh_device_triangles(const rtr_bvh* b) { return (b && b->built) ? b->tris : nullptr; }
 const rtr_mesh* rtr_bvh_device_meshes(const rtr_bvh* b) { return (b && b->built) ? b->meshes : nullptr; }
 
@@ -700,10 +701,17 @@ static int trace_args_ok(rtr_ctx* ctx, const rtr_bvh* b, const void* cam_or_rays
     if (!cam_or_rays) return rtr_set_error(ctx, RTR_E_INVALID, "trace: NULL camera/rays");
     return RTR_OK;
 }
+// the by-the-letter order walks the 48-byte nodes, which a traversal-only replica does not have
+static int order_ok(rtr_ctx* ctx, const rtr_bvh* b, uint32_t flags) {
+    if ((flags & RTR_TRACE_REFERENCE_ORDER) && b->trav_only)
+        return rtr_set_error(ctx, RTR_E_STATE, "trace: RTR_TRACE_REFERENCE_ORDER needs the flat nodes; this BVH holds traversal records only");
+    return RTR_OK;
+}
 
 int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
                           uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t flags, rtr_hit* hits_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (!hits_dev) return rtr_set_error(ctx, RTR_E_INVALID, "trace_primary: NULL output");
     return rtr_trace_primary_launch(ctx, b, *cam, width, height, denom_w, denom_h, row0, row1, flags, hits_dev);
 }
@@ -711,6 +719,7 @@ int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam,
 int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
                       uint32_t denom_w, uint32_t denom_h, uint32_t flags, rtr_hit* hits_out) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (!hits_out) return rtr_set_error(ctx, RTR_E_INVALID, "trace_primary: NULL output");
     const size_t bytes = (size_t)width * height * sizeof(rtr_hit);
     Staging st;
@@ -730,6 +739,7 @@ int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uin
 int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays_dev, uint64_t n_rays, int any_hit,
                        const float* t_max_dev, uint32_t flags, rtr_hit* hits_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, n_rays ? (const void*)rays_dev : (const void*)b));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (n_rays && !hits_dev) return rtr_set_error(ctx, RTR_E_INVALID, "trace_rays: NULL output");
     return rtr_trace_rays_launch(ctx, b, rays_dev, n_rays, any_hit, t_max_dev, flags, hits_dev);
 }
@@ -737,6 +747,7 @@ int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays_dev, 
 int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t n_rays, int any_hit, const float* t_max,
                    uint32_t flags, rtr_hit* hits_out) {
     RTR_CHECK(trace_args_ok(ctx, b, n_rays ? (const void*)rays : (const void*)b));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (n_rays == 0) return RTR_OK;
     if (!hits_out) return rtr_set_error(ctx, RTR_E_INVALID, "trace_rays: NULL output");
     const size_t rb = n_rays * sizeof(rtr_ray), hb = n_rays * sizeof(rtr_hit), tb = t_max ? n_rays * 4 : 0;
@@ -762,6 +773,7 @@ int rtr_render_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32
                    uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow,
                    const float light_pos[3], uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
     return rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, row0, row1, bounces, shadow, light_pos, flags,
                              rgba_dev, hits_dev, rays_dev);
@@ -772,6 +784,7 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam
                            uint32_t shard_count, uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
                            float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
     if (shard_count == 0 || shard_rank >= shard_count || shard_count > 255)
         return rtr_set_error(ctx, RTR_E_INVALID, "render: bad shard %u of %u", shard_rank, shard_count);
@@ -785,6 +798,7 @@ int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam
                            uint32_t nranks, uint32_t rank, uint32_t bounces, int shadow, const float light_pos[3],
                            uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
     if (!stripes_of_rank || nranks == 0 || rank >= nranks)
         return rtr_set_error(ctx, RTR_E_INVALID, "render: bad stripe layout (rank %u of %u)", rank, nranks);
@@ -808,6 +822,7 @@ int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t w
                uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
                uint32_t flags, float* rgba_out, rtr_hit* hits_out, uint64_t* rays_traced) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, flags));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");
     if (row1 == 0) row1 = height;
     if (row0 >= row1 || row1 > height) return rtr_set_error(ctx, RTR_E_INVALID, "render: bad rows [%u,%u)", row0, row1);

@@ -34,6 +34,7 @@ struct rtr_bvh {
     uint32_t nb_meshes = 0;
     uint32_t radius = RTR_DEFAULT_SEARCH_RADIUS;
     bool adopted = false;    // flat/tris/meshes are borrowed, no build arrays
+    bool trav_only = false;  // received by rtr_bvh_broadcast_traversal: traversal records + node 0 only
     bool built = false;
 
     // inputs (device)

@@ -114,6 +114,7 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
     if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: bad root %d", root);
     const bool is_root = ctx->rank == root;
     if (is_root && (!*bvh || !(*bvh)->built)) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
+    if (is_root && (*bvh)->trav_only) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: the root holds traversal records only");
     NcclComm comm = ctx->nccl_comm;
 
     // 1. header: triangle and mesh counts
@@ -187,8 +188,80 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
         b->n = n; b->array_len = n; b->nb_meshes = nb_meshes;
         b->tris = b->tris_own; b->meshes = b->meshes_own; b->flat_view = b->flat_recv;
         b->wtri_view = b->wtri_own; b->wtri_by_rank = by_rank;
-        b->adopted = true;
+        b->adopted = true; b->trav_only = false;
         RTR_CHECK(rtr_bvh_pack_pairs_own(b));  // derived locally: cheaper than 64 B*(2n-1) more on the wire
+        b->built = true;
+    }
+    return RTR_OK;
+}
+
+int rtr_bvh_broadcast_traversal(rtr_ctx* ctx, rtr_bvh** bvh, int root, uint32_t expected_triangles) {
+    if (!ctx || !bvh) return RTR_E_INVALID;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: rtr_comm_init has not been called");
+    if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: bad root %d", root);
+    const bool is_root = ctx->rank == root;
+    if (is_root && (!*bvh || !(*bvh)->built)) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
+    NcclComm comm = ctx->nccl_comm;
+
+    // 1. header: triangle count -- unless every rank already knows it (a frame loop over one scene): then no
+    //    rank has to wait on the host for the root, and the receive can be enqueued ahead of the root's rebuild
+    uint32_t n = expected_triangles;
+    if (n == 0) {
+        RTR_CHECK(rtr_ws_reserve(ctx, 256));
+        uint32_t* h_hdr = static_cast<uint32_t*>(ctx->pinned) + 64;
+        uint32_t* d_hdr = static_cast<uint32_t*>(ctx->ws);
+        if (is_root) {
+            h_hdr[0] = (*bvh)->n; h_hdr[1] = h_hdr[2] = h_hdr[3] = 0;
+            RTR_CUDA(ctx, cudaMemcpyAsync(d_hdr, h_hdr, 16, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        RTR_NCCL(ctx, g_nccl.Broadcast(d_hdr, d_hdr, 16, kNcclUint8, root, comm, ctx->stream));
+        RTR_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n = h_hdr[0];
+        if (n == 0) return rtr_set_error(ctx, RTR_E_COMM, "bvh_broadcast: empty header from root");
+    } else if (is_root && (*bvh)->n != n) {
+        return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: the BVH has %u triangles, the ranks expect %u", (*bvh)->n, n);
+    }
+    const size_t nc = 2 * (size_t)n - 1;
+
+    // 2. receivers own their copy of the traversal records and of node 0 (the root box every ray starts with)
+    rtr_bvh* b = *bvh;
+    if (!is_root) {
+        if (!b) {
+            b = new (std::nothrow) rtr_bvh();
+            if (!b) return rtr_set_error(ctx, RTR_E_NOMEM, "bvh_broadcast: host allocation failed");
+            b->ctx = ctx;
+            *bvh = b;
+        }
+        b->built = false;
+        if (!b->flat_recv) {
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->flat_recv), sizeof(rtr_node)));
+            b->recv_cap = 0;  // one node only: a later full broadcast reallocates
+        }
+        if (b->pairs_own_cap < n) {
+            RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (b->pairs_own) cudaFree(b->pairs_own);
+            b->pairs_own = nullptr; b->pairs_own_cap = 0;
+            RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->pairs_own), nc * 4 * sizeof(uint4)));
+            b->pairs_own_cap = n;
+        }
+        if (!b->tparams) RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->tparams), sizeof(TraceParams)));
+    }
+    void* pairs = is_root ? const_cast<uint4*>(b->pairs_view) : b->pairs_own;
+    void* node0 = is_root ? const_cast<rtr_node*>(b->flat_view) : b->flat_recv;
+
+    // 3. one grouped broadcast: 64 B*(2n-1) + 48 B + trace constants
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    RTR_NCCL(ctx, g_nccl.Broadcast(pairs, pairs, nc * 4 * sizeof(uint4), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(node0, node0, sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL(ctx, g_nccl.GroupEnd());
+
+    if (!is_root) {
+        b->n = n; b->array_len = n; b->nb_meshes = 0;
+        b->tris = nullptr; b->meshes = nullptr; b->flat_view = b->flat_recv; b->wtri_view = nullptr;
+        b->pairs_view = b->pairs_own;
+        b->adopted = true; b->trav_only = true;
         b->built = true;
     }
     return RTR_OK;
