@@ -183,3 +183,54 @@ def test_adopted_bvh_traces_identically(ctx):
         other.close()
     finally:
         bvh.close()
+
+
+@pytest.mark.parametrize("layout", [[1, 1, 1], [3, 8, 8], [0, 4, 4], [5, 8]])
+def test_weighted_stripes_tile_the_frame(ctx, layout):
+    """Row blocks dealt with weights (rtr_render_stripes_dev): the stripes of all ranks, rendered one after
+    the other into one image on this GPU, give the plain frame -- including a rank that owns nothing."""
+    tris, meshes, L = scenes.soup(10000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H, rpb = 128, 200, 8
+        cam = synth.soup_camera(L, W, H)
+        full, _, fr = bvh.render(cam, W, H, W, H, bounces=1)
+        d_rgba = ctx.dev_alloc(W * H * 16); d_rays = ctx.dev_alloc(8)
+        ctx.zero(d_rgba, W * H * 16); ctx.zero(d_rays, 8)
+        for rank in range(len(layout)):
+            bvh.render_stripes_dev(cam, W, H, d_rgba, rpb, layout, rank, rays_dev=d_rays, denom_w=W, denom_h=H, bounces=1)
+        got = np.zeros((H, W, 4), np.float32); rays = np.zeros(1, np.uint64)
+        ctx.download(got, d_rgba); ctx.download(rays, d_rays)
+        ctx.dev_free(d_rgba); ctx.dev_free(d_rays)
+        assert np.array_equal(got, full.reshape(H, W, 4)) and int(rays[0]) == fr
+    finally:
+        bvh.close()
+
+
+def test_axis_parallel_rays_take_the_exact_slab_test(ctx, oracle):
+    """Rays with a zero direction component: the compressed traversal records cannot bound 1/0, the kernel
+    falls back to the reference slab test on the decoded boxes (Q11) -- same records as the oracle."""
+    tris, meshes, L = scenes.soup(20000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        flat = bvh.flat_nodes()
+        rng = np.random.default_rng(5)
+        n = 4096
+        rays = np.zeros(n, RAY)
+        o = rng.uniform(-0.5 * L, 0.5 * L, (n, 3)).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d[np.arange(n), rng.integers(0, 3, n)] = 0.0          # one component exactly zero
+        d[: n // 4, 1] = 0.0                                   # a quarter with two
+        d[(d == 0).all(axis=1)] = (1.0, 0.0, 0.0)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        o[:, 2] -= L                                           # from outside, towards the soup
+        d[:, 2] = np.abs(d[:, 2])
+        rays["o"][:, :3] = o; rays["o"][:, 3] = 1.0
+        rays["d"][:, :3] = d
+        got = bvh.trace_rays(rays)
+        exp = oracle.trace_rays(flat, tris, meshes, rays)
+        assert_hits_equal(got, exp, "axis-parallel")
+        ref = bvh.trace_rays(rays, flags=capi.TRACE_REFERENCE_ORDER)
+        assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+    finally:
+        bvh.close()
