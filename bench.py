@@ -448,9 +448,74 @@ def main():
 
     # ---- end to end through the host-pointer ABI ----
     e2e_steps = args.steps
+    e2e_how = "rtr_bvh_build (host triangles, synchronous upload) + frame + rtr_dev_download of the image, per step"
     if pipelined:
         run_pipelined(2, True)
         e2e_ms, e2e_rays, _ = timed_pipelined(e2e_steps, True)
+    elif world == 1 and not args.no_pipeline:
+        # Single GPU, double-buffered host traffic: the triangles of frame f+1 are uploaded (rtr_dev_upload_async,
+        # pinned host memory, its own stream) while frame f is rebuilt and traced, and the image of frame f is
+        # downloaded (rtr_dev_download_async) while frame f+1 is rebuilt.  Every step still moves its 640 MB in and
+        # its 133 MB out inside the timed region.
+        e2e_how = ("double-buffered: rtr_dev_upload_async of frame f+1's triangles and rtr_dev_download_async of frame "
+                   "f-1's image run beside rtr_bvh_build_dev + rays of frame f (three streams, rtr_ctx_switch_stream)")
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            d_tris2 = [d_tris, torch.empty_like(d_tris)]
+            d_rgba2 = [d_rgba, torch.empty_like(d_rgba)]
+        rgba_pinned2 = [rgba_pinned, torch.empty_like(rgba_pinned).pin_memory()]
+        meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory()
+        up_done, tris_free, frame_done, img_free = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(4))
+        stream.synchronize()
+
+        def e2e_upload(f):
+            k = f % 2
+            ctx.switch_stream(s_in.cuda_stream)
+            s_in.wait_event(tris_free[k])
+            ctx.upload_async(d_tris2[k].data_ptr(), tris_pinned.numpy())
+            ctx.upload_async(d_meshes.data_ptr(), meshes_pinned.numpy())
+            up_done[k].record(s_in)
+
+        def e2e_frame(f):
+            k = f % 2
+            ctx.switch_stream(stream.cuda_stream)
+            stream.wait_event(up_done[k])
+            stream.wait_event(img_free[k])
+            bvh.build_dev(d_tris2[k].data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            bvh.render_sharded_dev(cam, W, H, d_rgba2[k].data_ptr(), rpb, 0, 1, rays_dev=d_rays.data_ptr(),
+                                   bounces=bounces, flags=flags)
+            frame_done[k].record(stream)
+            tris_free[k].record(stream)
+            ctx.switch_stream(s_out.cuda_stream)
+            s_out.wait_event(frame_done[k])
+            ctx.download_async(rgba_pinned2[k].numpy(), d_rgba2[k].data_ptr())
+            img_free[k].record(s_out)
+            ctx.switch_stream(stream.cuda_stream)
+
+        def run_e2e(steps):
+            e2e_upload(0)
+            for f in range(steps):
+                if f + 1 < steps:
+                    e2e_upload(f + 1)
+                e2e_frame(f)
+            stream.wait_stream(s_out)
+            stream.wait_stream(s_in)
+
+        run_e2e(2)
+        barrier()
+        with torch.cuda.stream(stream):
+            d_rays.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ctx.launch_count
+        stream.synchronize()
+        e0.record(stream)
+        s_in.wait_event(e0)
+        run_e2e(e2e_steps)
+        e1.record(stream)
+        barrier(); s_in.synchronize(); s_out.synchronize()
+        e2e_ms, e2e_rays, _ = reduce_timing(e0.elapsed_time(e1), launches0)
+        # the last image really is in host memory
+        assert float(rgba_pinned2[(e2e_steps - 1) % 2][3]) == 1.0
     else:
         for _ in range(2):
             frame_e2e()
@@ -510,14 +575,15 @@ def main():
         hbm_kernels = [(k, v) for k, v in kern.items() if "algorithmic_GBps" in v]
         if hbm_kernels:
             name, v = max(hbm_kernels, key=lambda kv: kv[1]["ms_total"])
-            traffic = None
+            traffic = traffic_note = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic, traffic_note = tj.get(name), tj.get(name + "_note")
             except Exception:
                 pass
             roofline = {"bound": "hbm", "kernel": name, "achieved": v["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
-                        "frac": v["algorithmic_GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
-                        "avg_launch_ms": v["ms_total"] / v["launches"]}
+                        "frac": v["algorithmic_GBps"] / peak, "traffic": traffic, "traffic_note": traffic_note,
+                        "peak_source": peak_src, "avg_launch_ms": v["ms_total"] / v["launches"]}
         extras["build_roofline"] = {"algorithmic_bytes": build_bytes, "achieved_GBps": build_bytes / (stage[5] * 1e-3) / 1e9,
                                     "frac_of_peak": build_bytes / (stage[5] * 1e-3) / 1e9 / peak}
         extras["sort_roofline"] = {"algorithmic_bytes": 68.0 * n, "achieved_GBps": 68.0 * n / (stage[1] * 1e-3) / 1e9,
@@ -553,7 +619,7 @@ def main():
                        "l2": "inputs larger than L2 (640 MB of triangles + 960 MB of nodes per step), no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "how": e2e_how},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

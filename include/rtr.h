@@ -136,6 +136,11 @@ int rtr_dev_alloc(rtr_ctx* ctx, size_t bytes, void** out);
 int rtr_dev_free(rtr_ctx* ctx, void* p);
 int rtr_dev_upload(rtr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int rtr_dev_download(rtr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* the same, enqueued on the ctx stream without waiting (the host buffer must stay valid, and be pinned -- rtr_host_alloc --
+ * for the copy to run beside kernels): with rtr_ctx_switch_stream the triangles of frame f+1 can travel while frame f
+ * is traced */
+int rtr_dev_upload_async(rtr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int rtr_dev_download_async(rtr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int rtr_dev_zero(rtr_ctx* ctx, void* dst_dev, size_t bytes);
 
 /* ---- sort pre-passes pinned by tests/testsSortGPU ---- */

@@ -34,6 +34,7 @@ SYMBOLS = [
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
+    "rtr_dev_upload_async", "rtr_dev_download_async",
 ]
 
 
@@ -81,6 +82,8 @@ def load_library():
     L.rtr_dev_free.argtypes = [vp, vp]
     L.rtr_dev_upload.argtypes = [vp, vp, vp, sz]
     L.rtr_dev_download.argtypes = [vp, vp, vp, sz]
+    L.rtr_dev_upload_async.argtypes = [vp, vp, vp, sz]
+    L.rtr_dev_download_async.argtypes = [vp, vp, vp, sz]
     L.rtr_dev_zero.argtypes = [vp, vp, sz]
     L.rtr_bit_histogram32.argtypes = [vp, vp, u32, vp]
     L.rtr_bit_histogram32_dev.argtypes = [vp, vp, u32, vp]
@@ -236,6 +239,13 @@ class Context:
 
     def download(self, dst: np.ndarray, src_dev: int):
         self.check(self.lib.rtr_dev_download(self.handle, _ptr(dst), C.c_void_p(src_dev), dst.nbytes))
+
+    def upload_async(self, dst_dev: int, src: np.ndarray):
+        """Enqueue only; `src` must stay alive (and be pinned for the copy to overlap kernels)."""
+        self.check(self.lib.rtr_dev_upload_async(self.handle, C.c_void_p(dst_dev), _ptr(src), src.nbytes))
+
+    def download_async(self, dst: np.ndarray, src_dev: int):
+        self.check(self.lib.rtr_dev_download_async(self.handle, _ptr(dst), C.c_void_p(src_dev), dst.nbytes))
 
     def zero(self, dst_dev: int, nbytes: int):
         self.check(self.lib.rtr_dev_zero(self.handle, C.c_void_p(dst_dev), nbytes))

@@ -410,6 +410,16 @@ int rtr_dev_download(rtr_ctx* ctx, void* dst, const void* src, size_t bytes) {
     RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RTR_OK;
 }
+int rtr_dev_upload_async(rtr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || (bytes && (!dst || !src))) return RTR_E_INVALID;
+    RTR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RTR_OK;
+}
+int rtr_dev_download_async(rtr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || (bytes && (!dst || !src))) return RTR_E_INVALID;
+    RTR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RTR_OK;
+}
 int rtr_dev_zero(rtr_ctx* ctx, void* dst, size_t bytes) {
     if (!ctx || (bytes && !dst)) return RTR_E_INVALID;
     RTR_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
