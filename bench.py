@@ -46,7 +46,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-kernel side measurements")
     p.add_argument("--reference-order", action="store_true", help="trace in the shader's exact visiting order (no pruning)")
-    p.add_argument("--reserve-sms", type=int, default=8,
+    p.add_argument("--reserve-sms", type=int, default=0,
                    help="N>1: SMs the traversal leaves free for the NCCL kernels of the broadcast in flight")
     p.add_argument("--no-pipeline", action="store_true", help="N>1: rebuild, broadcast, render and gather strictly in sequence")
     return p.parse_args()
@@ -223,6 +223,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: librtr_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.reserve_sms <= 0:
+        args.reserve_sms = 8 if world <= 2 else 12   # the broadcast has a pipeline stage of its own: it only has to beat the rays
     if world > 1:
         if not args.no_pipeline:
             # the broadcast of the next frame's BVH runs beside the rays of the current one on --reserve-sms SMs:
@@ -321,54 +323,34 @@ def main():
             rays, launches = int(r[0].item()), int(r[1].item())
         return ms, rays, launches
 
-    # ---- N > 1: pipelined frames.  Rank 0 rebuilds and broadcasts frame f+1 (stream B) while every rank traces
-    #      its rows of frame f (stream R); two BVHs alternate.  The row blocks are dealt with weights so that the
-    #      rebuilding rank, which has less time left for rays, gets fewer of them (parallel.stripe_layout). ----
+    # ---- N > 1: pipelined frames, three stages on three streams: rank 0 rebuilds frame f+2 (stream A), every rank
+    #      exchanges frame f+1 (stream B), every rank traces its rows of frame f (stream R); three BVHs rotate.  The
+    #      row blocks are dealt with weights so that the rebuilding rank, which has less time left for rays, gets
+    #      fewer of them (parallel.stripe_layout), and the frame is gathered on rank 0 (the rank that hands it on). ----
     pipelined = world > 1 and not args.no_pipeline
     layout = [1] * world
     if pipelined:
+        NB = 3
+        stream_a = torch.cuda.Stream(device=dev)
         stream_b = torch.cuda.Stream(device=dev)
         stream_r = stream
-        bvhs = [bvh, capi.Bvh(ctx)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]       # BVH k rebuilt and received
-        released = [torch.cuda.Event(), torch.cuda.Event()]    # the rays of the frame that used BVH k are done
-        built = [torch.cuda.Event(), torch.cuda.Event()]       # rank 0: BVH k rebuilt (not yet broadcast)
-        total_frames = [0]
+        bvhs = [bvh] + [capi.Bvh(ctx) for _ in range(NB - 1)]
+        built = [torch.cuda.Event() for _ in range(NB)]       # rank 0: BVH k rebuilt (not yet sent)
+        ready = [torch.cuda.Event() for _ in range(NB)]       # BVH k rebuilt and received
+        released = [torch.cuda.Event() for _ in range(NB)]    # the rays of the frame that used BVH k are done
+        sent = [torch.cuda.Event() for _ in range(NB)]        # rank 0: BVH k has left (it may be rebuilt)
+        last_built = [None]
         ctx.reserve_sms(args.reserve_sms)
 
-        def submit_build(f, e2e):
-            k = f % 2
-            ctx.switch_stream(stream_b.cuda_stream)
-            stream_b.wait_event(released[k])
-            if rank == 0:
-                if e2e:
-                    bvhs[k].build(tris_pinned.numpy().view(TRIANGLE), meshes_np)
-                else:
-                    bvhs[k].build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
-            built[k].record(stream_b)
-            mark("built", f, stream_b)
-            bvhs[k].broadcast(0, traversal_only=not args.reference_order, expected_triangles=n)   # 64 B*(2n-1), enqueue only
-            ready[k].record(stream_b)
-            mark("bcast", f, stream_b)
-
-        def submit_render(f, e2e):
-            k = f % 2
-            ctx.switch_stream(stream_r.cuda_stream)
-            stream_r.wait_event(ready[k])
-            if rank == 0 and f + 1 < total_frames[0]:
-                # the persistent traversal kernel would hold the SMs the next rebuild needs: on the building rank
-                # the rays of frame f start once the rebuild of f+1 is through (its broadcast runs beside them)
-                stream_r.wait_event(built[(f + 1) % 2])
-            mark("rays0", f, stream_r)
-            bvhs[k].render_stripes_dev(cam, W, H, d_rgba.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
-                                       bounces=bounces, flags=flags)
-            released[k].record(stream_r)
-            mark("rays1", f, stream_r)
-            ctx.allgather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, layout)
-            mark("gather", f, stream_r)
-            if e2e and rank == 0:
-                ctx.download(rgba_pinned.numpy(), d_rgba.data_ptr())      # D2H of the frame (synchronises stream R)
-
+        # e2e arm: double-buffered host traffic (as on one GPU, see below)
+        x_in, x_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            x_rgba = [d_rgba, torch.empty_like(d_rgba)]
+            x_tris = [d_tris, torch.empty_like(d_tris)] if rank == 0 else None
+        x_rgba_pinned = [rgba_pinned, torch.empty_like(rgba_pinned).pin_memory()] if rank == 0 else None
+        x_meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory() if rank == 0 else None
+        x_up_done, x_tris_free, x_frame_done, x_img_free = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(4))
+        stream.synchronize()
         marks = []
 
         def mark(what, f, st):
@@ -377,16 +359,91 @@ def main():
                 e.record(st)
                 marks.append((what, f, e))
 
+        def submit_build(f, e2e):
+            """stage A, rank 0 only: rebuild BVH f % NB."""
+            if rank != 0:
+                return
+            k = f % NB
+            ctx.switch_stream(stream_a.cuda_stream)
+            stream_a.wait_event(released[k])   # own rays of the frame that used this BVH
+            stream_a.wait_event(sent[k])       # and its broadcast
+            if e2e:
+                # host triangles of this frame: uploaded on their own stream (beside the work of earlier frames),
+                # then rebuilt from the device copy
+                j = f % 2
+                ctx.switch_stream(x_in.cuda_stream)
+                x_in.wait_event(x_tris_free[j])
+                ctx.upload_async(x_tris[j].data_ptr(), tris_pinned.numpy())
+                ctx.upload_async(d_meshes.data_ptr(), x_meshes_pinned.numpy())
+                x_up_done[j].record(x_in)
+                ctx.switch_stream(stream_a.cuda_stream)
+                stream_a.wait_event(x_up_done[j])
+                bvhs[k].build_dev(x_tris[j].data_ptr(), n, n, d_meshes.data_ptr(), 1)
+                x_tris_free[j].record(stream_a)
+            else:
+                bvhs[k].build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            built[k].record(stream_a)
+            last_built[0] = built[k]
+            mark("built", f, stream_a)
+
+        def submit_exchange(f):
+            """stage B, every rank: BVH f % NB travels from rank 0 (64 B*(2n-1), enqueue only)."""
+            k = f % NB
+            ctx.switch_stream(stream_b.cuda_stream)
+            if rank == 0:
+                stream_b.wait_event(built[k])
+            else:
+                stream_b.wait_event(released[k])   # the rays of the frame that used this receive buffer
+            bvhs[k].broadcast(0, traversal_only=not args.reference_order, expected_triangles=n)
+            ready[k].record(stream_b)
+            if rank == 0:
+                sent[k].record(stream_b)
+            mark("bcast", f, stream_b)
+
+        def submit_rays(f, e2e):
+            """stage R, every rank: the rays of its stripes of frame f, then the frame is gathered on rank 0."""
+            k = f % NB
+            ctx.switch_stream(stream_r.cuda_stream)
+            stream_r.wait_event(ready[k])
+            if rank == 0 and layout[0] > 0 and last_built[0] is not None:
+                # the persistent traversal kernel would hold the SMs a rebuild needs: on the building rank the rays
+                # start once the rebuild submitted last is through
+                stream_r.wait_event(last_built[0])
+            mark("rays0", f, stream_r)
+            j = f % 2
+            img = x_rgba[j] if e2e else d_rgba
+            if e2e and rank == 0:
+                stream_r.wait_event(x_img_free[j])   # the download of the frame that used this image buffer is through
+            bvhs[k].render_stripes_dev(cam, W, H, img.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
+                                       bounces=bounces, flags=flags)
+            released[k].record(stream_r)
+            mark("rays1", f, stream_r)
+            ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
+            mark("gather", f, stream_r)
+            if e2e and rank == 0:
+                x_frame_done[j].record(stream_r)
+                ctx.switch_stream(x_out.cuda_stream)
+                x_out.wait_event(x_frame_done[j])
+                ctx.download_async(x_rgba_pinned[j].numpy(), img.data_ptr())   # D2H of the frame, beside the next one
+                x_img_free[j].record(x_out)
+                ctx.switch_stream(stream_r.cuda_stream)
+
         def run_pipelined(steps, e2e):
-            total_frames[0] = steps
+            # every rank issues its NCCL calls in the same order: exchange(f+1), gather(f), exchange(f+2), ...
+            last_built[0] = None
             submit_build(0, e2e)
+            submit_exchange(0)
+            if steps > 1:
+                submit_build(1, e2e)
             for f in range(steps):
                 if f + 1 < steps:
-                    submit_build(f + 1, e2e)   # enqueued before the rays of frame f: runs beside them
-                submit_render(f, e2e)
+                    submit_exchange(f + 1)
+                if f + 2 < steps:
+                    submit_build(f + 2, e2e)     # host-blocking on rank 0: everything it must not delay is enqueued
+                submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
-            barrier(); stream_b.synchronize()
+            barrier(); stream_a.synchronize(); stream_b.synchronize()
             del marks[:]
             with torch.cuda.stream(stream_r):
                 d_rays.zero_()
@@ -394,11 +451,15 @@ def main():
             launches0 = ctx.launch_count
             stream_r.synchronize()
             e0.record(stream_r)
-            stream_b.wait_event(e0)            # the first rebuild starts inside the timed region
+            for st in (stream_a, stream_b, x_in):
+                st.wait_event(e0)            # nothing of the region starts before it
             run_pipelined(steps, e2e)
-            stream_r.wait_stream(stream_b)
+            for st in (stream_a, stream_b, x_out):
+                stream_r.wait_stream(st)
             e1.record(stream_r)
-            barrier(); stream_b.synchronize()
+            barrier()
+            for st in (stream_a, stream_b, x_in, x_out):
+                st.synchronize()
             ctx.switch_stream(stream_r.cuda_stream)
             if marks:  # RTR_BENCH_TRACE=1: when each phase of each frame ended, ms after the start of the timed region
                 sys.stderr.write("rank %d: " % rank + "  ".join("%s%d@%.1f" % (w, f, e0.elapsed_time(e)) for w, f, e in marks) + "\n")
@@ -408,6 +469,7 @@ def main():
         # weights from this box's own timings: rebuild + broadcast on rank 0, a full frame of rays on one GPU
         for _ in range(2):
             frame_device()
+        ctx.gather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, [1] * world, 0)   # first use connects the send/recv channels
         barrier()
         t0, t1, t2, t3, t4 = (torch.cuda.Event(enable_timing=True) for _ in range(5))
         t0.record(stream)
@@ -418,7 +480,7 @@ def main():
         t2.record(stream)
         bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, bounces=bounces, flags=flags)
         t3.record(stream)
-        ctx.allgather_rows(d_rgba.data_ptr(), W, H, 16, rpb)
+        ctx.gather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, [1] * world, 0)
         t4.record(stream)
         barrier()
         tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2), t2.elapsed_time(t3), t3.elapsed_time(t4)],
@@ -450,6 +512,8 @@ def main():
     e2e_steps = args.steps
     e2e_how = "rtr_bvh_build (host triangles, synchronous upload) + frame + rtr_dev_download of the image, per step"
     if pipelined:
+        e2e_how = ("pipelined frames; on rank 0 rtr_dev_upload_async of frame f+1's triangles and rtr_dev_download_async of "
+                   "frame f's gathered image run on their own streams beside the rebuild and the rays")
         run_pipelined(2, True)
         e2e_ms, e2e_rays, _ = timed_pipelined(e2e_steps, True)
     elif world == 1 and not args.no_pipeline:
@@ -614,7 +678,7 @@ def main():
                        "rays_per_step": rays // args.steps, "search_radius": 16,
                        "trace_order": "reference" if args.reference_order else "pruned (identical records)",
                        "parallelism": ("build on rank 0 + NCCL broadcast + %d-row blocks dealt to %d rank(s)" % (rpb, world)) +
-                                      ((", frames pipelined (rebuild+broadcast of f+1 beside the rays of f), stripes per rank %s, %d SMs left to NCCL"
+                                      ((", frames pipelined (rebuild of f+2 | broadcast of f+1 | rays of f, gathered on rank 0), stripes per rank %s, %d SMs left to NCCL"
                                         % (layout, args.reserve_sms)) if pipelined else ""),
                        "l2": "inputs larger than L2 (640 MB of triangles + 960 MB of nodes per step), no flush needed"},
             "clocks": clocks,
@@ -630,7 +694,8 @@ def main():
         print(json.dumps(line, default=float))
 
     if pipelined:
-        bvhs[1].close()
+        for other in bvhs[1:]:
+            other.close()
     bvh.close()
     if comm:
         comm.close()

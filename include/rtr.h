@@ -290,6 +290,10 @@ int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t h
 int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
                           uint32_t rows_per_block, const uint32_t* stripes_of_rank);
 
+/* only `root` ends up with the whole image: every block travels once, from its owner to the root (ncclSend/ncclRecv) */
+int rtr_gather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                       uint32_t rows_per_block, const uint32_t* stripes_of_rank, int root);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ SYMBOLS = [
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
-    "rtr_dev_upload_async", "rtr_dev_download_async",
+    "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes",
 ]
 
 
@@ -134,6 +134,7 @@ def load_library():
     L.rtr_allgather_rows.argtypes = [vp, vp, u32, u32, u32, u32]
     L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+    L.rtr_gather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp, i32]
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     _lib = L
@@ -343,6 +344,13 @@ class Context:
 
     def comm_destroy(self):
         self.check(self.lib.rtr_comm_destroy(self.handle))
+
+    def gather_stripes(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int,
+                       stripes_of_rank, root: int = 0):
+        """Like allgather_stripes, but only `root` receives the blocks (each travels once)."""
+        st = np.ascontiguousarray(stripes_of_rank, dtype=np.uint32)
+        self.check(self.lib.rtr_gather_stripes(self.handle, C.c_void_p(image_dev), width, height, bytes_per_pixel,
+                                               rows_per_block, _ptr(st), root))
 
     def switch_stream(self, cuda_stream: int):
         """Enqueue later calls on `cuda_stream` without waiting for the work already enqueued (pipelined frames)."""

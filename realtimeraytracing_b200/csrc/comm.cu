@@ -23,6 +23,8 @@ struct NcclApi {
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int);
     int (*CommDestroy)(NcclComm);
     int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
     int (*GroupStart)();
     int (*GroupEnd)();
     const char* (*GetErrorString)(int);
@@ -49,6 +51,8 @@ int load_nccl(rtr_ctx* ctx) {
     RTR_SYM(CommInitRank, "ncclCommInitRank");
     RTR_SYM(CommDestroy, "ncclCommDestroy");
     RTR_SYM(Broadcast, "ncclBroadcast");
+    RTR_SYM(Send, "ncclSend");
+    RTR_SYM(Recv, "ncclRecv");
     RTR_SYM(GroupStart, "ncclGroupStart");
     RTR_SYM(GroupEnd, "ncclGroupEnd");
     RTR_SYM(GetErrorString, "ncclGetErrorString");
@@ -306,6 +310,34 @@ int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_
         char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
         RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, owner[blk % owner.size()],
                                        ctx->nccl_comm, ctx->stream));
+    }
+    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    return RTR_OK;
+}
+
+int rtr_gather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
+                       uint32_t rows_per_block, const uint32_t* stripes_of_rank, int root) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!image_dev || width == 0 || height == 0 || bytes_per_pixel == 0 || rows_per_block == 0 || !stripes_of_rank)
+        return rtr_set_error(ctx, RTR_E_INVALID, "gather_stripes: bad argument");
+    if (ctx->nranks == 1) return RTR_OK;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "gather_stripes: rtr_comm_init has not been called");
+    if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "gather_stripes: bad root %d", root);
+    const std::vector<int> owner = rtr_stripe_owners(stripes_of_rank, ctx->nranks);  // stripe -> rank
+    if (owner.empty()) return rtr_set_error(ctx, RTR_E_INVALID, "gather_stripes: no stripes");
+    const size_t row_bytes = (size_t)width * bytes_per_pixel;
+    const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
+    // point to point: every block travels once, from its owner to the root (an all-gather moves nranks - 1 copies)
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    for (uint32_t blk = 0; blk < blocks; ++blk) {
+        const int own = owner[blk % owner.size()];
+        if (own == root || (ctx->rank != root && ctx->rank != own)) continue;
+        const uint32_t r0 = blk * rows_per_block;
+        const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
+        char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
+        const size_t bytes = (size_t)(r1 - r0) * row_bytes;
+        if (ctx->rank == root) RTR_NCCL(ctx, g_nccl.Recv(p, bytes, kNcclUint8, own, ctx->nccl_comm, ctx->stream));
+        else RTR_NCCL(ctx, g_nccl.Send(p, bytes, kNcclUint8, root, ctx->nccl_comm, ctx->stream));
     }
     RTR_NCCL(ctx, g_nccl.GroupEnd());
     return RTR_OK;

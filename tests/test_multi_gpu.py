@@ -55,6 +55,16 @@ def _worker(rank, world, port, out_dir):
             exp_t = torch.from_numpy(np.ascontiguousarray(expected.reshape(H, W, 4)) if rank == 0 else np.zeros((H, W, 4), np.float32)).cuda()
             dist.broadcast(exp_t, src=0)
             assert np.array_equal(got, exp_t.cpu().numpy()), "rank %d traversal_only=%s" % (rank, traversal_only)
+            # the same frame gathered on rank 0 only (every block travels once)
+            d_img = ctx.dev_alloc(W * H * 16)
+            ctx.zero(d_img, W * H * 16)
+            bvh.render_stripes_dev(cam, W, H, d_img, rpb, layout, rank, denom_w=W, denom_h=H, bounces=2)
+            ctx.gather_stripes(d_img, W, H, 16, rpb, layout, 0)
+            got0 = np.zeros((H, W, 4), np.float32)
+            ctx.download(got0, d_img)
+            ctx.dev_free(d_img)
+            if rank == 0:
+                assert np.array_equal(got0, exp_t.cpu().numpy()), "gather_stripes traversal_only=%s" % traversal_only
             if traversal_only and rank != 0:
                 with pytest.raises(capi.RtrError):
                     bvh.trace_primary(cam, W, H, W, H, flags=capi.TRACE_REFERENCE_ORDER)
