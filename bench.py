@@ -224,7 +224,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if args.reserve_sms <= 0:
-        args.reserve_sms = 8 if world <= 2 else 12   # the broadcast has a pipeline stage of its own: it only has to beat the rays
+        args.reserve_sms = 8 if world <= 2 else 24   # measured: with fewer channels the broadcast to 7 peers, not the rays, sets the frame time
     if world > 1:
         if not args.no_pipeline:
             # the broadcast of the next frame's BVH runs beside the rays of the current one on --reserve-sms SMs:
@@ -349,7 +349,8 @@ def main():
             x_tris = [d_tris, torch.empty_like(d_tris)] if rank == 0 else None
         x_rgba_pinned = [rgba_pinned, torch.empty_like(rgba_pinned).pin_memory()] if rank == 0 else None
         x_meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory() if rank == 0 else None
-        x_up_done, x_tris_free, x_frame_done, x_img_free = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(4))
+        x_up_done, x_tris_free, x_frame_done, x_img_free, x_img_done = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(5))
+        streams_r = [stream_r, torch.cuda.Stream(device=dev)]
         stream.synchronize()
         marks = []
 
@@ -403,30 +404,34 @@ def main():
         def submit_rays(f, e2e):
             """stage R, every rank: the rays of its stripes of frame f, then the frame is gathered on rank 0."""
             k = f % NB
-            ctx.switch_stream(stream_r.cuda_stream)
-            stream_r.wait_event(ready[k])
+            j = f % 2
+            sr = streams_r[j]   # consecutive frames alternate between two streams: the first rays of frame f+1 fill the
+            #                     SMs that the last, longest paths of frame f no longer need
+            ctx.switch_stream(sr.cuda_stream)
+            sr.wait_event(ready[k])
+            sr.wait_event(x_img_done[j])          # frame f-2 has left this image buffer
             if rank == 0 and layout[0] > 0 and last_built[0] is not None:
                 # the persistent traversal kernel would hold the SMs a rebuild needs: on the building rank the rays
                 # start once the rebuild submitted last is through
-                stream_r.wait_event(last_built[0])
-            mark("rays0", f, stream_r)
-            j = f % 2
-            img = x_rgba[j] if e2e else d_rgba
+                sr.wait_event(last_built[0])
+            mark("rays0", f, sr)
+            img = x_rgba[j]
             if e2e and rank == 0:
-                stream_r.wait_event(x_img_free[j])   # the download of the frame that used this image buffer is through
+                sr.wait_event(x_img_free[j])   # the download of the frame that used this image buffer is through
             bvhs[k].render_stripes_dev(cam, W, H, img.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
                                        bounces=bounces, flags=flags)
-            released[k].record(stream_r)
-            mark("rays1", f, stream_r)
+            released[k].record(sr)
+            mark("rays1", f, sr)
             ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
-            mark("gather", f, stream_r)
+            x_img_done[j].record(sr)
+            mark("gather", f, sr)
             if e2e and rank == 0:
-                x_frame_done[j].record(stream_r)
+                x_frame_done[j].record(sr)
                 ctx.switch_stream(x_out.cuda_stream)
                 x_out.wait_event(x_frame_done[j])
                 ctx.download_async(x_rgba_pinned[j].numpy(), img.data_ptr())   # D2H of the frame, beside the next one
                 x_img_free[j].record(x_out)
-                ctx.switch_stream(stream_r.cuda_stream)
+                ctx.switch_stream(sr.cuda_stream)
 
         def run_pipelined(steps, e2e):
             # every rank issues its NCCL calls in the same order: exchange(f+1), gather(f), exchange(f+2), ...
@@ -443,7 +448,7 @@ def main():
                 submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
-            barrier(); stream_a.synchronize(); stream_b.synchronize()
+            barrier(); stream_a.synchronize(); stream_b.synchronize(); streams_r[1].synchronize()
             del marks[:]
             with torch.cuda.stream(stream_r):
                 d_rays.zero_()
@@ -451,14 +456,14 @@ def main():
             launches0 = ctx.launch_count
             stream_r.synchronize()
             e0.record(stream_r)
-            for st in (stream_a, stream_b, x_in):
+            for st in (stream_a, stream_b, x_in, streams_r[1]):
                 st.wait_event(e0)            # nothing of the region starts before it
             run_pipelined(steps, e2e)
-            for st in (stream_a, stream_b, x_out):
+            for st in (stream_a, stream_b, x_out, streams_r[1]):
                 stream_r.wait_stream(st)
             e1.record(stream_r)
             barrier()
-            for st in (stream_a, stream_b, x_in, x_out):
+            for st in (stream_a, stream_b, x_in, x_out, streams_r[1]):
                 st.synchronize()
             ctx.switch_stream(stream_r.cuda_stream)
             if marks:  # RTR_BENCH_TRACE=1: when each phase of each frame ended, ms after the start of the timed region

@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python -m realtimeraytracing_b200.build --force > gpurun_out/build.log 2>&1
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/tests_gpu.log 2>&1
+timeout 1500 python -m pytest tests/test_trace_gpu.py -x -q -m gpu > gpurun_out/tests_gpu.log 2>&1
 echo "tests exit $?" >> gpurun_out/tests_gpu.log
 tail -15 gpurun_out/tests_gpu.log
 {
-for cfg in "" "-DRTR_WALK_STEPS=1" "-DRTR_WALK_STEPS=3" "-DRTR_WALK_STEPS=4 -DRTR_BLOCK_BATCH=4" "-DRTR_SMEM_STACK=12" "-DRTR_WALK_STEPS=3 -DRTR_TRACE_MIN_CTAS=7"; do
+for cfg in "" "-DRTR_PREFETCH=0" "-DRTR_PREFETCH=1" "-DRTR_PREFETCH=2"; do
   RTR_NVCC_EXTRA="$cfg" timeout 300 python profiles/time_render.py --force-build 2>&1 | tail -1
 done
 } > gpurun_out/sweep_trace3.log 2>&1

@@ -529,6 +529,11 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 #endif
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
+#ifndef RTR_PREFETCH
+#define RTR_PREFETCH 2   // bit 0: record of a stacked child, bit 1: record of a parked leaf
+#endif
+constexpr int kPrefetch = RTR_PREFETCH;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef RTR_WALK_STEPS
 #define RTR_WALK_STEPS 4
 #endif
@@ -745,6 +750,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     if (pend_node == RTR_NONE) {  // park the leaf and keep walking
                         pend_node = a & ~kLeafBit;
                         need_pop = true;
+                        if (kPrefetch & 2) prefetch_l2(A.pairs + (size_t)pend_node * 4);  // its record will be wanted at the leaf step
                     }
                 } else {
                     // compressed child pair: one 256-bit load (LDG.E.256, sm_100+)
@@ -778,6 +784,8 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     if (hl && hr) {
                         const bool left_first = tl <= tr;
                         push_far(left_first ? tr : tl, left_first ? rw : lw);
+                        // the stacked child is visited later, if at all: start moving its record towards the SM now
+                        if (kPrefetch & 1) prefetch_l2(A.pairs + (size_t)((left_first ? rw : lw) & ~kLeafBit) * 4);
                         a = left_first ? lw : rw;
                     } else if (hl) a = lw;
                     else if (hr) a = rw;
