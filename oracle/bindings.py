@@ -109,6 +109,7 @@ class Oracle:
         L.orc_trace_primary.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, vp, i32]
         L.orc_trace_rays.argtypes = [vp, vp, vp, vp, u64, vp, i32]
         L.orc_render.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, vp, vp, vp, i32]
+        L.orc_shade.argtypes = [vp, u64, vp, vp, vp, i32, vp]
         L.orc_bounce_ray.argtypes = [vp, vp, vp, vp, vp]
         L.orc_bounce_ray.restype = i32
         L.orc_shadow_ray.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -273,6 +274,14 @@ class Oracle:
         self.lib.orc_render(_p(flat), _p(tris), _p(meshes), _p(cam), width, height, denom_w, denom_h,
                             row0, row1, bounces, 1 if shadow else 0, _p(light), _p(rgba), _p(hits), _p(nrays), threads)
         return rgba, hits, int(nrays[0])
+
+    def shade(self, hits, tris, meshes, materials, wireframe=False):
+        """getColor of raytracer.glsl (no BVH overlay): rgba [n, 4]."""
+        hits = np.ascontiguousarray(hits)
+        materials = np.ascontiguousarray(materials, dtype=np.float32)
+        out = np.zeros((hits.size, 4), dtype=np.float32)
+        self.lib.orc_shade(_p(hits), hits.size, _p(tris), _p(meshes), _p(materials), 1 if wireframe else 0, _p(out))
+        return out
 
     def num_threads(self):
         return int(self.lib.orc_num_threads())

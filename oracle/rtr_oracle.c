@@ -772,3 +772,23 @@ void orc_render(const orc_node* flat, const orc_triangle* tris,
         }
     if (rays_traced) *rays_traced = total;
 }
+
+
+/* raytracer.glsl:159-179 (getColor) + :299-331 (main), uIsBVHDisplayed == false */
+void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const orc_mesh* meshes,
+               const float* materials, int wireframe, float* rgba_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        float c[4] = {0.f, 0.f, 0.f, 1.f};                         /* :300 */
+        const orc_hit* h = &hits[i];
+        if (h->did_hit != 0) {                                      /* :165 */
+            const uint32_t model = tris[h->triangle_id].model_id;           /* :166 */
+            const float* m = materials + 4 * (size_t)meshes[model].material_id;
+            for (int k = 0; k < 4; ++k) c[k] = c[k] + m[k];         /* :167 */
+            if (wireframe) {                                        /* :170-178 */
+                const float th = 0.02f;                             /* :71 */
+                if (h->b0 < th || h->b1 < th || h->b2 < th) { c[0] = c[1] = c[2] = 0.f; c[3] = 1.f; }
+            }
+        }
+        for (int k = 0; k < 4; ++k) rgba_out[4 * i + k] = c[k];    /* :330 */
+    }
+}

@@ -169,6 +169,13 @@ void orc_render(const orc_node* flat, const orc_triangle* tris,
                 const float light_pos[3],
                 float* rgba_out, orc_hit* primary_hits_out, uint64_t* rays_traced,
                 int threads);
+/* getColor + main of raytracer.glsl (:159-179, :299-331) without the BVH overlay: the reference's actual frame.
+ * value = (0,0,0,1); if the pixel hit: value += colour of the material of the triangle's model; wireframe: a hit
+ * with a barycentric below WIREFRAME_LINE_WIDTH (0.02, :71) is (0,0,0,1).  materials: 4 floats each (material.hpp:9-11).
+ * The material id is the host's meshes[model]._MaterialId (the shader reads it at stride 80 instead of the host's 68,
+ * Q7: identical for model 0, i.e. for every single-model scene). */
+void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const orc_mesh* meshes,
+               const float* materials, int wireframe, float* rgba_out);
 /* deterministic secondary-ray definitions (shared with the CUDA path) */
 int orc_bounce_ray(const orc_ray* in, const orc_hit* hit, const orc_triangle* tris,
                    const orc_mesh* meshes, orc_ray* out);

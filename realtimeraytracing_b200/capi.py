@@ -12,6 +12,7 @@ RTR_OK = 0
 ERROR_NAMES = {0: "RTR_OK", -1: "RTR_E_INVALID", -2: "RTR_E_CUDA", -3: "RTR_E_NOMEM", -4: "RTR_E_NODEVICE",
                -5: "RTR_E_UNSUPPORTED", -6: "RTR_E_STATE", -7: "RTR_E_COMM"}
 TRACE_DEFAULT = 0
+SHADE_WIREFRAME = 1  # RTR_SHADE_WIREFRAME
 TRACE_REFERENCE_ORDER = 1
 NCCL_UNIQUE_ID_BYTES = 128
 
@@ -34,7 +35,7 @@ SYMBOLS = [
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
-    "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes",
+    "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
 ]
 
 
@@ -135,6 +136,8 @@ def load_library():
     L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
     L.rtr_gather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp, i32]
+    L.rtr_shade.argtypes = [vp, vp, C.c_uint64, vp, u32, vp, u32, vp, u32, u32, vp]
+    L.rtr_shade_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u32, vp]
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     _lib = L
@@ -344,6 +347,20 @@ class Context:
 
     def comm_destroy(self):
         self.check(self.lib.rtr_comm_destroy(self.handle))
+
+    def shade(self, hits, tris, meshes, materials, wireframe: bool = False) -> np.ndarray:
+        """getColor of raytracer.glsl (:159-179) on hit records: the reference's rgba32f pixels, [n, 4]."""
+        hits = _as(hits, HIT); tris = _as(tris, TRIANGLE); meshes = _as(meshes, MESH)
+        materials = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros((hits.size, 4), dtype=np.float32)
+        self.check(self.lib.rtr_shade(self.handle, _ptr(hits), hits.size, _ptr(tris), tris.size, _ptr(meshes), meshes.size,
+                                      _ptr(materials), materials.shape[0], SHADE_WIREFRAME if wireframe else 0, _ptr(out)))
+        return out
+
+    def shade_dev(self, hits_dev: int, n: int, tris_dev: int, meshes_dev: int, materials_dev: int, rgba_dev: int,
+                  wireframe: bool = False):
+        self.check(self.lib.rtr_shade_dev(self.handle, C.c_void_p(hits_dev), n, C.c_void_p(tris_dev), C.c_void_p(meshes_dev),
+                                          C.c_void_p(materials_dev), SHADE_WIREFRAME if wireframe else 0, C.c_void_p(rgba_dev)))
 
     def gather_stripes(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int,
                        stripes_of_rank, root: int = 0):

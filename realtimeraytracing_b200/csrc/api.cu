@@ -828,6 +828,54 @@ int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam
                              rgba_dev, hits_dev, rays_dev, rows_per_block, (uint32_t)owner.size(), mine, off);
 }
 
+int rtr_shade_dev(rtr_ctx* ctx, const rtr_hit* hits_dev, uint64_t n, const rtr_triangle* tris_dev, const rtr_mesh* meshes_dev,
+                  const rtr_material* materials_dev, uint32_t flags, float* rgba_dev) {
+    if (!ctx) return RTR_E_INVALID;
+    if (n && (!hits_dev || !tris_dev || !meshes_dev || !materials_dev || !rgba_dev))
+        return rtr_set_error(ctx, RTR_E_INVALID, "shade: NULL argument");
+    return rtr_shade_launch(ctx, hits_dev, n, tris_dev, meshes_dev, materials_dev, flags, rgba_dev);
+}
+
+int rtr_shade(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle* tris, uint32_t nb_triangles,
+              const rtr_mesh* meshes, uint32_t nb_meshes, const rtr_material* materials, uint32_t nb_materials,
+              uint32_t flags, float* rgba_out) {
+    if (!ctx) return RTR_E_INVALID;
+    if (n == 0) return RTR_OK;
+    if (!hits || !tris || !meshes || !materials || !rgba_out || !nb_triangles || !nb_meshes || !nb_materials)
+        return rtr_set_error(ctx, RTR_E_INVALID, "shade: NULL or empty argument");
+    // the records index triangles, models and materials: reject what the shader would read out of bounds
+    for (uint64_t i = 0; i < n; ++i)
+        if (hits[i].did_hit && hits[i].triangle_id >= nb_triangles)
+            return rtr_set_error(ctx, RTR_E_INVALID, "shade: hit %llu names triangle %u of %u", (unsigned long long)i,
+                                 hits[i].triangle_id, nb_triangles);
+    for (uint32_t t = 0; t < nb_triangles; ++t)
+        if (tris[t].model_id >= nb_meshes) return rtr_set_error(ctx, RTR_E_INVALID, "shade: triangle %u names model %u of %u", t, tris[t].model_id, nb_meshes);
+    for (uint32_t m = 0; m < nb_meshes; ++m)
+        if (meshes[m].material_id >= nb_materials) return rtr_set_error(ctx, RTR_E_INVALID, "shade: model %u names material %u of %u", m, meshes[m].material_id, nb_materials);
+    const size_t hb = n * sizeof(rtr_hit), tb = (size_t)nb_triangles * sizeof(rtr_triangle), mb = (size_t)nb_meshes * sizeof(rtr_mesh);
+    const size_t ab = (size_t)nb_materials * sizeof(rtr_material), cb = n * 16;
+    Staging st;
+    RTR_CHECK(staging_begin(ctx, hb + tb + mb + ab + cb + 2048, 0, &st));
+    rtr_hit* d_hits = static_cast<rtr_hit*>(staging_take(&st, hb));
+    rtr_triangle* d_tris = static_cast<rtr_triangle*>(staging_take(&st, tb));
+    rtr_mesh* d_meshes = static_cast<rtr_mesh*>(staging_take(&st, mb));
+    rtr_material* d_mat = static_cast<rtr_material*>(staging_take(&st, ab));
+    float* d_rgba = static_cast<float*>(staging_take(&st, cb));
+    auto body = [&]() -> int {
+        RTR_CUDA(ctx, cudaMemcpyAsync(d_hits, hits, hb, cudaMemcpyHostToDevice, ctx->stream));
+        RTR_CUDA(ctx, cudaMemcpyAsync(d_tris, tris, tb, cudaMemcpyHostToDevice, ctx->stream));
+        RTR_CUDA(ctx, cudaMemcpyAsync(d_meshes, meshes, mb, cudaMemcpyHostToDevice, ctx->stream));
+        RTR_CUDA(ctx, cudaMemcpyAsync(d_mat, materials, ab, cudaMemcpyHostToDevice, ctx->stream));
+        RTR_CHECK(rtr_shade_launch(ctx, d_hits, n, d_tris, d_meshes, d_mat, flags, d_rgba));
+        RTR_CUDA(ctx, cudaMemcpyAsync(rgba_out, d_rgba, cb, cudaMemcpyDeviceToHost, ctx->stream));
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RTR_OK;
+    };
+    const int r = body();
+    staging_end(&st);
+    return r;
+}
+
 int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height, uint32_t denom_w,
                uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
                uint32_t flags, float* rgba_out, rtr_hit* hits_out, uint64_t* rays_traced) {

@@ -183,3 +183,5 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
                       const float light[3], uint32_t flags, float* rgba_dev, rtr_hit* hits_dev, uint64_t* rays_dev,
                       uint32_t rows_per_block = 0, uint32_t total_stripes = 1, uint32_t nb_stripes = 1,
                       const uint8_t* stripe_offsets = nullptr);
+int rtr_shade_launch(rtr_ctx* ctx, const rtr_hit* hits_dev, uint64_t n, const rtr_triangle* tris_dev, const rtr_mesh* meshes_dev,
+                     const rtr_material* materials_dev, uint32_t flags, float* rgba_dev);

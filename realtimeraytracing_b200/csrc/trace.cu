@@ -917,6 +917,30 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     if (rays_traced && lane == 0u && traced) atomicAdd(rays_traced, (unsigned long long)traced);
 }
 
+// getColor + main of raytracer.glsl (:159-179, :299-331), BVH overlay off: the reference's frame from hit records
+__global__ void __launch_bounds__(256)
+shade_kernel(const rtr_hit* __restrict__ hits, uint64_t n, const rtr_triangle* __restrict__ tris,
+             const rtr_mesh* __restrict__ meshes, const rtr_material* __restrict__ materials, uint32_t flags,
+             float4* __restrict__ rgba) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2* hp = reinterpret_cast<const uint2*>(hits + i);  // 24-byte records: three 8-byte loads
+    const uint2 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+    float4 c = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (h2.x != 0u) {
+        const uint32_t model = __ldg(&tris[h2.y].model_id);
+        const float* m = materials[__ldg(&meshes[model].material_id)].color;
+        c.x = __fadd_rn(c.x, __ldg(m)); c.y = __fadd_rn(c.y, __ldg(m + 1));
+        c.z = __fadd_rn(c.z, __ldg(m + 2)); c.w = __fadd_rn(c.w, __ldg(m + 3));
+        if (flags & RTR_SHADE_WIREFRAME) {
+            const float th = 0.02f;  // WIREFRAME_LINE_WIDTH, raytracer.glsl:71
+            if (__uint_as_float(h0.x) < th || __uint_as_float(h0.y) < th || __uint_as_float(h1.x) < th)
+                c = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
+    }
+    rgba[i] = c;
+}
+
 inline Accel accel_of(const rtr_bvh* b) {
     Accel A;
     A.nodes = b->flat_view; A.wtri = b->wtri_view; A.pairs = b->pairs_view; A.by_rank = b->wtri_by_rank ? 1u : 0u;
@@ -1043,4 +1067,15 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
         return RTR_OK;
     }
     return launch_persistent(ctx, b, pixel_jobs(cam, width, denom_w, denom_h, rm, bounces, shadow, light, rgba, hits), rays);
+}
+
+int rtr_shade_launch(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle* tris, const rtr_mesh* meshes,
+                     const rtr_material* materials, uint32_t flags, float* rgba) {
+    if (n == 0) return RTR_OK;
+    if (n >= (1ull << 40)) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "shade: too many pixels");
+    RTR_PROF(ctx, "shade_kernel");
+    shade_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(hits, n, tris, meshes, materials, flags,
+                                                                       reinterpret_cast<float4*>(rgba));
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
 }

@@ -154,3 +154,20 @@ def test_mesh_traversal_ties_and_render(oracle):
     assert np.all(rgba[..., 3] == 1.0) and rgba[..., 0].max() > 0.1
     barys = np.stack([hits["b0"], hits["b1"], hits["b2"]], 1)[hits["did_hit"] == 1]
     assert np.all(barys >= 0) and np.allclose(barys.sum(1), 1.0, atol=1e-5)
+
+
+def test_shade_follows_getcolor(oracle):
+    """raytracer.glsl:159-179 by hand: a miss is (0,0,0,1), a hit adds the material colour of the triangle's model,
+    wireframe blackens hits whose barycentric is below 0.02."""
+    from realtimeraytracing_b200.layouts import HIT, MESH, TRIANGLE
+    tris = np.zeros(3, TRIANGLE); tris["model_id"] = [0, 1, 1]
+    meshes = np.zeros(2, MESH); meshes["material_id"] = [1, 0]
+    materials = np.array([[0.25, 0.5, 0.75, 1.0], [1.0, 0.0, 0.5, 0.125]], np.float32)
+    hits = np.zeros(4, HIT)
+    hits[1] = (0.3, 0.3, 0.4, 2.0, 1, 0)     # triangle 0 -> model 0 -> material 1
+    hits[2] = (0.01, 0.49, 0.5, 1.0, 1, 2)   # near an edge; triangle 2 -> model 1 -> material 0
+    hits[3] = (0.5, 0.49, 0.019, 1.0, 1, 1)
+    plain = oracle.shade(hits, tris, meshes, materials)
+    assert np.array_equal(plain, np.array([[0, 0, 0, 1], [1, 0, 0.5, 1.125], [0.25, 0.5, 0.75, 2], [0.25, 0.5, 0.75, 2]], np.float32))
+    wire = oracle.shade(hits, tris, meshes, materials, wireframe=True)
+    assert np.array_equal(wire, np.array([[0, 0, 0, 1], [1, 0, 0.5, 1.125], [0, 0, 0, 1], [0, 0, 0, 1]], np.float32))

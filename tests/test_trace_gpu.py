@@ -234,3 +234,29 @@ def test_axis_parallel_rays_take_the_exact_slab_test(ctx, oracle):
         assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
     finally:
         bvh.close()
+
+
+@pytest.mark.parametrize("wireframe", [False, True])
+def test_shaded_frame_equals_getcolor(ctx, oracle, wireframe):
+    """The reference's actual output: primary hits -> getColor (raytracer.glsl:159-179), two models with
+    different materials, with and without the wireframe mode."""
+    from realtimeraytracing_b200.layouts import MESH
+    tris, meshes = synth.grid_mesh(24, 20)
+    tris = tris.copy(); tris["model_id"][tris.size // 2:] = 1
+    meshes = np.concatenate([meshes, meshes]).view(MESH).copy()
+    meshes["material_id"] = [1, 0]
+    materials = np.array([[0.2, 0.4, 0.6, 1.0], [0.9, 0.1, 0.3, 0.5]], np.float32)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H = 96, 64
+        cam = synth.reference_camera(aspect=W / H)
+        hits = bvh.trace_primary(cam, W, H, W, H)
+        assert 0.2 < hits["did_hit"].mean() < 1.0
+        got = ctx.shade(hits, tris, meshes, materials, wireframe=wireframe)
+        exp = oracle.shade(hits, tris, meshes, materials, wireframe=wireframe)
+        assert np.array_equal(got, exp)
+        assert len(np.unique(got.view([("c", "<f4", 4)]))) >= (2 if wireframe else 3)
+        with pytest.raises(capi.RtrError):
+            ctx.shade(hits, tris, meshes, materials[:1], wireframe=wireframe)   # model 0 names material 1
+    finally:
+        bvh.close()
