@@ -5,7 +5,7 @@ timeout 1500 python -m pytest tests/test_trace_gpu.py -x -q -m gpu > gpurun_out/
 echo "tests exit $?" >> gpurun_out/tests_gpu.log
 tail -15 gpurun_out/tests_gpu.log
 {
-for cfg in "" "-DRTR_PREFETCH=0" "-DRTR_PREFETCH=1" "-DRTR_PREFETCH=2"; do
+for cfg in "" "-DRTR_LEAF_BATCH=14"; do
   RTR_NVCC_EXTRA="$cfg" timeout 300 python profiles/time_render.py --force-build 2>&1 | tail -1
 done
 } > gpurun_out/sweep_trace3.log 2>&1

@@ -809,21 +809,26 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     uint4 c0, c1, c2, c3;
                     ld_nc_256(A.pairs + (size_t)pend_node * 4, c0, c1);
                     ld_nc_256(A.pairs + (size_t)pend_node * 4 + 2, c2, c3);
-                    const float4 blo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
-                    const float4 bhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
-                    float te;
-                    if (intersect_box(r, blo, bhi, te) && !(te > limit)) {
-                        TriWorld w;  // shader naming (Q8): _P1 = host P2, _P2 = host P1
-                        w.p0 = make_float3(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x));
-                        w.p2 = make_float3(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w));
-                        w.p1 = make_float3(__uint_as_float(c3.x), __uint_as_float(c3.y), __uint_as_float(c3.z));
-                        Hit h;
-                        if (ray_triangle_w(r, w, 0u, 0u, h)) {
-                            if (st & 0x10000u) {
-                                if (h.t < best_t) { best_node = pend_node; a = kDry; sp = 0; }
-                            } else if (h.t < best_t || (h.t == best_t && best_node != RTR_NONE && pend_node > best_node)) {
-                                best_t = h.t; best_node = pend_node;
-                                limit = limit_of(h.t);
+                    // Both tests are pure: "box passes, then triangle hits" == "triangle hits, and box passes".  The
+                    // compressed parent already let this leaf through, so the exact box test rejects few and the
+                    // triangle test most: the triangle goes first, the box is only consulted for an actual hit.
+                    TriWorld w;  // shader naming (Q8): _P1 = host P2, _P2 = host P1
+                    w.p0 = make_float3(__uint_as_float(c1.z), __uint_as_float(c1.w), __uint_as_float(c2.x));
+                    w.p2 = make_float3(__uint_as_float(c2.y), __uint_as_float(c2.z), __uint_as_float(c2.w));
+                    w.p1 = make_float3(__uint_as_float(c3.x), __uint_as_float(c3.y), __uint_as_float(c3.z));
+                    Hit h;
+                    if (ray_triangle_w(r, w, 0u, 0u, h)) {
+                        const bool any_mode = (st & 0x10000u) != 0u;
+                        const bool better = h.t < best_t ||
+                                            (!any_mode && h.t == best_t && best_node != RTR_NONE && pend_node > best_node);
+                        if (better) {
+                            const float4 blo = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), 0.f);
+                            const float4 bhi = make_float4(__uint_as_float(c0.w), __uint_as_float(c1.x), __uint_as_float(c1.y), 0.f);
+                            float te;
+                            if (intersect_box(r, blo, bhi, te)) {
+                                best_node = pend_node;
+                                if (any_mode) { a = kDry; sp = 0; }
+                                else { best_t = h.t; limit = limit_of(h.t); }
                             }
                         }
                     }
