@@ -190,6 +190,14 @@ int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t nb_triangles,
 /* device inputs, borrowed (must stay alive while the BVH is traced); asynchronous */
 int rtr_bvh_build_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t nb_triangles, uint32_t tris_array_len,
                       const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t search_radius, rtr_bvh** out);
+/* the same builder with the leaves ordered by 63-bit Morton keys (21 bits per axis, rtr_morton_codes64; 8 sort passes
+ * over (u64 key, u32 index) pairs).  The reference has 30-bit codes only (bvh.cpp:358-372): this is the "64-bit keys"
+ * variant of north_star, defined by oracle/rtr_oracle.c: orc_bvh_build64; its leaf order refines the 32-bit one
+ * (code64 >> 33 == code32) and only differs where 10 bits per axis cannot tell centroids apart. */
+int rtr_bvh_build64(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t nb_triangles, uint32_t tris_array_len,
+                    const rtr_mesh* meshes, uint32_t nb_meshes, uint32_t search_radius, rtr_bvh** out);
+int rtr_bvh_build64_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t nb_triangles, uint32_t tris_array_len,
+                        const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t search_radius, rtr_bvh** out);
 int rtr_bvh_destroy(rtr_bvh* bvh);
 uint32_t rtr_bvh_nb_triangles(const rtr_bvh* bvh);
 uint32_t rtr_bvh_nb_nodes(const rtr_bvh* bvh); /* 2n-1 */
@@ -201,6 +209,7 @@ int rtr_bvh_enable_stage_timing(rtr_bvh* bvh, int enable);
 int rtr_bvh_stage_ms(rtr_bvh* bvh, float out[6]);
 /* sorted Morton codes (PlocParams::_MortonCodes) and BVH_Params::_TriangleIndices (bvh.hpp:55) */
 int rtr_bvh_morton_codes(rtr_bvh* bvh, uint32_t* out);
+int rtr_bvh_morton_codes64(rtr_bvh* bvh, uint64_t* out); /* sorted 63-bit codes of a rtr_bvh_build64 BVH */
 int rtr_bvh_triangle_indices(rtr_bvh* bvh, uint32_t* out);
 /* BVH_Params::_Clusters/_Parent/_LeftChild/_RightChild/_IsLeaf (bvh.hpp:50-54) by cluster id,
  * ids in serial-merge order (Q3); absent links are RTR_NONE; any pointer may be NULL */

@@ -85,6 +85,8 @@ class Oracle:
         L.orc_radix_sort_pairs_u64.argtypes = [vp, vp, u32]
         L.orc_bvh_build.argtypes = [vp, u32, u32, vp, u32, u32]
         L.orc_bvh_build.restype = vp
+        L.orc_bvh_build64.argtypes = [vp, u32, u32, vp, u32, u32]
+        L.orc_bvh_build64.restype = vp
         L.orc_bvh_destroy.argtypes = [vp]
         L.orc_bvh_nb_iterations.argtypes = [vp]
         L.orc_bvh_nb_iterations.restype = u32
@@ -182,9 +184,10 @@ class Oracle:
         return keys, vals
 
     # ---- PLOC + flatten ----
-    def bvh_build(self, tris, meshes, n=None, search_radius=16) -> OracleBvh:
+    def bvh_build(self, tris, meshes, n=None, search_radius=16, key_bits=32) -> OracleBvh:
         n = tris.size if n is None else n
-        h = self.lib.orc_bvh_build(_p(tris), n, tris.size, _p(meshes), meshes.size, search_radius)
+        fn = self.lib.orc_bvh_build64 if key_bits == 64 else self.lib.orc_bvh_build
+        h = fn(_p(tris), n, tris.size, _p(meshes), meshes.size, search_radius)
         if not h:
             raise ValueError("orc_bvh_build rejected its arguments")
         try:

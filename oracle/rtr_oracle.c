@@ -319,9 +319,27 @@ static float merged_area(const orc_node* a, const orc_node* b) {
     return 2 * (dx * dy + dy * dz + dz * dx);
 }
 
+static orc_bvh* bvh_build_impl(const orc_triangle* tris, uint32_t n, uint32_t array_len,
+                               const orc_mesh* meshes, uint32_t nb_meshes,
+                               uint32_t search_radius, int key_bits);
+
 orc_bvh* orc_bvh_build(const orc_triangle* tris, uint32_t n, uint32_t array_len,
                        const orc_mesh* meshes, uint32_t nb_meshes,
                        uint32_t search_radius) {
+    return bvh_build_impl(tris, n, array_len, meshes, nb_meshes, search_radius, 32);
+}
+/* the same builder over 63-bit Morton keys (21 bits per axis, orc_morton_codes64): only the leaf order changes.
+ * No reference definition exists (bvh.cpp has 30-bit codes only); the 64-bit order refines the 32-bit one
+ * (code64 >> 33 == code32), ties are broken by the original index like std::sort over pairs does (bvh.cpp:223-231). */
+orc_bvh* orc_bvh_build64(const orc_triangle* tris, uint32_t n, uint32_t array_len,
+                         const orc_mesh* meshes, uint32_t nb_meshes,
+                         uint32_t search_radius) {
+    return bvh_build_impl(tris, n, array_len, meshes, nb_meshes, search_radius, 64);
+}
+
+static orc_bvh* bvh_build_impl(const orc_triangle* tris, uint32_t n, uint32_t array_len,
+                               const orc_mesh* meshes, uint32_t nb_meshes,
+                               uint32_t search_radius, int key_bits) {
     if (!tris || !meshes || n == 0 || array_len < n || nb_meshes == 0) return NULL;
     orc_bvh* b = (orc_bvh*)calloc(1, sizeof(orc_bvh));
     uint32_t nc = 2 * n - 1;
@@ -338,9 +356,16 @@ orc_bvh* orc_bvh_build(const orc_triangle* tris, uint32_t n, uint32_t array_len,
     b->trace_merges = (uint32_t*)malloc(cap_it * 4);
 
     /* bvh.cpp:214-232 */
-    orc_morton_codes(tris, n, array_len, meshes, b->morton_sorted);
     for (uint32_t i = 0; i < n; ++i) b->triangle_indices[i] = i;
-    orc_sort_pairs(b->morton_sorted, b->triangle_indices, n);
+    if (key_bits == 64) {
+        b->morton_sorted64 = (uint64_t*)malloc((size_t)n * 8);
+        orc_morton_codes64(tris, n, array_len, meshes, b->morton_sorted64);
+        orc_radix_sort_pairs_u64(b->morton_sorted64, b->triangle_indices, n);  /* stable: ties keep index order */
+        for (uint32_t i = 0; i < n; ++i) b->morton_sorted[i] = (uint32_t)(b->morton_sorted64[i] >> 33);
+    } else {
+        orc_morton_codes(tris, n, array_len, meshes, b->morton_sorted);
+        orc_sort_pairs(b->morton_sorted, b->triangle_indices, n);
+    }
 
     /* bvh.cpp:26-46 */
     uint32_t* c_in = (uint32_t*)malloc((size_t)n * 4);
@@ -415,13 +440,14 @@ orc_bvh* orc_bvh_build(const orc_triangle* tris, uint32_t n, uint32_t array_len,
 
 void orc_bvh_destroy(orc_bvh* b) {
     if (!b) return;
-    free(b->morton_sorted); free(b->triangle_indices); free(b->clusters);
+    free(b->morton_sorted); free(b->morton_sorted64); free(b->triangle_indices); free(b->clusters);
     free(b->parent); free(b->left); free(b->right);
     free(b->trace_active); free(b->trace_merges);
     free(b);
 }
 uint32_t orc_bvh_nb_iterations(const orc_bvh* b) { return b->nb_iterations; }
 const uint32_t* orc_bvh_morton_sorted(const orc_bvh* b) { return b->morton_sorted; }
+const uint64_t* orc_bvh_morton_sorted64(const orc_bvh* b) { return b->morton_sorted64; }
 const uint32_t* orc_bvh_triangle_indices(const orc_bvh* b) { return b->triangle_indices; }
 const orc_node* orc_bvh_clusters(const orc_bvh* b) { return b->clusters; }
 const uint32_t* orc_bvh_parent(const orc_bvh* b) { return b->parent; }

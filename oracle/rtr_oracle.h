@@ -104,6 +104,7 @@ typedef struct {
     uint32_t n;            /* triangles */
     uint32_t nb_clusters;  /* 2n-1 */
     uint32_t* morton_sorted;     /* [n] */
+    uint64_t* morton_sorted64;   /* [n], orc_bvh_build64 only (else NULL) */
     uint32_t* triangle_indices;  /* [n] */
     orc_node* clusters;          /* [2n-1] by cluster id; internal links are 0 (Q10) */
     uint32_t* parent;            /* [2n-1], 0xFFFFFFFF = none */
@@ -118,6 +119,11 @@ typedef struct {
 orc_bvh* orc_bvh_build(const orc_triangle* tris, uint32_t n, uint32_t array_len,
                        const orc_mesh* meshes, uint32_t nb_meshes,
                        uint32_t search_radius);
+/* same builder, leaves ordered by 63-bit Morton keys (no reference definition, see rtr_oracle.c) */
+orc_bvh* orc_bvh_build64(const orc_triangle* tris, uint32_t n, uint32_t array_len,
+                         const orc_mesh* meshes, uint32_t nb_meshes,
+                         uint32_t search_radius);
+const uint64_t* orc_bvh_morton_sorted64(const orc_bvh* b);
 void orc_bvh_destroy(orc_bvh* b);
 /* plain accessors for ctypes users */
 uint32_t orc_bvh_nb_iterations(const orc_bvh* b);

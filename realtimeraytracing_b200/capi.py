@@ -36,6 +36,7 @@ SYMBOLS = [
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
     "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
+    "rtr_bvh_build64", "rtr_bvh_build64_dev", "rtr_bvh_morton_codes64",
 ]
 
 
@@ -102,6 +103,9 @@ def load_library():
     L.rtr_scene_bounds.argtypes = [vp, vp, u32, vp, u32, vp]
     L.rtr_bvh_build.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
     L.rtr_bvh_build_dev.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
+    L.rtr_bvh_build64.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
+    L.rtr_bvh_build64_dev.argtypes = [vp, vp, u32, u32, vp, u32, u32, pp]
+    L.rtr_bvh_morton_codes64.argtypes = [vp, vp]
     L.rtr_bvh_destroy.argtypes = [vp]
     L.rtr_bvh_nb_triangles.argtypes = [vp]
     L.rtr_bvh_nb_triangles.restype = u32
@@ -396,16 +400,20 @@ class Bvh:
         self.handle = C.c_void_p()
 
     # -- construction --
-    def build(self, tris, meshes, n=None, search_radius: int = 16):
+    def build(self, tris, meshes, n=None, search_radius: int = 16, key_bits: int = 32):
+        """key_bits 32: the reference's 30-bit Morton codes; 64: 63-bit codes (rtr_bvh_build64)."""
         tris, meshes = _as(tris, TRIANGLE), _as(meshes, MESH)
         n = tris.size if n is None else n
-        self.ctx.check(self.lib.rtr_bvh_build(self.ctx.handle, _ptr(tris), n, tris.size, _ptr(meshes), meshes.size,
-                                              search_radius, C.byref(self.handle)))
+        fn = self.lib.rtr_bvh_build64 if key_bits == 64 else self.lib.rtr_bvh_build
+        self.ctx.check(fn(self.ctx.handle, _ptr(tris), n, tris.size, _ptr(meshes), meshes.size,
+                          search_radius, C.byref(self.handle)))
         return self
 
-    def build_dev(self, tris_dev: int, n: int, array_len: int, meshes_dev: int, nb_meshes: int, search_radius: int = 16):
-        self.ctx.check(self.lib.rtr_bvh_build_dev(self.ctx.handle, C.c_void_p(tris_dev), n, array_len,
-                                                  C.c_void_p(meshes_dev), nb_meshes, search_radius, C.byref(self.handle)))
+    def build_dev(self, tris_dev: int, n: int, array_len: int, meshes_dev: int, nb_meshes: int, search_radius: int = 16,
+                  key_bits: int = 32):
+        fn = self.lib.rtr_bvh_build64_dev if key_bits == 64 else self.lib.rtr_bvh_build_dev
+        self.ctx.check(fn(self.ctx.handle, C.c_void_p(tris_dev), n, array_len,
+                          C.c_void_p(meshes_dev), nb_meshes, search_radius, C.byref(self.handle)))
         return self
 
     def adopt_dev(self, nodes_dev: int, n: int, tris_dev: int, meshes_dev: int, nb_meshes: int):
@@ -462,6 +470,11 @@ class Bvh:
     def morton_codes(self) -> np.ndarray:
         out = np.zeros(self.nb_triangles, dtype=np.uint32)
         self.ctx.check(self.lib.rtr_bvh_morton_codes(self.handle, _ptr(out)))
+        return out
+
+    def morton_codes64(self) -> np.ndarray:
+        out = np.zeros(self.nb_triangles, dtype=np.uint64)
+        self.ctx.check(self.lib.rtr_bvh_morton_codes64(self.handle, _ptr(out)))
         return out
 
     def triangle_indices(self) -> np.ndarray:

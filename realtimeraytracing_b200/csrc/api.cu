@@ -64,12 +64,13 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 }
 
 void bvh_free_arrays(rtr_bvh* b) {
-    void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->order, b->cin, b->cout, b->tile_status,
+    void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->order, b->codes64, b->cin, b->cout, b->tile_status,
                     b->state, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
                     b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     b->codes = b->tri_idx = b->isize = b->ipos = b->order = b->cin = b->cout = nullptr;
+    b->codes64 = nullptr; b->codes64_cap = 0;
     b->node = nullptr;
     b->tile_status = nullptr; b->state = nullptr;
     b->trace_active = b->trace_merges = b->iter_first_id = nullptr;
@@ -533,8 +534,8 @@ int rtr_scene_bounds(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t array_len,
 }
 
 // ---- BVH ----
-int rtr_bvh_build_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uint32_t array_len,
-                      const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+static int build_dev_impl(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uint32_t array_len,
+                          const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t radius, uint32_t key_bits, rtr_bvh** out) {
     RTR_CHECK(check_build_args(ctx, tris_dev, n, array_len, meshes_dev, nb_meshes, radius, out));
     rtr_bvh* b = *out;
     if (!b) {
@@ -542,14 +543,24 @@ int rtr_bvh_build_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, ui
         if (!b) return rtr_set_error(ctx, RTR_E_NOMEM, "bvh_build: host allocation failed");
         b->ctx = ctx;
     }
+    b->key_bits = key_bits;
     const int r = bvh_build_common(ctx, tris_dev, n, array_len, meshes_dev, nb_meshes, radius, b);
     if (r != RTR_OK && !*out) { rtr_bvh_destroy(b); return r; }
     *out = b;
     return r;
 }
 
-int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t array_len, const rtr_mesh* meshes,
-                  uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+int rtr_bvh_build_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uint32_t array_len,
+                      const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+    return build_dev_impl(ctx, tris_dev, n, array_len, meshes_dev, nb_meshes, radius, 32, out);
+}
+int rtr_bvh_build64_dev(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uint32_t array_len,
+                        const rtr_mesh* meshes_dev, uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+    return build_dev_impl(ctx, tris_dev, n, array_len, meshes_dev, nb_meshes, radius, 64, out);
+}
+
+static int build_host_impl(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t array_len, const rtr_mesh* meshes,
+                           uint32_t nb_meshes, uint32_t radius, uint32_t key_bits, rtr_bvh** out) {
     RTR_CHECK(check_build_args(ctx, tris, n, array_len, meshes, nb_meshes, radius, out));
     rtr_bvh* b = *out;
     const bool fresh = (b == nullptr);
@@ -558,6 +569,7 @@ int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t a
         if (!b) return rtr_set_error(ctx, RTR_E_NOMEM, "bvh_build: host allocation failed");
         b->ctx = ctx;
     }
+    b->key_bits = key_bits;
     auto body = [&]() -> int {
         // like the reference ctor, keep private copies of both vectors (bvh.cpp:16-17)
         if (b->tris_own_cap < array_len) {
@@ -580,6 +592,15 @@ int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t a
     if (r != RTR_OK && fresh) { rtr_bvh_destroy(b); return r; }
     *out = b;
     return r;
+}
+
+int rtr_bvh_build(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t array_len, const rtr_mesh* meshes,
+                  uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+    return build_host_impl(ctx, tris, n, array_len, meshes, nb_meshes, radius, 32, out);
+}
+int rtr_bvh_build64(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, uint32_t array_len, const rtr_mesh* meshes,
+                    uint32_t nb_meshes, uint32_t radius, rtr_bvh** out) {
+    return build_host_impl(ctx, tris, n, array_len, meshes, nb_meshes, radius, 64, out);
 }
 
 int rtr_bvh_adopt_dev(rtr_ctx* ctx, const rtr_node* nodes_dev, uint32_t nb_triangles, const rtr_triangle* tris_dev,
@@ -655,7 +676,15 @@ int rtr_bvh_iteration_trace(rtr_bvh* b, uint32_t* active, uint32_t* merges, uint
 int rtr_bvh_morton_codes(rtr_bvh* b, uint32_t* out) {
     return with_bvh(b, true, [&]() -> int {
         if (!out) return rtr_set_error(b->ctx, RTR_E_INVALID, "NULL out");
+        if (b->key_bits == 64) return rtr_set_error(b->ctx, RTR_E_STATE, "built over 64-bit keys: use rtr_bvh_morton_codes64");
         return rtr_dev_download(b->ctx, out, b->codes, (size_t)b->n * 4);
+    });
+}
+int rtr_bvh_morton_codes64(rtr_bvh* b, uint64_t* out) {
+    return with_bvh(b, true, [&]() -> int {
+        if (!out) return rtr_set_error(b->ctx, RTR_E_INVALID, "NULL out");
+        if (b->key_bits != 64) return rtr_set_error(b->ctx, RTR_E_STATE, "built over 32-bit keys: use rtr_bvh_morton_codes");
+        return rtr_dev_download(b->ctx, out, b->codes64, (size_t)b->n * 8);
     });
 }
 int rtr_bvh_triangle_indices(rtr_bvh* b, uint32_t* out) {

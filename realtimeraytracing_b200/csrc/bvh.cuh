@@ -44,6 +44,9 @@ struct rtr_bvh {
     rtr_mesh* meshes_own = nullptr;    size_t meshes_own_cap = 0; // meshes
 
     // build arrays (device), sized by capacity
+    uint32_t key_bits = 32;        // Morton key width of the last build: 32 (30-bit codes, the reference) or 64 (63-bit)
+    uint64_t* codes64 = nullptr;   // [cap]  sorted 63-bit Morton codes (64-bit builds only, allocated on first use)
+    size_t codes64_cap = 0;
     uint32_t* codes = nullptr;     // [cap]  sorted Morton codes
     uint32_t* tri_idx = nullptr;   // [cap]  BVH_Params::_TriangleIndices
     float4* node = nullptr;        // [2*(2cap-1)] by cluster id, 32 B records: (min.xyz, max.x)(max.y, max.z, bits(left | triangle id), bits(right | NONE))

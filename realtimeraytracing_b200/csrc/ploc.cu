@@ -805,11 +805,20 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     RTR_CHECK(record(b, 0));
 
     // 1. scene box + Morton codes (+ iota indices)
-    RTR_CHECK(rtr_morton_launch(ctx, b->tris, n, b->array_len, b->meshes, b->codes, b->tri_idx, nullptr,
-                                b->bounds12, b->ordered6));
+    if (b->key_bits == 64 && b->codes64_cap < n) {
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (b->codes64) cudaFree(b->codes64);
+        b->codes64 = nullptr; b->codes64_cap = 0;
+        RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b->codes64), (size_t)b->capacity * sizeof(uint64_t)));
+        b->codes64_cap = b->capacity;
+    }
+    RTR_CHECK(rtr_morton_launch(ctx, b->tris, n, b->array_len, b->meshes, b->codes, b->tri_idx,
+                                b->key_bits == 64 ? b->codes64 : nullptr, b->bounds12, b->ordered6));
     RTR_CHECK(record(b, 1));
-    // 2. stable sort of (code, index); Morton codes use bits [0,30)
-    RTR_CHECK(rtr_sort_impl_u32(ctx, b->codes, b->tri_idx, n, 0, 32));
+    // 2. stable sort of (code, index): 30-bit codes in a u32 (the reference), or 63-bit codes in a u64 (21 bits
+    //    per axis, 8 passes; the codes array then holds the unsorted 30-bit codes and is not exported)
+    if (b->key_bits == 64) RTR_CHECK(rtr_sort_impl_u64(ctx, b->codes64, b->tri_idx, n, 0, 63));
+    else RTR_CHECK(rtr_sort_impl_u32(ctx, b->codes, b->tri_idx, n, 0, 32));
     RTR_CHECK(record(b, 2));
     // 3. leaves
     RTR_CUDA(ctx, cudaMemsetAsync(b->tparams, 0, sizeof(TraceParams), ctx->stream));

@@ -170,3 +170,44 @@ def test_build_one_million_matches_oracle(ctx, oracle):
         assert oracle.hash_flat_nodes(bvh.flat_nodes()) == oracle.hash_flat_nodes(oracle.flatten(ob.clusters, ob.left, ob.right))
     finally:
         bvh.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 1025, 30011, 200000])
+def test_build_over_64_bit_keys_matches_oracle(ctx, oracle, n):
+    """rtr_bvh_build64: leaves ordered by 63-bit Morton keys (21 bits per axis), 8 Onesweep passes over
+    (u64, u32) pairs, then the same PLOC + flatten -- bit-exact against oracle orc_bvh_build64."""
+    tris, meshes, L = scenes.soup(n, seed=4000 + n)
+    ob = oracle.bvh_build(tris, meshes, key_bits=64)
+    bvh = capi.Bvh(ctx).build(tris, meshes, key_bits=64)
+    try:
+        codes64 = bvh.morton_codes64()
+        assert np.array_equal(codes64, np.sort(oracle.morton_codes64(tris, meshes), kind="stable"))
+        assert np.array_equal(bvh.triangle_indices(), ob.triangle_indices)
+        clusters, parent, left, right, _ = bvh.clusters()
+        assert np.array_equal(left, ob.left) and np.array_equal(right, ob.right) and np.array_equal(parent, ob.parent)
+        assert np.array_equal(node_words(clusters), node_words(ob.clusters))
+        assert np.array_equal(node_words(bvh.flat_nodes()), node_words(oracle.flatten(ob.clusters, ob.left, ob.right)))
+        # the 64-bit order refines the 32-bit one: code64 >> 33 is the sorted sequence of the reference's codes
+        assert np.array_equal((codes64 >> np.uint64(33)).astype(np.uint32), np.sort(oracle.morton_codes(tris, meshes)))
+        with pytest.raises(capi.RtrError):
+            bvh.morton_codes()
+        # the same object goes back to the reference's keys
+        bvh.build(tris, meshes)
+        ob32 = oracle.bvh_build(tris, meshes)
+        assert np.array_equal(bvh.triangle_indices(), ob32.triangle_indices)
+        assert np.array_equal(node_words(bvh.flat_nodes()), node_words(oracle.flatten(ob32.clusters, ob32.left, ob32.right)))
+    finally:
+        bvh.close()
+
+
+def test_64_bit_keys_trace_like_the_oracle(ctx, oracle):
+    tris, meshes, L = scenes.soup(20000, seed=9)
+    bvh = capi.Bvh(ctx).build(tris, meshes, key_bits=64)
+    try:
+        W, H = 96, 64
+        cam = synth.soup_camera(L, W, H)
+        got = bvh.trace_primary(cam, W, H, W, H)
+        exp = oracle.trace_primary(bvh.flat_nodes(), tris, meshes, cam, W, H, W, H)
+        assert np.array_equal(got.view(np.uint8), exp.view(np.uint8))
+    finally:
+        bvh.close()

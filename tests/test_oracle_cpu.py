@@ -171,3 +171,17 @@ def test_shade_follows_getcolor(oracle):
     assert np.array_equal(plain, np.array([[0, 0, 0, 1], [1, 0, 0.5, 1.125], [0.25, 0.5, 0.75, 2], [0.25, 0.5, 0.75, 2]], np.float32))
     wire = oracle.shade(hits, tris, meshes, materials, wireframe=True)
     assert np.array_equal(wire, np.array([[0, 0, 0, 1], [1, 0, 0.5, 1.125], [0, 0, 0, 1], [0, 0, 0, 1]], np.float32))
+
+
+def test_oracle_build64_refines_the_32_bit_order(oracle):
+    """orc_bvh_build64 is the same builder over 63-bit keys: a valid tree whose leaf order, truncated to 30 bits,
+    is the reference's sorted code sequence."""
+    import scenes
+    tris, meshes, _ = scenes.soup(3000, seed=21)
+    b64 = oracle.bvh_build(tris, meshes, key_bits=64)
+    b32 = oracle.bvh_build(tris, meshes)
+    assert np.array_equal(b64.morton_sorted, b32.morton_sorted)          # code64 >> 33 == code32, both sorted
+    assert sorted(b64.triangle_indices.tolist()) == list(range(tris.size))
+    c64 = oracle.morton_codes64(tris, meshes)
+    assert np.array_equal(c64[b64.triangle_indices], np.sort(c64, kind="stable"))
+    assert int(b64.left[-1]) != 0xFFFFFFFF and b64.trace_merges.sum() == tris.size - 1
