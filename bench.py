@@ -224,7 +224,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if args.reserve_sms <= 0:
-        args.reserve_sms = 8 if world <= 2 else 24   # measured: with fewer channels the broadcast to 7 peers, not the rays, sets the frame time
+        args.reserve_sms = 8 if world <= 2 else 16   # whole SMs are vacated for NCCL (rtr_ctx_reserve_sms); 16 channels move the broadcast to 7 peers in 3.3 ms
     if world > 1:
         if not args.no_pipeline:
             # the broadcast of the next frame's BVH runs beside the rays of the current one on --reserve-sms SMs:
@@ -350,7 +350,9 @@ def main():
         x_rgba_pinned = [rgba_pinned, torch.empty_like(rgba_pinned).pin_memory()] if rank == 0 else None
         x_meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory() if rank == 0 else None
         x_up_done, x_tris_free, x_frame_done, x_img_free, x_img_done = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(5))
-        streams_r = [stream_r, torch.cuda.Stream(device=dev)]
+        # one stream for the rays of all frames: two persistent launches in flight at once would feed the later one's
+        # CTAs, as slots free up, into the SMs the earlier one vacated for NCCL -- where they leave at once
+        streams_r = [stream_r, stream_r]
         stream.synchronize()
         marks = []
 
@@ -405,8 +407,7 @@ def main():
             """stage R, every rank: the rays of its stripes of frame f, then the frame is gathered on rank 0."""
             k = f % NB
             j = f % 2
-            sr = streams_r[j]   # consecutive frames alternate between two streams: the first rays of frame f+1 fill the
-            #                     SMs that the last, longest paths of frame f no longer need
+            sr = streams_r[j]
             ctx.switch_stream(sr.cuda_stream)
             sr.wait_event(ready[k])
             sr.wait_event(x_img_done[j])          # frame f-2 has left this image buffer

@@ -294,6 +294,7 @@ int rtr_ctx_destroy(rtr_ctx* ctx) {
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->sm_table) cudaFree(ctx->sm_table);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RTR_OK;

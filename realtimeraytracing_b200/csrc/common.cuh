@@ -21,6 +21,8 @@ struct rtr_ctx {
     int device = 0;
     int sm_count = RTR_SM_COUNT_B200;
     int reserved_sms = 0;  // SMs the persistent traversal leaves free (rtr_ctx_reserve_sms)
+    uint32_t* sm_table = nullptr;  // 2 x [1 + 1024], per launch: SMs claimed so far, then one state word per %smid
+    uint32_t sm_table_turn = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     uint64_t launches = 0;

@@ -590,7 +590,30 @@ struct JobDesc {
 // from its 64-byte record.
 __global__ void __launch_bounds__(kTraceBlock, RTR_TRACE_MIN_CTAS)
 trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDesc jd,
-                        unsigned long long* __restrict__ rays_traced) {
+                        unsigned long long* __restrict__ rays_traced, uint32_t* __restrict__ sm_table, uint32_t reserve) {
+    // rtr_ctx_reserve_sms: the launch covers every resident slot of the device and the CTAs that land on the first
+    // `reserve` SMs to show up leave at once, so that WHOLE SMs stay empty for the kernels of a concurrent
+    // collective (a smaller grid would still spread over all SMs and leave no room for a 512-thread NCCL CTA).
+    // The first CTA of an SM decides for it; sm_table[0] counts the SMs given away, sm_table[1 + smid] is
+    // 0 unseen / 1 deciding / 2 given away / 3 kept.
+    if (reserve != 0u) {
+        __shared__ uint32_t s_leave;
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            uint32_t* slot = sm_table + 1u + (smid & 1023u);
+            uint32_t state = atomicCAS(slot, 0u, 1u);
+            if (state == 0u) {
+                state = atomicAdd(sm_table, 1u) < reserve ? 2u : 3u;
+                atomicExch(slot, state);
+            } else {
+                while (state == 1u) state = ld_relaxed_u32(slot);
+            }
+            s_leave = state == 2u ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_leave) return;
+    }
     // Traversal stack: the first kSmemStack entries of every thread live in shared memory, laid out
     // [word][depth][thread] so that any mix of depths across a warp is bank-conflict free (bank = lane);
     // a divergent local-memory access would cost one L1 wavefront per lane instead.
@@ -960,12 +983,20 @@ int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const uint32_t need = (jd.total + kTraceBlock - 1) / kTraceBlock;
-    uint32_t grid = (uint32_t)((ctx->sm_count - ctx->reserved_sms) * ctas_per_sm);
-    if (grid > need) grid = need;
+    const uint32_t full = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    uint32_t grid = full, reserve = 0u;
+    if (need <= (uint32_t)((ctx->sm_count - ctx->reserved_sms) * ctas_per_sm)) grid = need;  // small job: room is left anyway
+    else reserve = (uint32_t)ctx->reserved_sms;
     if (grid == 0) return RTR_OK;
+    uint32_t* table = nullptr;
+    if (reserve != 0u) {  // two tables in turn: consecutive launches may run on different streams and overlap
+        if (!ctx->sm_table) RTR_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->sm_table), 2 * 1025 * sizeof(uint32_t)));
+        table = ctx->sm_table + 1025 * (ctx->sm_table_turn++ & 1u);
+        RTR_CUDA(ctx, cudaMemsetAsync(table, 0, 1025 * sizeof(uint32_t), ctx->stream));
+    }
     RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->job_counter, 0, sizeof(uint32_t), ctx->stream));
     trace_persistent_kernel<<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, jd,
-                                                                   reinterpret_cast<unsigned long long*>(rays));
+                                                                   reinterpret_cast<unsigned long long*>(rays), table, reserve);
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;
 }
