@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-stage device times of the rebuild (events inside the library), for parameter sweeps:
-RTR_NVCC_EXTRA="-DRTR_PLOC_PP=4" python profiles/time_build.py --tris 10000000 --force-build"""
+RTR_NVCC_EXTRA="-DRTR_PLOC_WARPS=8" python profiles/time_build.py --tris 10000000 --force-build"""
 import argparse, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
