@@ -98,6 +98,155 @@ struct CameraGPU {
 };
 static_assert(sizeof(CameraGPU) == sizeof(rtr_camera), "CameraGPU layout");
 
+// cr::Camera (srcCommon/scene/camera.hpp:35-106, camera.cpp): produces the CameraGPU the traversal consumes.
+// Host-side scalar code like the reference's; the arithmetic follows GLM 0.9.9.9 operation by operation
+// (lookAtRH matrix_transform.inl:153-173, perspectiveRH_NO matrix_clip_space.inl:249-262, inverse
+// func_matrix.inl:347-405, normalize = v * (1 / sqrt(dot)), dot = (x + y) + z, radians = deg * 0.0174532925...f)
+// so that getGpuData() is bit-identical to the reference's on the same libm
+// (tests/test_camera_cpu.py compares against the reference's own camera.cpp, oracle/_ref/libref_camera.so).
+// Compile without FMA contraction (-ffp-contract=off, or no -march that enables FMA).
+enum CameraMovement { FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN };
+
+class Camera {
+public:
+    bool _Accelerate = false;
+
+    Camera(const float position[3], float aspectRatio, float fov = 45.f, float near_ = 0.1f, float far_ = 200.f,
+           const float* worldUp = nullptr) {
+        _AspectRatio = aspectRatio; _Fov = fov; _Near = near_; _Far = far_;
+        _WorldUp[0] = worldUp ? worldUp[0] : 0.f; _WorldUp[1] = worldUp ? worldUp[1] : 1.f; _WorldUp[2] = worldUp ? worldUp[2] : 0.f;
+        for (int k = 0; k < 3; ++k) _Eye[k] = position[k];
+        updateCameraVectors();
+    }
+
+    CameraGPU getGpuData() const {  // camera.cpp:23-34
+        CameraGPU out;
+        std::memset(&out, 0, sizeof(out));
+        float view[16], proj[16], inv[16];
+        getView(view); getPerspective(proj);
+        std::memcpy(&out._View, view, 64);
+        std::memcpy(&out._Proj, proj, 64);
+        inverse4(view, inv); std::memcpy(&out._InvView, inv, 64);
+        inverse4(proj, inv); std::memcpy(&out._InvProj, inv, 64);
+        const float eye[4] = {_Eye[0], _Eye[1], _Eye[2], 1.f};
+        std::memcpy(&out._Eye, eye, 16);
+        out._PlaneHeight = getPlaneHeight();
+        out._PlaneWidth = out._PlaneHeight * _AspectRatio;  // getPlaneWidth(planeHeight), camera.cpp:64-66
+        out._PlaneNear = _Near;
+        return out;
+    }
+    void getView(float m[16]) const {  // glm::lookAt(_Eye, _Eye + _At, _Up), right-handed
+        const float center[3] = {_Eye[0] + _At[0], _Eye[1] + _At[1], _Eye[2] + _At[2]};
+        float f[3] = {center[0] - _Eye[0], center[1] - _Eye[1], center[2] - _Eye[2]}, s[3], u[3];
+        normalize3(f);
+        cross3(f, _Up, s); normalize3(s);
+        cross3(s, f, u);
+        for (int i = 0; i < 16; ++i) m[i] = 0.f;
+        m[15] = 1.f;
+        m[0] = s[0]; m[4] = s[1]; m[8] = s[2];
+        m[1] = u[0]; m[5] = u[1]; m[9] = u[2];
+        m[2] = -f[0]; m[6] = -f[1]; m[10] = -f[2];
+        m[12] = -dot3(s, _Eye); m[13] = -dot3(u, _Eye); m[14] = dot3(f, _Eye);
+    }
+    void getPerspective(float m[16]) const {  // glm::perspective(radians(_Fov), aspect, near, far), RH, depth -1..1
+        const float fovy = radians(_Fov);
+        const float tanHalfFovy = std::tan(fovy / 2.f);
+        for (int i = 0; i < 16; ++i) m[i] = 0.f;
+        m[0] = 1.f / (_AspectRatio * tanHalfFovy);
+        m[5] = 1.f / tanHalfFovy;
+        m[10] = -(_Far + _Near) / (_Far - _Near);
+        m[11] = -1.f;
+        m[14] = -(2.f * _Far * _Near) / (_Far - _Near);
+    }
+    float getPlaneHeight() const { return 2.f * _Near * std::tan(0.5f * radians(_Fov)); }  // camera.cpp:52-54
+
+    void processKeyboard(CameraMovement direction, float deltaTime) {  // camera.cpp:68-93
+        float velocity = 20.f * deltaTime;
+        if (_Accelerate) velocity *= 5.f;
+        const float* v = direction <= BACKWARD ? _At : (direction <= RIGHT ? _Right : _WorldUp);
+        const bool minus = direction == FORWARD || direction == LEFT || direction == DOWN;
+        for (int k = 0; k < 3; ++k) { const float d = v[k] * velocity; _Eye[k] = minus ? _Eye[k] - d : _Eye[k] + d; }
+    }
+    void ProcessMouseMovement(float xoffset, float yoffset, bool constrainPitch = true) {  // camera.cpp:95-109
+        xoffset *= 0.1f; yoffset *= 0.1f;
+        _Yaw += xoffset; _Pitch += yoffset;
+        if (constrainPitch) { if (_Pitch > 89.0f) _Pitch = 89.0f; if (_Pitch < -89.0f) _Pitch = -89.0f; }
+        updateCameraVectors();
+    }
+    const float* getPosition() const { return _Eye; }
+    const float* getAt() const { return _At; }
+
+private:
+    float _Eye[3], _At[3], _WorldUp[3], _Up[3], _Right[3];
+    float _Fov = 0.f, _AspectRatio = 0.f, _Near = 0.f, _Far = 0.f;
+    float _Yaw = -90.f, _Pitch = 0.f;
+
+    static float radians(float deg) { return deg * 0.01745329251994329576923690768489f; }
+    static float dot3(const float a[3], const float b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+    static void cross3(const float x[3], const float y[3], float o[3]) {
+        o[0] = x[1] * y[2] - y[1] * x[2]; o[1] = x[2] * y[0] - y[2] * x[0]; o[2] = x[0] * y[1] - y[0] * x[1];
+    }
+    static void normalize3(float v[3]) {
+        const float inv = 1.f / std::sqrt(dot3(v, v));
+        v[0] *= inv; v[1] *= inv; v[2] *= inv;
+    }
+    void updateCameraVectors() {  // camera.cpp:111-123: unqualified cos/sin on a float are the double functions
+        const double yaw = radians(_Yaw), pitch = radians(_Pitch);
+        float front[3];
+        front[0] = (float)(std::cos(yaw) * std::cos(pitch));
+        front[1] = (float)std::sin(pitch);
+        front[2] = (float)(std::sin(yaw) * std::cos(pitch));
+        normalize3(front);
+        for (int k = 0; k < 3; ++k) _At[k] = front[k];
+        cross3(_At, _WorldUp, _Right); normalize3(_Right);
+        cross3(_Right, _At, _Up); normalize3(_Up);
+    }
+    // glm::inverse(mat4), func_matrix.inl:347-405; m[c * 4 + r]
+    static void inverse4(const float m[16], float out[16]) {
+#define RTR_M(c, r) m[(c) * 4 + (r)]
+        const float Coef00 = RTR_M(2, 2) * RTR_M(3, 3) - RTR_M(3, 2) * RTR_M(2, 3);
+        const float Coef02 = RTR_M(1, 2) * RTR_M(3, 3) - RTR_M(3, 2) * RTR_M(1, 3);
+        const float Coef03 = RTR_M(1, 2) * RTR_M(2, 3) - RTR_M(2, 2) * RTR_M(1, 3);
+        const float Coef04 = RTR_M(2, 1) * RTR_M(3, 3) - RTR_M(3, 1) * RTR_M(2, 3);
+        const float Coef06 = RTR_M(1, 1) * RTR_M(3, 3) - RTR_M(3, 1) * RTR_M(1, 3);
+        const float Coef07 = RTR_M(1, 1) * RTR_M(2, 3) - RTR_M(2, 1) * RTR_M(1, 3);
+        const float Coef08 = RTR_M(2, 1) * RTR_M(3, 2) - RTR_M(3, 1) * RTR_M(2, 2);
+        const float Coef10 = RTR_M(1, 1) * RTR_M(3, 2) - RTR_M(3, 1) * RTR_M(1, 2);
+        const float Coef11 = RTR_M(1, 1) * RTR_M(2, 2) - RTR_M(2, 1) * RTR_M(1, 2);
+        const float Coef12 = RTR_M(2, 0) * RTR_M(3, 3) - RTR_M(3, 0) * RTR_M(2, 3);
+        const float Coef14 = RTR_M(1, 0) * RTR_M(3, 3) - RTR_M(3, 0) * RTR_M(1, 3);
+        const float Coef15 = RTR_M(1, 0) * RTR_M(2, 3) - RTR_M(2, 0) * RTR_M(1, 3);
+        const float Coef16 = RTR_M(2, 0) * RTR_M(3, 2) - RTR_M(3, 0) * RTR_M(2, 2);
+        const float Coef18 = RTR_M(1, 0) * RTR_M(3, 2) - RTR_M(3, 0) * RTR_M(1, 2);
+        const float Coef19 = RTR_M(1, 0) * RTR_M(2, 2) - RTR_M(2, 0) * RTR_M(1, 2);
+        const float Coef20 = RTR_M(2, 0) * RTR_M(3, 1) - RTR_M(3, 0) * RTR_M(2, 1);
+        const float Coef22 = RTR_M(1, 0) * RTR_M(3, 1) - RTR_M(3, 0) * RTR_M(1, 1);
+        const float Coef23 = RTR_M(1, 0) * RTR_M(2, 1) - RTR_M(2, 0) * RTR_M(1, 1);
+        const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+        const float Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+        const float Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+        const float Vec0[4] = {RTR_M(1, 0), RTR_M(0, 0), RTR_M(0, 0), RTR_M(0, 0)};
+        const float Vec1[4] = {RTR_M(1, 1), RTR_M(0, 1), RTR_M(0, 1), RTR_M(0, 1)};
+        const float Vec2[4] = {RTR_M(1, 2), RTR_M(0, 2), RTR_M(0, 2), RTR_M(0, 2)};
+        const float Vec3[4] = {RTR_M(1, 3), RTR_M(0, 3), RTR_M(0, 3), RTR_M(0, 3)};
+        const float SignA[4] = {+1.f, -1.f, +1.f, -1.f}, SignB[4] = {-1.f, +1.f, -1.f, +1.f};
+        float Inverse[16];
+        for (int k = 0; k < 4; ++k) {
+            const float Inv0 = (Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k];
+            const float Inv1 = (Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k];
+            const float Inv2 = (Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k];
+            const float Inv3 = (Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k];
+            Inverse[0 * 4 + k] = Inv0 * SignA[k]; Inverse[1 * 4 + k] = Inv1 * SignB[k];
+            Inverse[2 * 4 + k] = Inv2 * SignA[k]; Inverse[3 * 4 + k] = Inv3 * SignB[k];
+        }
+        const float Dot0[4] = {RTR_M(0, 0) * Inverse[0], RTR_M(0, 1) * Inverse[4], RTR_M(0, 2) * Inverse[8], RTR_M(0, 3) * Inverse[12]};
+        const float Dot1 = (Dot0[0] + Dot0[1]) + (Dot0[2] + Dot0[3]);
+        const float OneOverDeterminant = 1.f / Dot1;
+        for (int i = 0; i < 16; ++i) out[i] = Inverse[i] * OneOverDeterminant;
+#undef RTR_M
+    }
+};
+
 // raytracer.glsl:36-40
 struct Hit {
     vec4 _Coords;  // (b0, b1, b2, t)

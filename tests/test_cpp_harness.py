@@ -19,7 +19,23 @@ def executables():
     env.pop("CXX", None)
     out = subprocess.run(["make", "-C", HARNESS, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    return {t: os.path.join(HARNESS, "build", t) for t in TESTS}
+    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera"]}
+
+
+def test_camera_mirror_is_bit_identical_to_the_reference(executables):
+    """cr::Camera of include/rtr_scene.hpp vs the reference's own camera.cpp (oracle/_ref/libref_camera.so, built from
+    /root/reference by oracle/Makefile): 2001 cameras incl. replayed mouse / keyboard input, CameraGPU byte for byte."""
+    from oracle import bindings as ob
+    try:
+        ob.build_reference()
+    except Exception:
+        pass  # no reference tree here: the prebuilt library travels with the repo snapshot
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_camera.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libref_camera.so not built (needs /root/reference)")
+    r = subprocess.run([executables["testCamera"], lib], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout
 
 
 def test_cpp_harness_compiles_and_links(executables):
