@@ -267,21 +267,31 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* c
                            float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
 /* ---- shading: getColor + main of raytracer.glsl (:159-179, :299-331), the reference's rgba32f frame from the hit
- * records of rtr_trace_primary.  value = (0,0,0,1); a hit adds the colour of the material of the triangle's model;
- * with RTR_SHADE_WIREFRAME a hit whose barycentric falls below WIREFRAME_LINE_WIDTH = 0.02 (:71, :170-178) is
- * (0,0,0,1).  The BVH-depth overlay (uIsBVHDisplayed) is not reproduced.  The material id is the host's
- * meshes[model]._MaterialId (the shader reads it at stride 80 where the host wrote stride 68, SURVEY Q7: the same
- * value for model 0, i.e. for every single-model scene). */
+ * records of rtr_trace_primary.  value = (0,0,0,1) -- or, with RTR_SHADE_BVH (uIsBVHDisplayed), the pixel's colour
+ * from rtr_bvh_depth_overlay; a hit adds the colour of the material of the triangle's model; with
+ * RTR_SHADE_WIREFRAME a hit whose barycentric falls below WIREFRAME_LINE_WIDTH = 0.02 (:71, :170-178) is (0,0,0,1).
+ * The material id is the host's meshes[model]._MaterialId (the shader reads it at stride 80 where the host wrote
+ * stride 68, SURVEY Q7: the same value for model 0, i.e. for every single-model scene). */
 /* cr::MaterialGPU, srcCommon/scene/pbr/material.hpp:9-11 */
 typedef struct rtr_material {
     float color[4];
 } rtr_material;
 #define RTR_SHADE_WIREFRAME 1u
+#define RTR_SHADE_BVH 2u
 int rtr_shade(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle* triangles, uint32_t nb_triangles,
               const rtr_mesh* meshes, uint32_t nb_meshes, const rtr_material* materials, uint32_t nb_materials,
-              uint32_t flags, float* rgba_out /* [n*4] */);
+              uint32_t flags, const float* bvh_rgba /* [n*4], only read with RTR_SHADE_BVH */, float* rgba_out /* [n*4] */);
 int rtr_shade_dev(rtr_ctx* ctx, const rtr_hit* hits_dev, uint64_t n, const rtr_triangle* triangles_dev,
-                  const rtr_mesh* meshes_dev, const rtr_material* materials_dev, uint32_t flags, float* rgba_dev);
+                  const rtr_mesh* meshes_dev, const rtr_material* materials_dev, uint32_t flags,
+                  const float* bvh_rgba_dev, float* rgba_dev);
+/* the BVH-depth overlay of the shader (uDepthDisplayBVH, raytracer.glsl:269-275 with intersectBVH's edge code 2,
+ * :222-233): per pixel the colour of the node at depth `display_depth` (root = 0) that getClosestHitBVH visits last
+ * among those the primary ray intersects -- (0.5,0,0.5,0.1), or (0.7,0,0.7,0.1) where the ray enters the box near one
+ * of its edges; (0,0,0,0) where there is none.  out: 4 floats per pixel. */
+int rtr_bvh_depth_overlay(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera, uint32_t width, uint32_t height,
+                          uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba_out);
+int rtr_bvh_depth_overlay_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera, uint32_t width, uint32_t height,
+                              uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba_dev);
 
 /* weighted dealing: rank r owns stripes_of_rank[r] stripes (host array of nranks entries, at most
  * RTR_MAX_STRIPES_PER_RANK each, 255 in total; 0 = renders nothing, e.g. a rank busy rebuilding); block b belongs to

@@ -111,7 +111,8 @@ class Oracle:
         L.orc_trace_primary.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, vp, i32]
         L.orc_trace_rays.argtypes = [vp, vp, vp, vp, u64, vp, i32]
         L.orc_render.argtypes = [vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, vp, vp, vp, i32]
-        L.orc_shade.argtypes = [vp, u64, vp, vp, vp, i32, vp]
+        L.orc_shade.argtypes = [vp, u64, vp, vp, vp, i32, vp, vp]
+        L.orc_depth_overlay.argtypes = [vp, vp, u32, u32, u32, u32, i32, vp]
         L.orc_bounce_ray.argtypes = [vp, vp, vp, vp, vp]
         L.orc_bounce_ray.restype = i32
         L.orc_shadow_ray.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -278,12 +279,22 @@ class Oracle:
                             row0, row1, bounces, 1 if shadow else 0, _p(light), _p(rgba), _p(hits), _p(nrays), threads)
         return rgba, hits, int(nrays[0])
 
-    def shade(self, hits, tris, meshes, materials, wireframe=False):
-        """getColor of raytracer.glsl (no BVH overlay): rgba [n, 4]."""
+    def shade(self, hits, tris, meshes, materials, wireframe=False, bvh_rgba=None):
+        """getColor of raytracer.glsl: rgba [n, 4]; bvh_rgba = depth_overlay(...) when the BVH is displayed."""
         hits = np.ascontiguousarray(hits)
         materials = np.ascontiguousarray(materials, dtype=np.float32)
         out = np.zeros((hits.size, 4), dtype=np.float32)
-        self.lib.orc_shade(_p(hits), hits.size, _p(tris), _p(meshes), _p(materials), 1 if wireframe else 0, _p(out))
+        b = None if bvh_rgba is None else np.ascontiguousarray(bvh_rgba, dtype=np.float32)
+        self.lib.orc_shade(_p(hits), hits.size, _p(tris), _p(meshes), _p(materials), 1 if wireframe else 0,
+                           None if b is None else _p(b), _p(out))
+        return out
+
+    def depth_overlay(self, flat, cam, width, height, depth, denom_w=None, denom_h=None):
+        """bvhColor of the shader's traversal per pixel, [height*width, 4]."""
+        out = np.zeros((width * height, 4), dtype=np.float32)
+        self.lib.orc_depth_overlay(_p(np.ascontiguousarray(flat)), _p(cam), width, height,
+                                   width if denom_w is None else denom_w, height if denom_h is None else denom_h,
+                                   depth, _p(out))
         return out
 
     def num_threads(self):

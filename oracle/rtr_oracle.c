@@ -802,9 +802,10 @@ void orc_render(const orc_node* flat, const orc_triangle* tris,
 
 /* raytracer.glsl:159-179 (getColor) + :299-331 (main), uIsBVHDisplayed == false */
 void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const orc_mesh* meshes,
-               const float* materials, int wireframe, float* rgba_out) {
+               const float* materials, int wireframe, const float* bvh_rgba, float* rgba_out) {
     for (uint64_t i = 0; i < n; ++i) {
         float c[4] = {0.f, 0.f, 0.f, 1.f};                         /* :300 */
+        if (bvh_rgba) memcpy(c, bvh_rgba + 4 * i, 16);             /* :161-163, uIsBVHDisplayed */
         const orc_hit* h = &hits[i];
         if (h->did_hit != 0) {                                      /* :165 */
             const uint32_t model = tris[h->triangle_id].model_id;           /* :166 */
@@ -817,4 +818,74 @@ void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const 
         }
         for (int k = 0; k < 4; ++k) rgba_out[4 * i + k] = c[k];    /* :330 */
     }
+}
+
+/* raytracer.glsl:182-237 with its return code 2: the ray enters the box within BVH_LINE_WIDTH / (depth + 1) of two of
+ * its three slab pairs (a box edge, drawn as a line by the overlay) */
+static uint32_t intersect_box_edge(const orc_ray* ray, const orc_node* node, int display_depth) {
+    float tMin, tMax;
+    float ix = 1.0f / ray->direction[0];
+    float tx1 = (node->bmin[0] - ray->origin[0]) * ix;
+    float tx2 = (node->bmax[0] - ray->origin[0]) * ix;
+    tMin = fminf(tx1, tx2);
+    tMax = fmaxf(tx1, tx2);
+    if (tMax < 0.f || tMin > tMax) return 0;
+    float iy = 1.0f / ray->direction[1];
+    float ty1 = (node->bmin[1] - ray->origin[1]) * iy;
+    float ty2 = (node->bmax[1] - ray->origin[1]) * iy;
+    tMin = fmaxf(tMin, fminf(ty1, ty2));
+    tMax = fminf(tMax, fmaxf(ty1, ty2));
+    if (tMax < 0.f || tMin > tMax) return 0;
+    float iz = 1.0f / ray->direction[2];
+    float tz1 = (node->bmin[2] - ray->origin[2]) * iz;
+    float tz2 = (node->bmax[2] - ray->origin[2]) * iz;
+    tMin = fmaxf(tMin, fminf(tz1, tz2));
+    tMax = fminf(tMax, fmaxf(tz1, tz2));
+    if (tMax >= 0.f && tMin <= tMax) {
+        const float threshold = 0.05f / ((float)display_depth + 1.f);      /* :72, :223 */
+        float e[3];
+        for (int k = 0; k < 3; ++k) e[k] = ray->origin[k] + ray->direction[k] * tMin;  /* :224 */
+        const int cx = fabsf(e[0] - node->bmin[0]) < threshold || fabsf(e[0] - node->bmax[0]) < threshold;
+        const int cy = fabsf(e[1] - node->bmin[1]) < threshold || fabsf(e[1] - node->bmax[1]) < threshold;
+        const int cz = fabsf(e[2] - node->bmin[2]) < threshold || fabsf(e[2] - node->bmax[2]) < threshold;
+        if ((cx && cy) || (cx && cz) || (cy && cz)) return 2;
+        return 1;
+    }
+    return 0;
+}
+
+/* The bvhColor of getClosestHitBVH (raytracer.glsl:246-295), the shader's loop to the letter: LIFO stack with a depth
+ * stack, Left pushed before Right, no pruning; every intersected node at depth == display_depth overwrites the
+ * colour (:269-275), so the LAST one visited decides.  out: 4 floats per pixel, (0,0,0,0) where nothing at that depth
+ * is hit (:321). */
+void orc_depth_overlay(const orc_node* flat, const orc_camera* cam, uint32_t width, uint32_t height,
+                       uint32_t denom_w, uint32_t denom_h, int display_depth, float* out) {
+    static const float kBox[4] = {0.5f, 0.f, 0.5f, 0.1f}, kLine[4] = {0.7f, 0.f, 0.7f, 0.1f};  /* :69-70 */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (int64_t y = 0; y < (int64_t)height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            float* c = out + 4 * ((size_t)y * width + x);
+            c[0] = c[1] = c[2] = c[3] = 0.f;
+            if (x >= denom_w || (uint32_t)y >= denom_h) continue;
+            orc_ray ray;
+            orc_get_ray(cam, x, (uint32_t)y, denom_w, denom_h, &ray);
+            uint32_t stack[1024], depth[1024];
+            int sp = 0;
+            stack[sp] = 0; depth[sp] = 0; sp++;
+            while (sp > 0) {
+                --sp;
+                const uint32_t idx = stack[sp], d = depth[sp];
+                const orc_node* nd = &flat[idx];
+                const uint32_t code = intersect_box_edge(&ray, nd, display_depth);
+                if (code != 0) {
+                    if ((int)d == display_depth) memcpy(c, code == 2 ? kLine : kBox, 16);
+                    if (!(nd->left == 0 && nd->right == 0) && sp + 2 <= 1024) {
+                        stack[sp] = nd->left; depth[sp] = d + 1; sp++;
+                        stack[sp] = nd->right; depth[sp] = d + 1; sp++;
+                    }
+                }
+            }
+        }
 }

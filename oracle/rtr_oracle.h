@@ -181,7 +181,12 @@ void orc_render(const orc_node* flat, const orc_triangle* tris,
  * The material id is the host's meshes[model]._MaterialId (the shader reads it at stride 80 instead of the host's 68,
  * Q7: identical for model 0, i.e. for every single-model scene). */
 void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const orc_mesh* meshes,
-               const float* materials, int wireframe, float* rgba_out);
+               const float* materials, int wireframe, const float* bvh_rgba /* nullable: uIsBVHDisplayed */,
+               float* rgba_out);
+/* the bvhColor of getClosestHitBVH (raytracer.glsl:246-295, :222-233): colour of the last visited intersected node at
+ * depth display_depth -- box (0.5,0,0.5,0.1), or line (0.7,0,0.7,0.1) where the ray enters near a box edge */
+void orc_depth_overlay(const orc_node* flat, const orc_camera* cam, uint32_t width, uint32_t height,
+                       uint32_t denom_w, uint32_t denom_h, int display_depth, float* out);
 /* deterministic secondary-ray definitions (shared with the CUDA path) */
 int orc_bounce_ray(const orc_ray* in, const orc_hit* hit, const orc_triangle* tris,
                    const orc_mesh* meshes, orc_ray* out);

@@ -13,6 +13,7 @@ ERROR_NAMES = {0: "RTR_OK", -1: "RTR_E_INVALID", -2: "RTR_E_CUDA", -3: "RTR_E_NO
                -5: "RTR_E_UNSUPPORTED", -6: "RTR_E_STATE", -7: "RTR_E_COMM"}
 TRACE_DEFAULT = 0
 SHADE_WIREFRAME = 1  # RTR_SHADE_WIREFRAME
+SHADE_BVH = 2        # RTR_SHADE_BVH
 TRACE_REFERENCE_ORDER = 1
 NCCL_UNIQUE_ID_BYTES = 128
 
@@ -37,6 +38,7 @@ SYMBOLS = [
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
     "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
     "rtr_bvh_build64", "rtr_bvh_build64_dev", "rtr_bvh_morton_codes64",
+    "rtr_bvh_depth_overlay", "rtr_bvh_depth_overlay_dev",
 ]
 
 
@@ -140,8 +142,10 @@ def load_library():
     L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
     L.rtr_gather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp, i32]
-    L.rtr_shade.argtypes = [vp, vp, C.c_uint64, vp, u32, vp, u32, vp, u32, u32, vp]
-    L.rtr_shade_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u32, vp]
+    L.rtr_shade.argtypes = [vp, vp, C.c_uint64, vp, u32, vp, u32, vp, u32, u32, vp, vp]
+    L.rtr_shade_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u32, vp, vp]
+    L.rtr_bvh_depth_overlay.argtypes = [vp, vp, vp, u32, u32, u32, u32, i32, vp]
+    L.rtr_bvh_depth_overlay_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, i32, vp]
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     _lib = L
@@ -352,19 +356,23 @@ class Context:
     def comm_destroy(self):
         self.check(self.lib.rtr_comm_destroy(self.handle))
 
-    def shade(self, hits, tris, meshes, materials, wireframe: bool = False) -> np.ndarray:
-        """getColor of raytracer.glsl (:159-179) on hit records: the reference's rgba32f pixels, [n, 4]."""
+    def shade(self, hits, tris, meshes, materials, wireframe: bool = False, bvh_rgba=None) -> np.ndarray:
+        """getColor of raytracer.glsl (:159-179) on hit records: the reference's rgba32f pixels, [n, 4].
+        bvh_rgba = Bvh.depth_overlay(...) when the BVH is displayed (uIsBVHDisplayed)."""
         hits = _as(hits, HIT); tris = _as(tris, TRIANGLE); meshes = _as(meshes, MESH)
         materials = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 4)
         out = np.zeros((hits.size, 4), dtype=np.float32)
+        flags = (SHADE_WIREFRAME if wireframe else 0) | (SHADE_BVH if bvh_rgba is not None else 0)
+        b = None if bvh_rgba is None else np.ascontiguousarray(bvh_rgba, dtype=np.float32)
         self.check(self.lib.rtr_shade(self.handle, _ptr(hits), hits.size, _ptr(tris), tris.size, _ptr(meshes), meshes.size,
-                                      _ptr(materials), materials.shape[0], SHADE_WIREFRAME if wireframe else 0, _ptr(out)))
+                                      _ptr(materials), materials.shape[0], flags, _ptr(b), _ptr(out)))
         return out
 
     def shade_dev(self, hits_dev: int, n: int, tris_dev: int, meshes_dev: int, materials_dev: int, rgba_dev: int,
-                  wireframe: bool = False):
+                  wireframe: bool = False, bvh_rgba_dev=None):
+        flags = (SHADE_WIREFRAME if wireframe else 0) | (SHADE_BVH if bvh_rgba_dev else 0)
         self.check(self.lib.rtr_shade_dev(self.handle, C.c_void_p(hits_dev), n, C.c_void_p(tris_dev), C.c_void_p(meshes_dev),
-                                          C.c_void_p(materials_dev), SHADE_WIREFRAME if wireframe else 0, C.c_void_p(rgba_dev)))
+                                          C.c_void_p(materials_dev), flags, _ptr(bvh_rgba_dev), C.c_void_p(rgba_dev)))
 
     def gather_stripes(self, image_dev: int, width: int, height: int, bytes_per_pixel: int, rows_per_block: int,
                        stripes_of_rank, root: int = 0):
@@ -470,6 +478,14 @@ class Bvh:
     def morton_codes(self) -> np.ndarray:
         out = np.zeros(self.nb_triangles, dtype=np.uint32)
         self.ctx.check(self.lib.rtr_bvh_morton_codes(self.handle, _ptr(out)))
+        return out
+
+    def depth_overlay(self, camera, width, height, depth: int, denom_w=0, denom_h=0) -> np.ndarray:
+        """bvhColor of the shader's traversal (uDepthDisplayBVH = depth) per pixel, [height*width, 4]."""
+        camera = _as(camera, CAMERA)
+        out = np.zeros((width * height, 4), dtype=np.float32)
+        self.ctx.check(self.lib.rtr_bvh_depth_overlay(self.ctx.handle, self.handle, _ptr(camera), width, height,
+                                                      denom_w, denom_h, depth, _ptr(out)))
         return out
 
     def morton_codes64(self) -> np.ndarray:

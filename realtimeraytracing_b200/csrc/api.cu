@@ -859,20 +859,23 @@ int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam
 }
 
 int rtr_shade_dev(rtr_ctx* ctx, const rtr_hit* hits_dev, uint64_t n, const rtr_triangle* tris_dev, const rtr_mesh* meshes_dev,
-                  const rtr_material* materials_dev, uint32_t flags, float* rgba_dev) {
+                  const rtr_material* materials_dev, uint32_t flags, const float* bvh_rgba_dev, float* rgba_dev) {
     if (!ctx) return RTR_E_INVALID;
     if (n && (!hits_dev || !tris_dev || !meshes_dev || !materials_dev || !rgba_dev))
         return rtr_set_error(ctx, RTR_E_INVALID, "shade: NULL argument");
-    return rtr_shade_launch(ctx, hits_dev, n, tris_dev, meshes_dev, materials_dev, flags, rgba_dev);
+    if (n && (flags & RTR_SHADE_BVH) && !bvh_rgba_dev) return rtr_set_error(ctx, RTR_E_INVALID, "shade: RTR_SHADE_BVH without overlay colours");
+    return rtr_shade_launch(ctx, hits_dev, n, tris_dev, meshes_dev, materials_dev, flags, bvh_rgba_dev, rgba_dev);
 }
 
 int rtr_shade(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle* tris, uint32_t nb_triangles,
               const rtr_mesh* meshes, uint32_t nb_meshes, const rtr_material* materials, uint32_t nb_materials,
-              uint32_t flags, float* rgba_out) {
+              uint32_t flags, const float* bvh_rgba, float* rgba_out) {
     if (!ctx) return RTR_E_INVALID;
     if (n == 0) return RTR_OK;
     if (!hits || !tris || !meshes || !materials || !rgba_out || !nb_triangles || !nb_meshes || !nb_materials)
         return rtr_set_error(ctx, RTR_E_INVALID, "shade: NULL or empty argument");
+    const bool overlay = (flags & RTR_SHADE_BVH) != 0;
+    if (overlay && !bvh_rgba) return rtr_set_error(ctx, RTR_E_INVALID, "shade: RTR_SHADE_BVH without overlay colours");
     // the records index triangles, models and materials: reject what the shader would read out of bounds
     for (uint64_t i = 0; i < n; ++i)
         if (hits[i].did_hit && hits[i].triangle_id >= nb_triangles)
@@ -885,19 +888,49 @@ int rtr_shade(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle*
     const size_t hb = n * sizeof(rtr_hit), tb = (size_t)nb_triangles * sizeof(rtr_triangle), mb = (size_t)nb_meshes * sizeof(rtr_mesh);
     const size_t ab = (size_t)nb_materials * sizeof(rtr_material), cb = n * 16;
     Staging st;
-    RTR_CHECK(staging_begin(ctx, hb + tb + mb + ab + cb + 2048, 0, &st));
+    RTR_CHECK(staging_begin(ctx, hb + tb + mb + ab + 2 * cb + 2048, 0, &st));
     rtr_hit* d_hits = static_cast<rtr_hit*>(staging_take(&st, hb));
     rtr_triangle* d_tris = static_cast<rtr_triangle*>(staging_take(&st, tb));
     rtr_mesh* d_meshes = static_cast<rtr_mesh*>(staging_take(&st, mb));
     rtr_material* d_mat = static_cast<rtr_material*>(staging_take(&st, ab));
     float* d_rgba = static_cast<float*>(staging_take(&st, cb));
+    float* d_bvh = static_cast<float*>(staging_take(&st, cb));
     auto body = [&]() -> int {
         RTR_CUDA(ctx, cudaMemcpyAsync(d_hits, hits, hb, cudaMemcpyHostToDevice, ctx->stream));
         RTR_CUDA(ctx, cudaMemcpyAsync(d_tris, tris, tb, cudaMemcpyHostToDevice, ctx->stream));
         RTR_CUDA(ctx, cudaMemcpyAsync(d_meshes, meshes, mb, cudaMemcpyHostToDevice, ctx->stream));
         RTR_CUDA(ctx, cudaMemcpyAsync(d_mat, materials, ab, cudaMemcpyHostToDevice, ctx->stream));
-        RTR_CHECK(rtr_shade_launch(ctx, d_hits, n, d_tris, d_meshes, d_mat, flags, d_rgba));
+        if (overlay) RTR_CUDA(ctx, cudaMemcpyAsync(d_bvh, bvh_rgba, cb, cudaMemcpyHostToDevice, ctx->stream));
+        RTR_CHECK(rtr_shade_launch(ctx, d_hits, n, d_tris, d_meshes, d_mat, flags, overlay ? d_bvh : nullptr, d_rgba));
         RTR_CUDA(ctx, cudaMemcpyAsync(rgba_out, d_rgba, cb, cudaMemcpyDeviceToHost, ctx->stream));
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RTR_OK;
+    };
+    const int r = body();
+    staging_end(&st);
+    return r;
+}
+
+int rtr_bvh_depth_overlay_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
+                              uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba_dev) {
+    RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, RTR_TRACE_REFERENCE_ORDER));  // walks the 48-byte nodes
+    if (!bvh_rgba_dev) return rtr_set_error(ctx, RTR_E_INVALID, "depth_overlay: NULL output");
+    return rtr_depth_overlay_launch(ctx, b, *cam, width, height, denom_w, denom_h, display_depth, bvh_rgba_dev);
+}
+
+int rtr_bvh_depth_overlay(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
+                          uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba_out) {
+    RTR_CHECK(trace_args_ok(ctx, b, cam));
+    RTR_CHECK(order_ok(ctx, b, RTR_TRACE_REFERENCE_ORDER));
+    if (!bvh_rgba_out) return rtr_set_error(ctx, RTR_E_INVALID, "depth_overlay: NULL output");
+    const size_t cb = (size_t)width * height * 16;
+    Staging st;
+    RTR_CHECK(staging_begin(ctx, cb + 512, 0, &st));
+    float* d_out = static_cast<float*>(staging_take(&st, cb));
+    auto body = [&]() -> int {
+        RTR_CHECK(rtr_depth_overlay_launch(ctx, b, *cam, width, height, denom_w, denom_h, display_depth, d_out));
+        RTR_CUDA(ctx, cudaMemcpyAsync(bvh_rgba_out, d_out, cb, cudaMemcpyDeviceToHost, ctx->stream));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return RTR_OK;
     };

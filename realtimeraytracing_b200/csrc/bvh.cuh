@@ -187,4 +187,6 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
                       uint32_t rows_per_block = 0, uint32_t total_stripes = 1, uint32_t nb_stripes = 1,
                       const uint8_t* stripe_offsets = nullptr);
 int rtr_shade_launch(rtr_ctx* ctx, const rtr_hit* hits_dev, uint64_t n, const rtr_triangle* tris_dev, const rtr_mesh* meshes_dev,
-                     const rtr_material* materials_dev, uint32_t flags, float* rgba_dev);
+                     const rtr_material* materials_dev, uint32_t flags, const float* bvh_rgba_dev, float* rgba_dev);
+int rtr_depth_overlay_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                             uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba_dev);

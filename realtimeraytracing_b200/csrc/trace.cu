@@ -945,16 +945,74 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     if (rays_traced && lane == 0u && traced) atomicAdd(rays_traced, (unsigned long long)traced);
 }
 
-// getColor + main of raytracer.glsl (:159-179, :299-331), BVH overlay off: the reference's frame from hit records
+// intersectBVH of raytracer.glsl:182-237 with its return code 2 (the ray enters within BVH_LINE_WIDTH / (depth + 1) of
+// two of the three slab pairs: a box edge)
+__device__ __forceinline__ uint32_t intersect_box_edge(const Ray& r, const float4 lo, const float4 hi, float threshold) {
+    float t_entry;
+    if (!intersect_box(r, lo, hi, t_entry)) return 0u;
+    const float ex = __fadd_rn(r.ox, __fmul_rn(r.dx, t_entry));
+    const float ey = __fadd_rn(r.oy, __fmul_rn(r.dy, t_entry));
+    const float ez = __fadd_rn(r.oz, __fmul_rn(r.dz, t_entry));
+    const bool cx = fabsf(__fsub_rn(ex, lo.x)) < threshold || fabsf(__fsub_rn(ex, hi.x)) < threshold;
+    const bool cy = fabsf(__fsub_rn(ey, lo.y)) < threshold || fabsf(__fsub_rn(ey, hi.y)) < threshold;
+    const bool cz = fabsf(__fsub_rn(ez, lo.z)) < threshold || fabsf(__fsub_rn(ez, hi.z)) < threshold;
+    return ((cx && cy) || (cx && cz) || (cy && cz)) ? 2u : 1u;
+}
+
+// The bvhColor of getClosestHitBVH (raytracer.glsl:246-295): every intersected node at depth == display_depth
+// overwrites the colour, so the node the shader visits LAST decides.  The shader pops the right child first and does
+// not prune, and a node is only reached through intersected ancestors (which every intersected node has: merged
+// boxes are unions and the slab test is monotone): the last one visited is the intersected depth-D node with the
+// smallest flat index -- the first one a LEFT-first walk down to depth D meets.  One thread per pixel.
+__global__ void __launch_bounds__(kTraceBlock)
+depth_overlay_kernel(const rtr_node* __restrict__ nodes, const rtr_camera cam, uint32_t width, uint32_t height,
+                     uint32_t denom_w, uint32_t denom_h, int display_depth, float4* __restrict__ out) {
+    uint32_t x, y;
+    if (!pixel_of_thread(width, height, x, y)) return;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < denom_w && y < denom_h && display_depth >= 0 && display_depth < kStack) {
+        const Ray r = camera_ray(cam, x, y, denom_w, denom_h);
+        const float threshold = __fdiv_rn(0.05f, __fadd_rn((float)display_depth, 1.f));
+        uint32_t stack[kStack];   // right siblings still to try ...
+        uint8_t sdepth[kStack];   // ... and their depth (< kStack)
+        int sp = 0;
+        uint32_t cur = 0u, depth = 0u;
+        while (true) {
+            const NodeRec nd = load_node(nodes, cur);
+            const uint32_t code = intersect_box_edge(r, nd.lo, nd.hi, threshold);
+            bool descend = false;
+            if (code != 0u) {
+                if ((int)depth == display_depth) {
+                    c = code == 2u ? make_float4(0.7f, 0.f, 0.7f, 0.1f) : make_float4(0.5f, 0.f, 0.5f, 0.1f);
+                    break;
+                }
+                if (!is_leaf(nd.links)) {
+                    stack[sp] = nd.links.z; sdepth[sp] = (uint8_t)(depth + 1u); ++sp;   // sp <= depth < display_depth < kStack
+                    cur = nd.links.y; depth += 1u;
+                    descend = true;
+                }
+            }
+            if (!descend) {
+                if (sp == 0) break;
+                --sp;
+                cur = stack[sp]; depth = sdepth[sp];
+            }
+        }
+    }
+    out[(size_t)y * width + x] = c;
+}
+
+// getColor + main of raytracer.glsl (:159-179, :299-331): the reference's frame from hit records
 __global__ void __launch_bounds__(256)
 shade_kernel(const rtr_hit* __restrict__ hits, uint64_t n, const rtr_triangle* __restrict__ tris,
              const rtr_mesh* __restrict__ meshes, const rtr_material* __restrict__ materials, uint32_t flags,
-             float4* __restrict__ rgba) {
+             const float4* __restrict__ bvh_rgba, float4* __restrict__ rgba) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2* hp = reinterpret_cast<const uint2*>(hits + i);  // 24-byte records: three 8-byte loads
     const uint2 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
     float4 c = make_float4(0.f, 0.f, 0.f, 1.f);
+    if ((flags & RTR_SHADE_BVH) && bvh_rgba) c = __ldg(bvh_rgba + i);   // uIsBVHDisplayed, :161-163
     if (h2.x != 0u) {
         const uint32_t model = __ldg(&tris[h2.y].model_id);
         const float* m = materials[__ldg(&meshes[model].material_id)].color;
@@ -1105,12 +1163,26 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
     return launch_persistent(ctx, b, pixel_jobs(cam, width, denom_w, denom_h, rm, bounces, shadow, light, rgba, hits), rays);
 }
 
+int rtr_depth_overlay_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uint32_t width, uint32_t height,
+                             uint32_t denom_w, uint32_t denom_h, int display_depth, float* bvh_rgba) {
+    resolve_denoms(width, height, denom_w, denom_h);
+    if (width == 0 || height == 0 || denom_w == 0 || denom_h == 0)
+        return rtr_set_error(ctx, RTR_E_INVALID, "depth_overlay: bad image geometry %ux%u", width, height);
+    if (display_depth >= kStack) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "depth_overlay: depth %d >= %d", display_depth, kStack);
+    RTR_PROF(ctx, "depth_overlay_kernel");
+    depth_overlay_kernel<<<pixel_grid(width, height), kTraceBlock, 0, ctx->stream>>>(
+        b->flat_view, cam, width, height, denom_w, denom_h, display_depth, reinterpret_cast<float4*>(bvh_rgba));
+    RTR_LAUNCH_CHECK(ctx);
+    return RTR_OK;
+}
+
 int rtr_shade_launch(rtr_ctx* ctx, const rtr_hit* hits, uint64_t n, const rtr_triangle* tris, const rtr_mesh* meshes,
-                     const rtr_material* materials, uint32_t flags, float* rgba) {
+                     const rtr_material* materials, uint32_t flags, const float* bvh_rgba, float* rgba) {
     if (n == 0) return RTR_OK;
     if (n >= (1ull << 40)) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "shade: too many pixels");
     RTR_PROF(ctx, "shade_kernel");
     shade_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(hits, n, tris, meshes, materials, flags,
+                                                                       reinterpret_cast<const float4*>(bvh_rgba),
                                                                        reinterpret_cast<float4*>(rgba));
     RTR_LAUNCH_CHECK(ctx);
     return RTR_OK;

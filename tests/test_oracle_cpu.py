@@ -185,3 +185,30 @@ def test_oracle_build64_refines_the_32_bit_order(oracle):
     c64 = oracle.morton_codes64(tris, meshes)
     assert np.array_equal(c64[b64.triangle_indices], np.sort(c64, kind="stable"))
     assert int(b64.left[-1]) != 0xFFFFFFFF and b64.trace_merges.sum() == tris.size - 1
+
+
+def test_depth_overlay_oracle_on_a_two_leaf_tree(oracle):
+    """Hand-checkable overlay: depth 0 colours every pixel whose ray meets the root box, depth 1 the children; a ray
+    entering near an edge of the box gets the line colour (raytracer.glsl:222-233, :269-275)."""
+    import scenes
+    from realtimeraytracing_b200 import synth
+    tris, meshes, L = scenes.soup(2, seed=1)
+    b = oracle.bvh_build(tris, meshes)
+    flat = oracle.flatten(b.clusters, b.left, b.right)
+    W, H = 64, 48
+    cam = synth.soup_camera(L, W, H)
+    d0 = oracle.depth_overlay(flat, cam, W, H, 0)
+    d1 = oracle.depth_overlay(flat, cam, W, H, 1)
+    d2 = oracle.depth_overlay(flat, cam, W, H, 2)
+    box, line = (0.5, 0.0, 0.5, 0.1), (0.7, 0.0, 0.7, 0.1)
+    def kinds(a):
+        return {tuple(np.float32(c).tolist()) for c in np.unique(a, axis=0)}
+    f32 = lambda t: tuple(np.float32(x).item() for x in t)
+    assert kinds(d0) <= {f32(box), f32(line), (0.0, 0.0, 0.0, 0.0)} and f32(box) in kinds(d0)
+    hit0 = (d0[:, 3] > 0); hit1 = (d1[:, 3] > 0)
+    assert hit1.sum() > 0 and not (hit1 & ~hit0).any()       # children are inside the root box
+    assert not (d2[:, 3] > 0).any()                          # no node at depth 2 in a two-leaf tree
+    hits = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
+    img = oracle.shade(hits, tris, meshes, np.ones((1, 4), np.float32), bvh_rgba=d0)
+    miss = hits["did_hit"] == 0
+    assert np.array_equal(img[miss], d0[miss])               # a miss shows the overlay colour alone

@@ -260,3 +260,27 @@ def test_shaded_frame_equals_getcolor(ctx, oracle, wireframe):
             ctx.shade(hits, tris, meshes, materials[:1], wireframe=wireframe)   # model 0 names material 1
     finally:
         bvh.close()
+
+
+@pytest.mark.parametrize("depth", [0, 3, 7, 12])
+def test_bvh_depth_overlay_equals_the_shaders_loop(ctx, oracle, depth):
+    """uIsBVHDisplayed / uDepthDisplayBVH (raytracer.glsl:269-275, edge code 2 of intersectBVH :222-233): the kernel
+    finds the left-most intersected node of that depth, the oracle runs the shader's loop to the letter (every
+    intersected node of the depth overwrites the colour, the last one visited stays) -- same pixels; then getColor."""
+    tris, meshes, L = scenes.soup(6000, seed=3)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        W, H = 96, 64
+        cam = synth.soup_camera(L, W, H)
+        flat = bvh.flat_nodes()
+        got = bvh.depth_overlay(cam, W, H, depth, W, H)
+        exp = oracle.depth_overlay(flat, cam, W, H, depth)
+        assert np.array_equal(got, exp)
+        colours = {tuple(c) for c in np.unique(got, axis=0).tolist()}
+        assert len(colours) >= 2                       # box colour and background at least
+        hits = bvh.trace_primary(cam, W, H, W, H)
+        mats = np.array([[0.3, 0.6, 0.9, 1.0]], np.float32)
+        img = ctx.shade(hits, tris, meshes, mats, wireframe=True, bvh_rgba=got)
+        assert np.array_equal(img, oracle.shade(hits, tris, meshes, mats, wireframe=True, bvh_rgba=exp))
+    finally:
+        bvh.close()
