@@ -304,6 +304,36 @@ int rtr_render_stripes_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* c
                            uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
                            float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
+/* ---- scene ingestion (host only: no rtr_ctx, no device; errors through rtr_last_error(NULL)) ----
+ * What produces the TriangleGPU[] / MeshModelGPU[] arrays the build consumes. */
+
+/* replaces cr::Mesh::load (srcCommon/scene/geometry/mesh.cpp:186-263): the triangles of a Wavefront OBJ file in
+ * face order, w = 1, every _ModelId = model_id (Mesh::_Id).  Parsing follows tinyobjloader 1.2.0 (the copy in the
+ * reference's tree) bit for bit, including its decimal reader and its ear clipping of polygons; a malformed `f`
+ * statement or a corner that names a vertex the file does not have is RTR_E_INVALID (the reference exits / reads
+ * out of bounds).  *out_tris is malloc'ed by the library: release it with rtr_obj_free. */
+int rtr_obj_load(const char* path, uint32_t model_id, rtr_triangle** out_tris, uint64_t* out_n);
+int rtr_obj_parse(const char* text, uint64_t len, uint32_t model_id, rtr_triangle** out_tris, uint64_t* out_n);
+void rtr_obj_free(rtr_triangle* tris);
+
+/* replaces cr::Mesh::primitiveTriangle/Square/Cube/Sphere (mesh.cpp:64-183); the sphere is empty there too */
+#define RTR_PRIMITIVE_TRIANGLE 0
+#define RTR_PRIMITIVE_SQUARE 1
+#define RTR_PRIMITIVE_CUBE 2
+#define RTR_PRIMITIVE_SPHERE 3
+int rtr_mesh_primitive(int which, uint32_t model_id, rtr_triangle* out, uint64_t cap, uint64_t* out_n);
+
+/* replace cr::Mesh::setModel / setPosition / setScale / setRotation / setMaterial (mesh.cpp:18-62) on the
+ * MeshModelGPU record; same GLM operation order, so the matrices are bit-identical to the reference's */
+void rtr_mesh_init(rtr_mesh* m); /* identity, material 0 (mesh.hpp:13-14) */
+void rtr_mesh_set_model(rtr_mesh* m, const float model[16]);
+void rtr_mesh_set_position(rtr_mesh* m, float x, float y, float z);
+void rtr_mesh_set_scale(rtr_mesh* m, float scale);
+void rtr_mesh_set_rotation(rtr_mesh* m, float theta_x, float theta_y, float theta_z);
+void rtr_mesh_set_material(rtr_mesh* m, uint32_t material_id);
+/* replaces cr::Triangle::getCentroid(triangle, model) (triangle.cpp:30-32), the point the Morton codes are taken of */
+void rtr_triangle_centroid(const rtr_triangle* t, const float model[16], float out[3]);
+
 /* ---- multi-GPU (one process per GPU; NCCL resolved at run time with dlopen("libnccl.so.2"),
  * so inside a torch process it is the very library torch.distributed already loaded) ---- */
 #define RTR_NCCL_UNIQUE_ID_BYTES 128

@@ -13,6 +13,8 @@
 //   cr::TriangleGPU   <- srcCommon/scene/geometry/triangle.hpp:9-14   (64 B, _ModelId at 48)
 //   cr::MeshModelGPU  <- srcCommon/scene/geometry/mesh.hpp:12-15      (68 B)
 //   cr::AABB_GPU, cr::BVH_NodeGPU, cr::BVH_Params, cr::BVH  <- srcCommon/scene/geometry/bvh.hpp:22-91
+//   cr::Triangle, cr::Mesh (load / primitive* / set*)       <- triangle.hpp:16-34, mesh.hpp:17-44
+//   cr::Camera                                              <- srcCommon/scene/camera.hpp:35-106
 //
 // plus what the reference does on the host after the build and what it does per frame:
 //
@@ -33,6 +35,7 @@
 #include <cstring>
 #include <memory>
 #include <optional>
+#include <string>
 #include <vector>
 
 #include "rtr.h"
@@ -66,9 +69,9 @@ struct TriangleGPU {
 // mesh.hpp:12-15
 struct MeshModelGPU {
 #ifdef RTR_SCENE_USE_GLM
-    mat4 _Model = mat4(1.f);
+    mat4 _ModelMatrix = mat4(1.f);
 #else
-    mat4 _Model = mat4::identity();
+    mat4 _ModelMatrix = mat4::identity();
 #endif
     uint32_t _MaterialId = 0;
 };
@@ -273,6 +276,93 @@ inline rtr_ctx* defaultContext(int device = 0) {
     if (!ctx) RTR_SCENE_CHECK(nullptr, rtr_ctx_create(device, &ctx));
     return ctx;
 }
+
+// cr::Triangle (triangle.hpp:16-34, triangle.cpp)
+class Triangle {
+public:
+    static const size_t MAX_NB_TRIANGLES = 2 << 15;  // the reference's SSBO cap; nothing in this library is bound by it
+    TriangleGPU _InternalStruct{};
+
+    Triangle() = default;
+    explicit Triangle(const TriangleGPU& t) : _InternalStruct(t) {}
+    Triangle(const vec4& p0, const vec4& p1, const vec4& p2, uint32_t modelId) {
+        std::memset(&_InternalStruct, 0, sizeof(_InternalStruct));
+        _InternalStruct._P0 = p0; _InternalStruct._P1 = p1; _InternalStruct._P2 = p2;
+        _InternalStruct._ModelId = modelId;
+    }
+    Triangle(const vec3& p0, const vec3& p1, const vec3& p2, uint32_t modelId)
+        : Triangle(vec4{p0.x, p0.y, p0.z, 1.f}, vec4{p1.x, p1.y, p1.z, 1.f}, vec4{p2.x, p2.y, p2.z, 1.f}, modelId) {}
+
+    static vec3 getCentroid(const TriangleGPU& triangle, const mat4& model) {  // triangle.cpp:30-32
+        float c[3];
+        rtr_triangle_centroid(reinterpret_cast<const rtr_triangle*>(&triangle), reinterpret_cast<const float*>(&model), c);
+        return vec3{c[0], c[1], c[2]};
+    }
+};
+
+// cr::Mesh (mesh.hpp:17-44, mesh.cpp).  Loading and the matrix setters run in librtr_b200 (rtr_obj_load, rtr_mesh_*),
+// which follow the reference's tinyobjloader / GLM arithmetic bit for bit; a load error is fatal like the
+// reference's (errorHandler.cpp:13-29).
+class Mesh;
+using MeshPtr = std::shared_ptr<Mesh>;
+
+class Mesh {
+    static uint32_t& idGenerator() { static uint32_t next = 0; return next; }  // Mesh::_IdGenerator, mesh.cpp:9
+    uint32_t _Id = 0;
+
+public:
+    std::vector<Triangle> _Triangles{};
+    MeshModelGPU _InternalStruct;
+    static const size_t MAX_NB_MESHES = 2 << 5;
+
+    Mesh() { _Id = idGenerator()++; }
+    uint32_t getId() const { return _Id; }
+
+    void setModel(const mat4& model) { rtr_mesh_set_model(raw(), reinterpret_cast<const float*>(&model)); }
+    void setPosition(const vec3& position) { rtr_mesh_set_position(raw(), position.x, position.y, position.z); }
+    void setScale(float scale) { rtr_mesh_set_scale(raw(), scale); }
+    void setRotation(float thetaX, float thetaY, float thetaZ) { rtr_mesh_set_rotation(raw(), thetaX, thetaY, thetaZ); }
+    void setMaterial(uint32_t materialId) { rtr_mesh_set_material(raw(), materialId); }
+
+    static MeshPtr primitiveTriangle() { return primitive(RTR_PRIMITIVE_TRIANGLE); }
+    static MeshPtr primitiveSquare() { return primitive(RTR_PRIMITIVE_SQUARE); }
+    static MeshPtr primitiveCube() { return primitive(RTR_PRIMITIVE_CUBE); }
+    static MeshPtr primitiveSphere() { return primitive(RTR_PRIMITIVE_SPHERE); }
+
+    static MeshPtr load(const std::string& path) {  // mesh.cpp:186-263
+        MeshPtr mesh(new Mesh());
+        rtr_triangle* tris = nullptr;
+        uint64_t n = 0;
+        const int rc = rtr_obj_load(path.c_str(), mesh->_Id, &tris, &n);
+        if (rc != RTR_OK) {
+            std::fprintf(stderr, "Error triggered in %s:%d\n\tError loading object `%s': %s\nExiting the program!\n", __FILE__,
+                         __LINE__, path.c_str(), rtr_last_error(nullptr));
+            std::exit(EXIT_FAILURE);
+        }
+        mesh->adopt(tris, n);
+        rtr_obj_free(tris);
+        return mesh;
+    }
+
+    // the TriangleGPU records of the mesh, back to back (what glr::Scene::getTriangleToGPUData copies, scene.cpp:26-40)
+    void appendTo(std::vector<TriangleGPU>& out) const {
+        for (const Triangle& t : _Triangles) out.push_back(t._InternalStruct);
+    }
+
+private:
+    rtr_mesh* raw() { return reinterpret_cast<rtr_mesh*>(&_InternalStruct); }
+    void adopt(const rtr_triangle* tris, uint64_t n) {
+        _Triangles.resize(static_cast<size_t>(n));
+        for (size_t i = 0; i < _Triangles.size(); ++i) std::memcpy(&_Triangles[i]._InternalStruct, tris + i, sizeof(rtr_triangle));
+    }
+    static MeshPtr primitive(int which) {
+        MeshPtr mesh(new Mesh());
+        rtr_triangle tris[12];
+        uint64_t n = 0;
+        if (rtr_mesh_primitive(which, mesh->_Id, tris, 12, &n) == RTR_OK) mesh->adopt(tris, n);
+        return mesh;
+    }
+};
 
 // bvh.hpp:44-63 ; sized by the actual triangle count instead of Triangle::MAX_NB_TRIANGLES
 struct BVH_Params {

@@ -16,13 +16,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librtr_b200.so")
-SOURCES = ["api.cu", "morton.cu", "sort.cu", "ploc.cu", "trace.cu", "comm.cu"]
+SOURCES = ["api.cu", "morton.cu", "sort.cu", "ploc.cu", "trace.cu", "comm.cu", "mesh.cu"]
 HEADERS = ["common.cuh", "bvh.cuh", os.path.join("..", "..", "include", "rtr.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-    "-Xcompiler", "-fPIC,-O2,-fvisibility=default",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=default,-ffp-contract=off",
     "--expt-relaxed-constexpr",
 ]
 

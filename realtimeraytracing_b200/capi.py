@@ -39,6 +39,9 @@ SYMBOLS = [
     "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
     "rtr_bvh_build64", "rtr_bvh_build64_dev", "rtr_bvh_morton_codes64",
     "rtr_bvh_depth_overlay", "rtr_bvh_depth_overlay_dev",
+    "rtr_obj_load", "rtr_obj_parse", "rtr_obj_free", "rtr_mesh_primitive", "rtr_mesh_init", "rtr_mesh_set_model",
+    "rtr_mesh_set_position", "rtr_mesh_set_scale", "rtr_mesh_set_rotation", "rtr_mesh_set_material",
+    "rtr_triangle_centroid",
 ]
 
 
@@ -148,6 +151,17 @@ def load_library():
     L.rtr_bvh_depth_overlay_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, i32, vp]
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
+    f32 = C.c_float
+    L.rtr_obj_load.argtypes = [C.c_char_p, u32, pp, C.POINTER(u64)]
+    L.rtr_obj_parse.argtypes = [C.c_char_p, u64, u32, pp, C.POINTER(u64)]
+    L.rtr_obj_free.argtypes = [vp]
+    L.rtr_obj_free.restype = None
+    L.rtr_mesh_primitive.argtypes = [i32, u32, vp, u64, C.POINTER(u64)]
+    for name, args in (("rtr_mesh_init", [vp]), ("rtr_mesh_set_model", [vp, vp]), ("rtr_mesh_set_position", [vp, f32, f32, f32]),
+                       ("rtr_mesh_set_scale", [vp, f32]), ("rtr_mesh_set_rotation", [vp, f32, f32, f32]),
+                       ("rtr_mesh_set_material", [vp, u32]), ("rtr_triangle_centroid", [vp, vp, vp])):
+        getattr(L, name).argtypes = args
+        getattr(L, name).restype = None
     _lib = L
     return L
 
@@ -170,6 +184,62 @@ def _as(a, dtype):
             raise TypeError("expected an array of dtype %s" % (dtype,))
         a = a.astype(dtype)
     return a
+
+
+def _check_host(rc):
+    """Host-only entry points (no ctx) report through rtr_last_error(NULL)."""
+    if rc != 0:
+        msg = load_library().rtr_last_error(None)
+        raise RtrError(rc, msg.decode() if msg else "")
+
+
+def _take_triangles(out, n) -> np.ndarray:
+    L = load_library()
+    try:
+        tris = np.zeros(n.value, dtype=TRIANGLE)
+        if n.value:
+            C.memmove(tris.ctypes.data, out.value, n.value * TRIANGLE.itemsize)
+        return tris
+    finally:
+        L.rtr_obj_free(out)
+
+
+def load_obj(path: str, model_id: int = 0) -> np.ndarray:
+    """cr::Mesh::load (mesh.cpp:186-263): TRIANGLE[] of a Wavefront OBJ file, in face order."""
+    L = load_library()
+    out, n = C.c_void_p(), C.c_uint64()
+    _check_host(L.rtr_obj_load(os.fsencode(path), model_id, C.byref(out), C.byref(n)))
+    return _take_triangles(out, n)
+
+
+def parse_obj(text, model_id: int = 0) -> np.ndarray:
+    """The same from the file's bytes."""
+    L = load_library()
+    data = text.encode() if isinstance(text, str) else bytes(text)
+    out, n = C.c_void_p(), C.c_uint64()
+    _check_host(L.rtr_obj_parse(data, len(data), model_id, C.byref(out), C.byref(n)))
+    return _take_triangles(out, n)
+
+
+PRIMITIVE_TRIANGLE, PRIMITIVE_SQUARE, PRIMITIVE_CUBE, PRIMITIVE_SPHERE = 0, 1, 2, 3
+
+
+def mesh_primitive(which: int, model_id: int = 0) -> np.ndarray:
+    """cr::Mesh::primitiveTriangle/Square/Cube/Sphere (mesh.cpp:64-183)."""
+    L = load_library()
+    tris = np.zeros(12, dtype=TRIANGLE)
+    n = C.c_uint64()
+    _check_host(L.rtr_mesh_primitive(which, model_id, _ptr(tris), tris.size, C.byref(n)))
+    return tris[:n.value].copy()
+
+
+def triangle_centroid(tri: np.ndarray, model) -> np.ndarray:
+    """cr::Triangle::getCentroid(triangle, model) (triangle.cpp:30-32); model is the 16 floats, column-major."""
+    t = np.ascontiguousarray(tri, dtype=TRIANGLE).reshape(1)
+    m = np.ascontiguousarray(model, dtype=np.float32).reshape(16)
+    out = np.zeros(3, dtype=np.float32)
+    load_library().rtr_triangle_centroid(_ptr(t), _ptr(m), _ptr(out))
+    return out
 
 
 class Context:

@@ -60,6 +60,70 @@ def getBVH_NodesToGPUData(bvh: BVH) -> np.ndarray:
     return bvh.handle.flat_nodes()
 
 
+class Mesh:
+    """cr::Mesh (srcCommon/scene/geometry/mesh.hpp:17-44): a triangle list, a MeshModelGPU and the id every triangle
+    of the mesh carries in _ModelId.  All arithmetic is librtr_b200's (rtr_obj_load / rtr_mesh_*), so the records are
+    the bits the reference produces."""
+
+    _IdGenerator = 0  # mesh.cpp:9
+    MAX_NB_MESHES = MAX_NB_MESHES
+
+    def __init__(self, triangles=None):
+        self._Id = Mesh._IdGenerator
+        Mesh._IdGenerator += 1
+        self._InternalStruct = np.zeros(1, dtype=MESH)
+        capi.load_library().rtr_mesh_init(capi._ptr(self._InternalStruct))
+        self._Triangles = np.zeros(0, dtype=TRIANGLE) if triangles is None else np.array(triangles, dtype=TRIANGLE)
+        self._Triangles["model_id"] = self._Id
+
+    def setModel(self, model):
+        """mesh.cpp:24-26; `model` is 16 floats, column-major like glm::mat4."""
+        m = np.ascontiguousarray(model, dtype=np.float32).reshape(16)
+        capi.load_library().rtr_mesh_set_model(capi._ptr(self._InternalStruct), capi._ptr(m))
+
+    def setPosition(self, position):
+        x, y, z = (float(v) for v in position)
+        capi.load_library().rtr_mesh_set_position(capi._ptr(self._InternalStruct), x, y, z)
+
+    def setScale(self, scale: float):
+        capi.load_library().rtr_mesh_set_scale(capi._ptr(self._InternalStruct), float(scale))
+
+    def setRotation(self, thetaX: float, thetaY: float, thetaZ: float):
+        capi.load_library().rtr_mesh_set_rotation(capi._ptr(self._InternalStruct), float(thetaX), float(thetaY), float(thetaZ))
+
+    def setMaterial(self, materialId: int):
+        capi.load_library().rtr_mesh_set_material(capi._ptr(self._InternalStruct), int(materialId))
+
+    @staticmethod
+    def _primitive(which):
+        m = Mesh()
+        m._Triangles = capi.mesh_primitive(which, m._Id)
+        return m
+
+    @staticmethod
+    def primitiveTriangle():
+        return Mesh._primitive(capi.PRIMITIVE_TRIANGLE)
+
+    @staticmethod
+    def primitiveSquare():
+        return Mesh._primitive(capi.PRIMITIVE_SQUARE)
+
+    @staticmethod
+    def primitiveCube():
+        return Mesh._primitive(capi.PRIMITIVE_CUBE)
+
+    @staticmethod
+    def primitiveSphere():
+        return Mesh._primitive(capi.PRIMITIVE_SPHERE)
+
+    @staticmethod
+    def load(path: str):
+        """mesh.cpp:186-263"""
+        m = Mesh()
+        m._Triangles = capi.load_obj(path, m._Id)
+        return m
+
+
 class Scene:
     """The slice of glr::Scene that feeds the accelerated path."""
 
@@ -71,9 +135,17 @@ class Scene:
         self._BVH = None
         self._reference_padding = reference_padding
 
-    def addMesh(self, triangles: np.ndarray, model=None, material_id: int = 0):
-        """scene.cpp:42-47; triangles' _ModelId is set to the mesh slot like Mesh::_Id."""
+    def addMesh(self, triangles, model=None, material_id: int = 0):
+        """scene.cpp:42-47.  A `Mesh` is taken as it is (its triangles carry Mesh::_Id, which is the mesh slot only
+        when meshes are added in creation order -- as in the reference); a bare TRIANGLE array gets a mesh record
+        made here and _ModelId = the mesh slot."""
         if self._reference_padding and len(self._Meshes) == MAX_NB_MESHES:
+            return
+        if isinstance(triangles, Mesh):
+            tris, mesh = triangles._Triangles, triangles._InternalStruct
+            self._Meshes.append((tris, mesh))
+            self._NbMeshes += 1
+            self._NbTriangles += tris.size if not self._reference_padding else min(tris.size, MAX_NB_TRIANGLES)
             return
         mesh = np.zeros(1, dtype=MESH)
         mesh["m"][0] = (np.eye(4, dtype=np.float32) if model is None else np.asarray(model, dtype=np.float32)).T.reshape(16)
@@ -112,4 +184,4 @@ class Scene:
         return getBVH_NodesToGPUData(self._BVH)
 
 
-__all__ = ["BVH", "BVH_Params", "Scene", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]
+__all__ = ["BVH", "BVH_Params", "Scene", "Mesh", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]

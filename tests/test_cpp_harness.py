@@ -19,7 +19,7 @@ def executables():
     env.pop("CXX", None)
     out = subprocess.run(["make", "-C", HARNESS, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera"]}
+    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera", "testMesh"]}
 
 
 def test_camera_mirror_is_bit_identical_to_the_reference(executables):
@@ -36,6 +36,19 @@ def test_camera_mirror_is_bit_identical_to_the_reference(executables):
     r = subprocess.run([executables["testCamera"], lib], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+def test_mesh_mirror_is_bit_identical_to_the_reference(executables):
+    """cr::Mesh / cr::Triangle of include/rtr_scene.hpp vs the reference's own mesh.cpp (oracle/_ref/libref_mesh.so):
+    Mesh::load on the OBJ fixtures, primitives, 2000 replayed setter sequences and centroids."""
+    import glob
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_mesh.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libref_mesh.so not built (needs /root/reference)")
+    objs = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "obj", "*.obj")))
+    r = subprocess.run([executables["testMesh"], lib] + objs, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout and "%d cases" % (len(objs) + 4 + 2000) in r.stdout
 
 
 def test_cpp_harness_compiles_and_links(executables):
