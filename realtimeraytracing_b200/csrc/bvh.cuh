@@ -100,6 +100,12 @@ struct rtr_bvh {
 //     w4..w6  per axis k the byte quadruple (Llo, Lhi, Rlo, Rhi): child plane = origin_k + byte * step_k,
 //             min planes rounded down, max planes rounded up -- a SUPERSET of the child's exact box
 //     w7      flat index of the right child (the left child is p + 1: DFS pre-order, scene.cpp:189-199)
+//   inner node p, second 32 bytes (the "wide step", one more 256-bit load): four slots on the SAME grid --
+//     slot 0 / 1 = the children of L (slot 0 = L itself and slot 1 unused when L is a leaf), slot 2 / 3 = those of R
+//     w8..w10   per axis the byte quadruple (S0lo, S0hi, S1lo, S1hi);  w11  flat index of slot 1
+//     w12..w14  per axis the byte quadruple (S2lo, S2hi, S3lo, S3hi);  w15  flat index of slot 3
+//     (slot 0 is at p + 2, or p + 1 when L is a leaf; slot 2 at right + 1, or right when R is a leaf)
+//     flags bit3..bit6: slot 0..3 is a leaf; bit7: the second half is usable
 //   leaf p (64 bytes, two 256-bit loads):
 //     exact box min.xyz, max.xyz | world-space vertices P0, P1, P2 (host naming) | triangle id
 //
@@ -114,10 +120,13 @@ __device__ __forceinline__ int trav_ilogb(double x) {  // floor(log2 x) of a pos
 }
 __device__ __forceinline__ double trav_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
 
-// One axis: grid step 2^e with origin + 255 * step >= hi, then the four plane bytes.  Everything is checked
-// in double, where origin + byte * step is exact (the step is kept within 2^-40 of the origin's magnitude).
-__device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
-                                                 uint32_t& ebyte, uint32_t& quad, bool& ok) {
+// One axis of a node's grid: step 2^e with origin + 255 * step >= hi.  Everything is checked in double, where
+// origin + byte * step is exact (the step is kept within 2^-40 of the origin's magnitude).
+struct TravAxis {
+    double lo, step, inv_step;
+    uint32_t ebyte;
+};
+__device__ __forceinline__ TravAxis trav_axis_frame(float nlo_f, float nhi_f, bool& ok) {
     const double lo = nlo_f, hi = nhi_f;
     const double ext = hi - lo;
     int e = -100;
@@ -131,7 +140,13 @@ __device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float
     }
     if (e < -100) e = -100;
     if (!(ext >= 0.0) || e > 30 || !(fabs(lo) < 1e15)) { ok = false; e = 0; }
-    const double step = trav_pow2(e), inv_step = trav_pow2(-e);
+    TravAxis f;
+    f.lo = lo; f.step = trav_pow2(e); f.inv_step = trav_pow2(-e); f.ebyte = (uint32_t)(e + 127);
+    return f;
+}
+// the four plane bytes (Alo, Ahi, Blo, Bhi) of two boxes inside the node: min planes rounded down, max planes up
+__device__ __forceinline__ uint32_t trav_axis_quad(const TravAxis& f, float alo, float ahi, float blo, float bhi, bool& ok) {
+    const double lo = f.lo, step = f.step, inv_step = f.inv_step;
     auto down = [&](float x) -> uint32_t {
         const double t = fmin(fmax(((double)x - lo) * inv_step, 0.0), 255.0);
         int q = __double2int_rd(t);
@@ -144,12 +159,18 @@ __device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float
         if (q < 255 && lo + (double)q * step < (double)x) ++q;
         return (uint32_t)q;
     };
-    ebyte = (uint32_t)(e + 127);
-    quad = down(llo) | (up(lhi) << 8) | (down(rlo) << 16) | (up(rhi) << 24);
-    // the bytes must really bound the children (they always do for the exact unions a PLOC tree holds)
-    const double l0 = lo + (double)(quad & 0xFFu) * step, l1 = lo + (double)((quad >> 8) & 0xFFu) * step;
-    const double r0 = lo + (double)((quad >> 16) & 0xFFu) * step, r1 = lo + (double)(quad >> 24) * step;
-    if (!(l0 <= (double)llo && l1 >= (double)lhi && r0 <= (double)rlo && r1 >= (double)rhi)) ok = false;
+    const uint32_t quad = down(alo) | (up(ahi) << 8) | (down(blo) << 16) | (up(bhi) << 24);
+    // the bytes must really bound the boxes (they always do for the exact unions a PLOC tree holds)
+    const double a0 = lo + (double)(quad & 0xFFu) * step, a1 = lo + (double)((quad >> 8) & 0xFFu) * step;
+    const double b0 = lo + (double)((quad >> 16) & 0xFFu) * step, b1 = lo + (double)(quad >> 24) * step;
+    if (!(a0 <= (double)alo && a1 >= (double)ahi && b0 <= (double)blo && b1 >= (double)bhi)) ok = false;
+    return quad;
+}
+__device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
+                                                 uint32_t& ebyte, uint32_t& quad, bool& ok) {
+    const TravAxis f = trav_axis_frame(nlo_f, nhi_f, ok);
+    ebyte = f.ebyte;
+    quad = trav_axis_quad(f, llo, lhi, rlo, rhi, ok);
 }
 
 // node box n, child boxes l and r as (min.xyz, max.x)(max.y, max.z) float4 + float2
@@ -165,6 +186,18 @@ __device__ __forceinline__ void trav_encode_inner(const float4 nlo, const float2
     o0 = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z),
                     ex | (ey << 8) | (ez << 16) | (flags << 24));
     o1 = make_uint4(qx, qy, qz, right);
+}
+// Second half of an inner record: the four GRANDCHILD slots on the node's own grid (see the layout above).
+// box k = (min.xyz, max.x)(max.y, max.z); an unused slot repeats its sibling.  ok = false: the node keeps to pair steps.
+__device__ __forceinline__ void trav_encode_quads(const float4 nlo, const float2 nhi, const float4 lo[4], const float2 hi[4],
+                                                  uint32_t idx1, uint32_t idx3, uint4& o2, uint4& o3, bool& ok) {
+    const TravAxis fx = trav_axis_frame(nlo.x, nlo.w, ok);
+    const TravAxis fy = trav_axis_frame(nlo.y, nhi.x, ok);
+    const TravAxis fz = trav_axis_frame(nlo.z, nhi.y, ok);
+    o2 = make_uint4(trav_axis_quad(fx, lo[0].x, lo[0].w, lo[1].x, lo[1].w, ok), trav_axis_quad(fy, lo[0].y, hi[0].x, lo[1].y, hi[1].x, ok),
+                    trav_axis_quad(fz, lo[0].z, hi[0].y, lo[1].z, hi[1].y, ok), idx1);
+    o3 = make_uint4(trav_axis_quad(fx, lo[2].x, lo[2].w, lo[3].x, lo[3].w, ok), trav_axis_quad(fy, lo[2].y, hi[2].x, lo[3].y, hi[3].x, ok),
+                    trav_axis_quad(fz, lo[2].z, hi[2].y, lo[3].z, hi[3].y, ok), idx3);
 }
 #endif
 

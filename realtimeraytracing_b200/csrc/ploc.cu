@@ -723,6 +723,54 @@ pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t
     store_inner_record(pairs, i, o0, o1);
 }
 
+// Second half of every inner traversal record (bvh.cuh): the four grandchild slots on the node's own grid, for the
+// traversal's wide step.  One thread per flat index, after the first halves and the flat nodes are written.
+__global__ void __launch_bounds__(256)
+pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* __restrict__ pairs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb_nodes) return;
+    const uint4* me = reinterpret_cast<const uint4*>(flat + i);
+    const uint4 links = __ldg(me + 2);
+    if (links.y == 0u && links.z == 0u) return;
+    const uint4 m0 = __ldg(me), m1 = __ldg(me + 1);
+    const uint32_t child[2] = {links.y, links.z};
+    float4 lo[4];
+    float2 hi[4];
+    uint32_t idx[4], leaf_bits = 0u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint4* c = reinterpret_cast<const uint4*>(flat + child[k]);
+        const uint4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+        if (c2.y == 0u && c2.z == 0u) {  // the child is a leaf: it is its own first slot, the second repeats it (unused)
+            lo[2 * k] = lo[2 * k + 1] = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), __uint_as_float(c1.x));
+            hi[2 * k] = hi[2 * k + 1] = make_float2(__uint_as_float(c1.y), __uint_as_float(c1.z));
+            idx[2 * k] = idx[2 * k + 1] = child[k];
+            leaf_bits |= 3u << (2 * k);
+        } else {
+            const uint32_t g[2] = {c2.y, c2.z};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint4* q = reinterpret_cast<const uint4*>(flat + g[j]);
+                const uint4 g0 = __ldg(q), g1 = __ldg(q + 1), g2 = __ldg(q + 2);
+                lo[2 * k + j] = make_float4(__uint_as_float(g0.x), __uint_as_float(g0.y), __uint_as_float(g0.z), __uint_as_float(g1.x));
+                hi[2 * k + j] = make_float2(__uint_as_float(g1.y), __uint_as_float(g1.z));
+                idx[2 * k + j] = g[j];
+                if (g2.y == 0u && g2.z == 0u) leaf_bits |= 1u << (2 * k + j);
+            }
+        }
+    }
+    bool ok = true;
+    uint4 o2, o3;
+    trav_encode_quads(make_float4(__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z), __uint_as_float(m1.x)),
+                      make_float2(__uint_as_float(m1.y), __uint_as_float(m1.z)), lo, hi, idx[1], idx[3], o2, o3, ok);
+    uint4* rec = pairs + (size_t)i * 4;
+    uint32_t w3 = rec[0].w;
+    if (ok && !((w3 >> 24) & 4u)) w3 |= (0x80u | (leaf_bits << 3)) << 24;
+    rec[0].w = w3;
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(rec + 2), "r"(o2.x), "r"(o2.y), "r"(o2.z), "r"(o2.w), "r"(o3.x), "r"(o3.y), "r"(o3.z), "r"(o3.w) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // BVH_Params view by cluster id for the accessors / the cr::BVH shim (not on the timed path)
 // ---------------------------------------------------------------------------------------
@@ -786,6 +834,8 @@ int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
     const uint32_t nc = 2 * b->n - 1;
     pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->wtri_view,
                                                                  b->pairs_own, b->tparams);
+    RTR_LAUNCH_CHECK(ctx);
+    pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->pairs_own);
     RTR_LAUNCH_CHECK(ctx);
     b->pairs_view = b->pairs_own;
     return RTR_OK;
@@ -919,6 +969,9 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         const uint32_t nc = 2 * n - 1;
         RTR_PROF(ctx, "flatten_emit_kernel");
         flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, n, order, b->node, b->isize, b->wtri, b->flat, b->pairs);
+        RTR_LAUNCH_CHECK(ctx);
+        RTR_PROF(ctx, "pack_quads_kernel");
+        pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat, nc, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     }
     b->pairs_view = b->pairs;  // written by the flatten kernels

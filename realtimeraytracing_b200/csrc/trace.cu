@@ -534,6 +534,26 @@ constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays 
 #endif
 constexpr int kPrefetch = RTR_PREFETCH;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// Records of the two children of the node being tested (0 = off, 1 = towards L2, 2 = towards L1).  The left child sits
+// at a + 1, so its prefetch leaves with the node's own load; the right child's index arrives with the record and its
+// prefetch overlaps the plane tests.
+#ifndef RTR_PF_LEFT
+#define RTR_PF_LEFT 0
+#endif
+#ifndef RTR_PF_RIGHT
+#define RTR_PF_RIGHT 0
+#endif
+// Wide step: test the four grandchild slots of the second record half (bvh.cuh) instead of the child pair -- half the
+// dependent fetches per ray.
+#ifndef RTR_WIDE
+#define RTR_WIDE 1
+#endif
+constexpr bool kWide = RTR_WIDE != 0;
+template <int LEVEL> __device__ __forceinline__ void prefetch_child(const void* p) {
+    if (LEVEL == 1) prefetch_l2(p);
+    if (LEVEL == 2) prefetch_l1(p);
+}
 #ifndef RTR_WALK_STEPS
 #define RTR_WALK_STEPS 4
 #endif
@@ -704,6 +724,25 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
         tnl = fmaxf(tnl, __fmaf_rn(x0, sa, bn)); tfl = fminf(tfl, __fmaf_rn(x1, sa, bf));
         tnr = fmaxf(tnr, __fmaf_rn(x2, sa, bn)); tfr = fminf(tfr, __fmaf_rn(x3, sa, bf));
     };
+    // the same for the four slots of the wide step: quads (S0lo, S0hi, S1lo, S1hi) and (S2lo, S2hi, S3lo, S3hi)
+    auto axis_planes4 = [&](float c, uint32_t ebyte, uint32_t qa, uint32_t qb, float o, float j, float (&tn)[4], float (&tf)[4]) {
+        const float step = __uint_as_float(ebyte << 23);
+        const float sa = __fmul_rn(step, j);
+        const float sb = __fmul_rn(__fsub_rn(c, o), j);
+        const float m = __fmaf_rn(fabsf(sa), 0.52f, __fmaf_rn(fabsf(sb), 2e-6f, 1e-30f));
+        const float bn = __fmaf_rn(-8388608.f, sa, __fsub_rn(sb, m));
+        const float bf = __fmaf_rn(-8388608.f, sa, __fadd_rn(sb, m));
+        const uint32_t sel = j < 0.f ? 0x2301u : 0x3210u;
+        const uint32_t wa = __byte_perm(qa, qa, sel), wb = __byte_perm(qb, qb, sel);
+        tn[0] = fmaxf(tn[0], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650u)), sa, bn));
+        tf[0] = fminf(tf[0], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7651u)), sa, bf));
+        tn[1] = fmaxf(tn[1], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7652u)), sa, bn));
+        tf[1] = fminf(tf[1], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7653u)), sa, bf));
+        tn[2] = fmaxf(tn[2], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u)), sa, bn));
+        tf[2] = fminf(tf[2], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7651u)), sa, bf));
+        tn[3] = fmaxf(tn[3], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7652u)), sa, bn));
+        tf[3] = fminf(tf[3], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7653u)), sa, bf));
+    };
     // decoded planes of one axis, rounded outwards: min planes down, max planes up
     auto decode_axis = [&](float c, uint32_t ebyte, uint32_t quad, float& llo, float& lhi, float& rlo, float& rhi) {
         const float step = __uint_as_float(ebyte << 23);
@@ -778,10 +817,48 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                 } else {
                     // compressed child pair: one 256-bit load (LDG.E.256, sm_100+)
                     uint4 c0, c1;
+                    prefetch_child<RTR_PF_LEFT>(A.pairs + (size_t)a * 4 + 4);
                     ld_nc_256(A.pairs + (size_t)a * 4, c0, c1);
+                    uint4 c2 = make_uint4(0u, 0u, 0u, 0u), c3 = c2;
+                    const bool wide_ray = kWide && !(st & 0x40000u);
+                    if (wide_ray) ld_nc_256(A.pairs + (size_t)a * 4 + 2, c2, c3);  // both halves in flight together
+                    prefetch_child<RTR_PF_RIGHT>(A.pairs + (size_t)c1.w * 4);
                     float tl = -INFINITY, fl = INFINITY, tr = -INFINITY, fr = INFINITY;
                     const uint32_t flags = c0.w >> 24;
                     bool hl, hr;
+                    if (wide_ray && (flags & 0x80u)) {
+                        // ---- wide step: the four grandchild slots, nearest first ----
+                        float tn[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, tf[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+                        axis_planes4(__uint_as_float(c0.x), c0.w & 0xFFu, c2.x, c3.x, r.ox, r.ix, tn, tf);
+                        axis_planes4(__uint_as_float(c0.y), (c0.w >> 8) & 0xFFu, c2.y, c3.y, r.oy, r.iy, tn, tf);
+                        axis_planes4(__uint_as_float(c0.z), (c0.w >> 16) & 0xFFu, c2.z, c3.z, r.oz, r.iz, tn, tf);
+                        const uint32_t used = 0x5u | ((flags & 1u) ? 0u : 2u) | ((flags & 2u) ? 0u : 8u);  // slots 1 / 3 exist iff L / R is inner
+                        float key[4];
+                        uint32_t wd[4];
+                        wd[0] = (a + 2u - (flags & 1u)) | ((flags & 0x08u) ? kLeafBit : 0u);
+                        wd[1] = c2.w | ((flags & 0x10u) ? kLeafBit : 0u);
+                        wd[2] = (c1.w + 1u - ((flags >> 1) & 1u)) | ((flags & 0x20u) ? kLeafBit : 0u);
+                        wd[3] = c3.w | ((flags & 0x40u) ? kLeafBit : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const bool h = ((used >> k) & 1u) && tf[k] >= 0.f && tn[k] <= tf[k] && !(tn[k] > limit);
+                            key[k] = h ? tn[k] : INFINITY;
+                        }
+                        auto cswap = [&](int i, int j) {
+                            const bool sw = key[j] < key[i];
+                            const float ki = key[i], kj = key[j];
+                            const uint32_t wi = wd[i], wj = wd[j];
+                            key[i] = sw ? kj : ki; key[j] = sw ? ki : kj;
+                            wd[i] = sw ? wj : wi; wd[j] = sw ? wi : wj;
+                        };
+                        cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                        if (key[3] < INFINITY) push_far(key[3], wd[3]);
+                        if (key[2] < INFINITY) push_far(key[2], wd[2]);
+                        if (key[1] < INFINITY) push_far(key[1], wd[1]);
+                        if (key[0] < INFINITY) a = wd[0];
+                        else need_pop = true;
+                        hl = hr = false;
+                    } else {
                     if (st & 0x40000u) {
                         // a direction component is 0 (or nearly): the reference's own slab test -- it is what defines
                         // the outcome for a ray parallel to a slab (Q11) -- on the decoded superset boxes
@@ -813,6 +890,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     } else if (hl) a = lw;
                     else if (hr) a = rw;
                     else need_pop = true;
+                    }
                 }
             }
             if (need_pop) pop_next();  // one site: lanes coming from a parked leaf and from a double miss pop together
