@@ -120,8 +120,8 @@ __device__ __forceinline__ int trav_ilogb(double x) {  // floor(log2 x) of a pos
 }
 __device__ __forceinline__ double trav_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
 
-// One axis of a node's grid: step 2^e with origin + 255 * step >= hi.  Everything is checked in double, where
-// origin + byte * step is exact (the step is kept within 2^-40 of the origin's magnitude).
+// One axis of a node's grid: step 2^e with origin + 255 * step >= hi (the extent is taken in double, where hi - lo of
+// two fp32 values is exact); the step is kept within 2^-40 of the origin's magnitude.
 struct TravAxis {
     double lo, step, inv_step;
     uint32_t ebyte;
@@ -144,33 +144,30 @@ __device__ __forceinline__ TravAxis trav_axis_frame(float nlo_f, float nhi_f, bo
     f.lo = lo; f.step = trav_pow2(e); f.inv_step = trav_pow2(-e); f.ebyte = (uint32_t)(e + 127);
     return f;
 }
-// the four plane bytes (Alo, Ahi, Blo, Bhi) of two boxes inside the node: min planes rounded down, max planes up
-__device__ __forceinline__ uint32_t trav_axis_quad(const TravAxis& f, float alo, float ahi, float blo, float bhi, bool& ok) {
-    const double lo = f.lo, step = f.step, inv_step = f.inv_step;
+// The four plane bytes (Alo, Ahi, Blo, Bhi) of two boxes inside the node: min planes rounded down, max planes up.
+// fp32 with directed rounding: x - lo is rounded towards the safe side and the division by the power-of-two step is
+// exact (rounded the same way where it leaves the normal range), so byte <= (x - lo) / step for a min plane and >= for
+// a max plane hold in exact arithmetic -- no check in higher precision is needed, and at worst the byte is one step
+// looser than the exactly rounded one.  (An earlier version did this in double with a verification pass: +0.2 ms per
+// 10 M-triangle rebuild for the same traversal time.)
+__device__ __forceinline__ uint32_t trav_axis_quad_f32(const TravAxis& f, float alo, float ahi, float blo, float bhi, bool& ok) {
+    const float lo = (float)f.lo, inv_step = (float)f.inv_step;  // both exact: the origin is an fp32 value, the step 2^e, |e| <= 100
     auto down = [&](float x) -> uint32_t {
-        const double t = fmin(fmax(((double)x - lo) * inv_step, 0.0), 255.0);
-        int q = __double2int_rd(t);
-        if (q > 0 && lo + (double)q * step > (double)x) --q;
-        return (uint32_t)q;
+        const float t = __fmul_rd(__fsub_rd(x, lo), inv_step);
+        return (uint32_t)__float2int_rd(fminf(fmaxf(t, 0.f), 255.f));
     };
     auto up = [&](float x) -> uint32_t {
-        const double t = fmin(fmax(((double)x - lo) * inv_step, 0.0), 255.0);
-        int q = __double2int_ru(t);
-        if (q < 255 && lo + (double)q * step < (double)x) ++q;
-        return (uint32_t)q;
+        const float t = __fmul_ru(__fsub_ru(x, lo), inv_step);
+        if (!(t <= 255.5f)) ok = false;  // beyond the grid (never for a box inside the node) or NaN
+        return (uint32_t)__float2int_ru(fminf(fmaxf(t, 0.f), 255.f));
     };
-    const uint32_t quad = down(alo) | (up(ahi) << 8) | (down(blo) << 16) | (up(bhi) << 24);
-    // the bytes must really bound the boxes (they always do for the exact unions a PLOC tree holds)
-    const double a0 = lo + (double)(quad & 0xFFu) * step, a1 = lo + (double)((quad >> 8) & 0xFFu) * step;
-    const double b0 = lo + (double)((quad >> 16) & 0xFFu) * step, b1 = lo + (double)(quad >> 24) * step;
-    if (!(a0 <= (double)alo && a1 >= (double)ahi && b0 <= (double)blo && b1 >= (double)bhi)) ok = false;
-    return quad;
+    return down(alo) | (up(ahi) << 8) | (down(blo) << 16) | (up(bhi) << 24);
 }
 __device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
                                                  uint32_t& ebyte, uint32_t& quad, bool& ok) {
     const TravAxis f = trav_axis_frame(nlo_f, nhi_f, ok);
     ebyte = f.ebyte;
-    quad = trav_axis_quad(f, llo, lhi, rlo, rhi, ok);
+    quad = trav_axis_quad_f32(f, llo, lhi, rlo, rhi, ok);
 }
 
 // node box n, child boxes l and r as (min.xyz, max.x)(max.y, max.z) float4 + float2
@@ -194,10 +191,10 @@ __device__ __forceinline__ void trav_encode_quads(const float4 nlo, const float2
     const TravAxis fx = trav_axis_frame(nlo.x, nlo.w, ok);
     const TravAxis fy = trav_axis_frame(nlo.y, nhi.x, ok);
     const TravAxis fz = trav_axis_frame(nlo.z, nhi.y, ok);
-    o2 = make_uint4(trav_axis_quad(fx, lo[0].x, lo[0].w, lo[1].x, lo[1].w, ok), trav_axis_quad(fy, lo[0].y, hi[0].x, lo[1].y, hi[1].x, ok),
-                    trav_axis_quad(fz, lo[0].z, hi[0].y, lo[1].z, hi[1].y, ok), idx1);
-    o3 = make_uint4(trav_axis_quad(fx, lo[2].x, lo[2].w, lo[3].x, lo[3].w, ok), trav_axis_quad(fy, lo[2].y, hi[2].x, lo[3].y, hi[3].x, ok),
-                    trav_axis_quad(fz, lo[2].z, hi[2].y, lo[3].z, hi[3].y, ok), idx3);
+    o2 = make_uint4(trav_axis_quad_f32(fx, lo[0].x, lo[0].w, lo[1].x, lo[1].w, ok), trav_axis_quad_f32(fy, lo[0].y, hi[0].x, lo[1].y, hi[1].x, ok),
+                    trav_axis_quad_f32(fz, lo[0].z, hi[0].y, lo[1].z, hi[1].y, ok), idx1);
+    o3 = make_uint4(trav_axis_quad_f32(fx, lo[2].x, lo[2].w, lo[3].x, lo[3].w, ok), trav_axis_quad_f32(fy, lo[2].y, hi[2].x, lo[3].y, hi[3].x, ok),
+                    trav_axis_quad_f32(fz, lo[2].z, hi[2].y, lo[3].z, hi[3].y, ok), idx3);
 }
 #endif
 

@@ -740,8 +740,9 @@ pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* _
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const uint4* c = reinterpret_cast<const uint4*>(flat + child[k]);
-        const uint4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+        const uint4 c2 = __ldg(c + 2);
         if (c2.y == 0u && c2.z == 0u) {  // the child is a leaf: it is its own first slot, the second repeats it (unused)
+            const uint4 c0 = __ldg(c), c1 = __ldg(c + 1);
             lo[2 * k] = lo[2 * k + 1] = make_float4(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z), __uint_as_float(c1.x));
             hi[2 * k] = hi[2 * k + 1] = make_float2(__uint_as_float(c1.y), __uint_as_float(c1.z));
             idx[2 * k] = idx[2 * k + 1] = child[k];
