@@ -530,10 +530,13 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
 #ifndef RTR_PREFETCH
-#define RTR_PREFETCH 2   // bit 0: record of a stacked child, bit 1: record of a parked leaf
+#define RTR_PREFETCH 2   // bit 0: record of a stacked child (pair step), bit 1: record of a parked leaf, bits 2/3: wide step
 #endif
 constexpr int kPrefetch = RTR_PREFETCH;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// three-input min / max (FMNMX3, sm_100+); NaN operands are ignored like in fminf / fmaxf
+__device__ __forceinline__ float max3f(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float min3f(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // Records of the two children of the node being tested (0 = off, 1 = towards L2, 2 = towards L1).  The left child sits
 // at a + 1, so its prefetch leaves with the node's own load; the right child's index arrives with the record and its
@@ -724,8 +727,9 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
         tnl = fmaxf(tnl, __fmaf_rn(x0, sa, bn)); tfl = fminf(tfl, __fmaf_rn(x1, sa, bf));
         tnr = fmaxf(tnr, __fmaf_rn(x2, sa, bn)); tfr = fminf(tfr, __fmaf_rn(x3, sa, bf));
     };
-    // the same for the four slots of the wide step: quads (S0lo, S0hi, S1lo, S1hi) and (S2lo, S2hi, S3lo, S3hi)
-    auto axis_planes4 = [&](float c, uint32_t ebyte, uint32_t qa, uint32_t qb, float o, float j, float (&tn)[4], float (&tf)[4]) {
+    // the same for the four slots of the wide step: quads (S0lo, S0hi, S1lo, S1hi) and (S2lo, S2hi, S3lo, S3hi);
+    // returns this axis' entry / exit distances, the caller combines the axes with three-input min / max
+    auto axis_vals4 = [&](float c, uint32_t ebyte, uint32_t qa, uint32_t qb, float o, float j, float (&vn)[4], float (&vf)[4]) {
         const float step = __uint_as_float(ebyte << 23);
         const float sa = __fmul_rn(step, j);
         const float sb = __fmul_rn(__fsub_rn(c, o), j);
@@ -734,14 +738,14 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
         const float bf = __fmaf_rn(-8388608.f, sa, __fadd_rn(sb, m));
         const uint32_t sel = j < 0.f ? 0x2301u : 0x3210u;
         const uint32_t wa = __byte_perm(qa, qa, sel), wb = __byte_perm(qb, qb, sel);
-        tn[0] = fmaxf(tn[0], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650u)), sa, bn));
-        tf[0] = fminf(tf[0], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7651u)), sa, bf));
-        tn[1] = fmaxf(tn[1], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7652u)), sa, bn));
-        tf[1] = fminf(tf[1], __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7653u)), sa, bf));
-        tn[2] = fmaxf(tn[2], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u)), sa, bn));
-        tf[2] = fminf(tf[2], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7651u)), sa, bf));
-        tn[3] = fmaxf(tn[3], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7652u)), sa, bn));
-        tf[3] = fminf(tf[3], __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7653u)), sa, bf));
+        vn[0] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650u)), sa, bn);
+        vf[0] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7651u)), sa, bf);
+        vn[1] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7652u)), sa, bn);
+        vf[1] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7653u)), sa, bf);
+        vn[2] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u)), sa, bn);
+        vf[2] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7651u)), sa, bf);
+        vn[3] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7652u)), sa, bn);
+        vf[3] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7653u)), sa, bf);
     };
     // decoded planes of one axis, rounded outwards: min planes down, max planes up
     auto decode_axis = [&](float c, uint32_t ebyte, uint32_t quad, float& llo, float& lhi, float& rlo, float& rhi) {
@@ -828,10 +832,16 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     bool hl, hr;
                     if (wide_ray && (flags & 0x80u)) {
                         // ---- wide step: the four grandchild slots, nearest first ----
-                        float tn[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, tf[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-                        axis_planes4(__uint_as_float(c0.x), c0.w & 0xFFu, c2.x, c3.x, r.ox, r.ix, tn, tf);
-                        axis_planes4(__uint_as_float(c0.y), (c0.w >> 8) & 0xFFu, c2.y, c3.y, r.oy, r.iy, tn, tf);
-                        axis_planes4(__uint_as_float(c0.z), (c0.w >> 16) & 0xFFu, c2.z, c3.z, r.oz, r.iz, tn, tf);
+                        // entry distance clamped at 0 and exit distance clamped at the pruning limit (>= 0 whenever a hit is
+                        // still possible): "exit >= 0, entry <= exit, entry <= limit" becomes one comparison per slot
+                        float tn[4], tf[4], vn[4], vf[4], un[4], uf[4];
+                        axis_vals4(__uint_as_float(c0.x), c0.w & 0xFFu, c2.x, c3.x, r.ox, r.ix, vn, vf);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { tn[k] = fmaxf(vn[k], 0.f); tf[k] = fminf(vf[k], limit); }
+                        axis_vals4(__uint_as_float(c0.y), (c0.w >> 8) & 0xFFu, c2.y, c3.y, r.oy, r.iy, vn, vf);
+                        axis_vals4(__uint_as_float(c0.z), (c0.w >> 16) & 0xFFu, c2.z, c3.z, r.oz, r.iz, un, uf);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { tn[k] = max3f(tn[k], vn[k], un[k]); tf[k] = min3f(tf[k], vf[k], uf[k]); }
                         const uint32_t used = 0x5u | ((flags & 1u) ? 0u : 2u) | ((flags & 2u) ? 0u : 8u);  // slots 1 / 3 exist iff L / R is inner
                         float key[4];
                         uint32_t wd[4];
@@ -840,10 +850,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         wd[2] = (c1.w + 1u - ((flags >> 1) & 1u)) | ((flags & 0x20u) ? kLeafBit : 0u);
                         wd[3] = c3.w | ((flags & 0x40u) ? kLeafBit : 0u);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const bool h = ((used >> k) & 1u) && tf[k] >= 0.f && tn[k] <= tf[k] && !(tn[k] > limit);
-                            key[k] = h ? tn[k] : INFINITY;
-                        }
+                        for (int k = 0; k < 4; ++k) key[k] = (((used >> k) & 1u) && tn[k] <= tf[k]) ? tn[k] : INFINITY;
                         auto cswap = [&](int i, int j) {
                             const bool sw = key[j] < key[i];
                             const float ki = key[i], kj = key[j];
@@ -852,6 +859,15 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                             wd[i] = sw ? wj : wi; wd[j] = sw ? wi : wj;
                         };
                         cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                        if (kPrefetch & 12) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const bool lf = (wd[k] & kLeafBit) != 0u;
+                                // bit 2: leaf records found by this step; bit 3: inner records stacked by it
+                                if (key[k] < INFINITY && ((lf && (kPrefetch & 4)) || (!lf && k > 0 && (kPrefetch & 8))))
+                                    prefetch_l2(A.pairs + (size_t)(wd[k] & ~kLeafBit) * 4);
+                            }
+                        }
                         if (key[3] < INFINITY) push_far(key[3], wd[3]);
                         if (key[2] < INFINITY) push_far(key[2], wd[2]);
                         if (key[1] < INFINITY) push_far(key[1], wd[1]);
