@@ -102,8 +102,8 @@ struct rtr_bvh {
 //     w7      flat index of the right child (the left child is p + 1: DFS pre-order, scene.cpp:189-199)
 //   inner node p, second 32 bytes (the "wide step", one more 256-bit load): four slots on the SAME grid --
 //     slot 0 / 1 = the children of L (slot 0 = L itself and slot 1 unused when L is a leaf), slot 2 / 3 = those of R
-//     w8..w10   per axis the byte quadruple (S0lo, S0hi, S1lo, S1hi);  w11  flat index of slot 1
-//     w12..w14  per axis the byte quadruple (S2lo, S2hi, S3lo, S3hi);  w15  flat index of slot 3
+//     w8..w10   per axis the byte quadruple (S0lo, S0hi, S1lo, S1hi);  w11  flat index of slot 1 (bit 31: it is a leaf)
+//     w12..w14  per axis the byte quadruple (S2lo, S2hi, S3lo, S3hi);  w15  flat index of slot 3 (bit 31: it is a leaf)
 //     (slot 0 is at p + 2, or p + 1 when L is a leaf; slot 2 at right + 1, or right when R is a leaf)
 //     flags bit3..bit6: slot 0..3 is a leaf; bit7: the second half is usable
 //   leaf p (64 bytes, two 256-bit loads):

@@ -763,7 +763,8 @@ pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* _
     bool ok = true;
     uint4 o2, o3;
     trav_encode_quads(make_float4(__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z), __uint_as_float(m1.x)),
-                      make_float2(__uint_as_float(m1.y), __uint_as_float(m1.z)), lo, hi, idx[1], idx[3], o2, o3, ok);
+                      make_float2(__uint_as_float(m1.y), __uint_as_float(m1.z)), lo, hi,
+                      idx[1] | ((leaf_bits & 2u) ? 0x80000000u : 0u), idx[3] | ((leaf_bits & 8u) ? 0x80000000u : 0u), o2, o3, ok);
     uint4* rec = pairs + (size_t)i * 4;
     uint32_t w3 = rec[0].w;
     if (ok && !((w3 >> 24) & 4u)) w3 |= (0x80u | (leaf_bits << 3)) << 24;

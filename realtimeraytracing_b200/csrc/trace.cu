@@ -552,6 +552,9 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #ifndef RTR_WIDE
 #define RTR_WIDE 1
 #endif
+#ifndef RTR_SORT_LEVEL
+#define RTR_SORT_LEVEL 5   // exchanges of the four-slot ordering network: 5 = sorted, 3 = only the nearest is exact
+#endif
 constexpr bool kWide = RTR_WIDE != 0;
 template <int LEVEL> __device__ __forceinline__ void prefetch_child(const void* p) {
     if (LEVEL == 1) prefetch_l2(p);
@@ -846,9 +849,9 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         float key[4];
                         uint32_t wd[4];
                         wd[0] = (a + 2u - (flags & 1u)) | ((flags & 0x08u) ? kLeafBit : 0u);
-                        wd[1] = c2.w | ((flags & 0x10u) ? kLeafBit : 0u);
+                        wd[1] = c2.w;  // slots 1 and 3 carry their leaf bit in the stored index
                         wd[2] = (c1.w + 1u - ((flags >> 1) & 1u)) | ((flags & 0x20u) ? kLeafBit : 0u);
-                        wd[3] = c3.w | ((flags & 0x40u) ? kLeafBit : 0u);
+                        wd[3] = c3.w;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) key[k] = (((used >> k) & 1u) && tn[k] <= tf[k]) ? tn[k] : INFINITY;
                         auto cswap = [&](int i, int j) {
@@ -858,7 +861,9 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                             key[i] = sw ? kj : ki; key[j] = sw ? ki : kj;
                             wd[i] = sw ? wj : wi; wd[j] = sw ? wi : wj;
                         };
-                        cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                        cswap(0, 1); cswap(2, 3); cswap(0, 2);
+                        if (RTR_SORT_LEVEL >= 4) cswap(1, 3);
+                        if (RTR_SORT_LEVEL >= 5) cswap(1, 2);
                         if (kPrefetch & 12) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
