@@ -873,9 +873,18 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                                     prefetch_l2(A.pairs + (size_t)(wd[k] & ~kLeafBit) * 4);
                             }
                         }
-                        if (key[3] < INFINITY) push_far(key[3], wd[3]);
-                        if (key[2] < INFINITY) push_far(key[2], wd[2]);
-                        if (key[1] < INFINITY) push_far(key[1], wd[1]);
+                        if (sp + 3 <= kSmemStack) {  // the usual case: no overflow checks per entry
+#pragma unroll
+                            for (int k = 3; k >= 1; --k)
+                                if (key[k] < INFINITY) {
+                                    s_stack[0][sp][threadIdx.x] = __float_as_uint(key[k]); s_stack[1][sp][threadIdx.x] = wd[k];
+                                    ++sp;
+                                }
+                        } else {
+                            if (key[3] < INFINITY) push_far(key[3], wd[3]);
+                            if (key[2] < INFINITY) push_far(key[2], wd[2]);
+                            if (key[1] < INFINITY) push_far(key[1], wd[1]);
+                        }
                         if (key[0] < INFINITY) a = wd[0];
                         else need_pop = true;
                         hl = hr = false;
