@@ -552,6 +552,12 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #ifndef RTR_WIDE
 #define RTR_WIDE 1
 #endif
+// A leaf met while the parking slot is free is parked in the same step (and the walk pops on) instead of costing a
+// walk step of its own.
+#ifndef RTR_EAGER_PARK
+#define RTR_EAGER_PARK 1
+#endif
+constexpr bool kEagerPark = RTR_EAGER_PARK != 0;
 #ifndef RTR_SORT_LEVEL
 #define RTR_SORT_LEVEL 5   // exchanges of the four-slot ordering network: 5 = sorted, 3 = only the nearest is exact
 #endif
@@ -708,6 +714,11 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             if (sp < kSmemStack) { te = __uint_as_float(s_stack[0][sp][threadIdx.x]); w = s_stack[1][sp][threadIdx.x]; }
             else { te = stack_t[sp - kSmemStack]; w = stack_a[sp - kSmemStack]; }
             if (te > limit) continue;
+            if (kEagerPark && (w & kLeafBit) != 0u && pend_node == RTR_NONE) {  // a leaf and the parking slot is free: park it, pop on
+                pend_node = w & ~kLeafBit;
+                if (kPrefetch & 2) prefetch_l2(A.pairs + (size_t)pend_node * 4);
+                continue;
+            }
             a = w;
             break;
         }
@@ -885,8 +896,13 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                             if (key[2] < INFINITY) push_far(key[2], wd[2]);
                             if (key[1] < INFINITY) push_far(key[1], wd[1]);
                         }
-                        if (key[0] < INFINITY) a = wd[0];
-                        else need_pop = true;
+                        if (key[0] < INFINITY) {
+                            if (kEagerPark && (wd[0] & kLeafBit) != 0u && pend_node == RTR_NONE) {  // park the nearest slot right away
+                                pend_node = wd[0] & ~kLeafBit;
+                                if (kPrefetch & 2) prefetch_l2(A.pairs + (size_t)pend_node * 4);
+                                need_pop = true;
+                            } else a = wd[0];
+                        } else need_pop = true;
                         hl = hr = false;
                     } else {
                     if (st & 0x40000u) {
