@@ -558,6 +558,9 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #define RTR_EAGER_PARK 1
 #endif
 constexpr bool kEagerPark = RTR_EAGER_PARK != 0;
+#ifndef RTR_REPARK
+#define RTR_REPARK 0
+#endif
 #ifndef RTR_SORT_LEVEL
 #define RTR_SORT_LEVEL 5   // exchanges of the four-slot ordering network: 5 = sorted, 3 = only the nearest is exact
 #endif
@@ -980,6 +983,10 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         }
                     }
                     pend_node = RTR_NONE;
+                    if (RTR_REPARK && a != kDry && (a & kLeafBit) != 0u) {  // the leaf this lane was blocked on moves into the slot
+                        pend_node = a & ~kLeafBit;
+                        pop_next();
+                    }
                 }
             }
             if (want_fin || (movable == 0u && m_blocked == 0u)) break;
