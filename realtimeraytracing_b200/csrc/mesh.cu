@@ -371,7 +371,7 @@ int rtr_mesh_primitive(int which, uint32_t model_id, rtr_triangle* out, uint64_t
     *out_n = n;
     if (n > cap || (n && !out)) return rtr_set_error(nullptr, RTR_E_INVALID, "mesh_primitive: %llu triangles, room for %llu",
                                                      (unsigned long long)n, (unsigned long long)cap);
-    memset(out, 0, n * sizeof(rtr_triangle));
+    if (n) memset(out, 0, n * sizeof(rtr_triangle));
     for (uint64_t i = 0; i < n; ++i) {
         float* dst[3] = {out[i].p0, out[i].p1, out[i].p2};
         for (int k = 0; k < 3; ++k) {

@@ -284,3 +284,32 @@ def test_bvh_depth_overlay_equals_the_shaders_loop(ctx, oracle, depth):
         assert np.array_equal(img, oracle.shade(hits, tris, meshes, mats, wireframe=True, bvh_rgba=exp))
     finally:
         bvh.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 31, 64])
+def test_tiny_trees_through_the_wide_step(ctx, oracle, n):
+    """Every shape of the four-slot record near the root: a leaf root, leaf children that occupy a slot as themselves,
+    one inner and one leaf child, full grandchildren (bvh.cuh, second record half)."""
+    tris, meshes, L = scenes.soup(n, seed=77 + n)
+    bvh, flat = build_pair(ctx, oracle, tris, meshes)
+    try:
+        W, H = 96, 64
+        cam = synth.soup_camera(L, W, H)
+        got = bvh.trace_primary(cam, W, H, W, H)
+        exp = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
+        assert_hits_equal(got, exp, "n=%d" % n)
+        # incoherent rays from inside and outside the scene, closest hit and any hit with a distance limit
+        rng = np.random.default_rng(n)
+        rays = np.zeros(4096, dtype=RAY)
+        rays["o"][:, :3] = rng.uniform(-1.5 * L, 1.5 * L, (rays.size, 3)).astype(np.float32)
+        rays["o"][:, 3] = 1.0
+        d = rng.normal(size=(rays.size, 3))
+        rays["d"][:, :3] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        got = bvh.trace_rays(rays)
+        exp = oracle.trace_rays(flat, tris, meshes, rays)
+        assert_hits_equal(got, exp, "n=%d random rays" % n)
+        tmax = rng.uniform(-0.2 * L, 2.0 * L, size=rays.size).astype(np.float32)  # some limits are negative: nothing can hit
+        occ = bvh.trace_rays(rays, any_hit=True, t_max=tmax)
+        assert np.array_equal(occ["did_hit"], oracle.any_hit(flat, tris, meshes, rays, tmax))
+    finally:
+        bvh.close()
