@@ -607,9 +607,9 @@ struct JobDesc {
 // distance, and the best hit is (t, leaf index) only: its barycentrics and triangle id are regenerated by one
 // more ray_triangle when the ray finishes.
 //
-// Inner nodes are expanded from the 32-byte compressed record (bvh.cuh) -- ONE 256-bit load per lane where
-// two 48-byte nodes took six 128-bit loads and the uncompressed pair two 256-bit ones; the kernel is bound by
-// L1 wavefronts of exactly these divergent loads.  The compressed child boxes are supersets, evaluated here
+// Inner nodes are expanded from the compressed record (bvh.cuh) -- 256-bit loads where two 48-byte nodes took six
+// 128-bit loads; the kernel was bound by L1 wavefronts of exactly these divergent loads, then by the number of
+// dependent fetches per ray (hence the wide step below).  The compressed child boxes are supersets, evaluated here
 // with an error margin that also covers the rounding of the reference's own slab test, so that
 //     reference slab test passes on the exact box  ==>  compressed test passes            (*)
 // and the entry distance computed here is a lower bound of the reference's.  With the node origin c, grid
@@ -623,6 +623,17 @@ struct JobDesc {
 // reference's slab test on the decoded superset boxes instead (monotone in the box, hence (*) again).  A
 // leaf is then tested exactly as in the reference: slab test on its own exact box, ray/triangle on its vertices, both
 // from its 64-byte record.
+//
+// Wide step (RTR_WIDE): the second half of an inner record holds the boxes of the node's four GRANDCHILD slots on
+// the same grid (same origin, same steps, bytes 0..255), so the derivation above applies to them word for word; a
+// slot's box is a superset of the grandchild's exact box, which contains every leaf box below it, hence (*) holds
+// for every leaf under a slot that is skipped.  One step tests the four slots, orders the hit ones by entry distance
+// and stacks up to three: half the dependent fetches per ray.  The step clamps the entry distance at 0 and the exit
+// distance at the pruning limit before comparing them -- "exit >= 0 and entry <= exit and entry <= limit" in one
+// comparison; the limit is >= 0 whenever a hit is still possible (it bounds a hit distance, and hits have t > 0),
+// and a negative limit (an any-hit ray with t_max < 0) can only reject.  Rays on the exact-slab path and nodes whose
+// second half could not be encoded keep to pair steps; the two kinds of step can alternate freely along a path,
+// every inner record serves both.
 __global__ void __launch_bounds__(kTraceBlock, RTR_TRACE_MIN_CTAS)
 trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDesc jd,
                         unsigned long long* __restrict__ rays_traced, uint32_t* __restrict__ sm_table, uint32_t reserve) {
