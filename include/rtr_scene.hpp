@@ -277,6 +277,28 @@ inline rtr_ctx* defaultContext(int device = 0) {
     return ctx;
 }
 
+// cr::MaterialGPU / cr::Material (srcCommon/scene/pbr/material.hpp:9-29, material.cpp): a colour per material
+struct MaterialGPU {
+    vec4 _Color = {1.f, 1.f, 1.f, 1.f};
+};
+static_assert(sizeof(MaterialGPU) == sizeof(rtr_material), "MaterialGPU layout");
+class Material {
+    static uint32_t& idGenerator() { static uint32_t next = 0; return next; }
+    uint32_t _Id = 0;
+
+public:
+    static const size_t MAX_NB_MATERIALS = 2 << 15;
+    MaterialGPU _InternalStruct{};
+    explicit Material(const vec4& color) : _Id(idGenerator()++) { _InternalStruct._Color = color; }
+    Material() : _Id(idGenerator()++) {  // material.cpp:17-27: three rand() draws
+        const float r = static_cast<float>(std::rand()) / static_cast<float>(RAND_MAX);
+        const float g = static_cast<float>(std::rand()) / static_cast<float>(RAND_MAX);
+        const float b = static_cast<float>(std::rand()) / static_cast<float>(RAND_MAX);
+        _InternalStruct._Color = vec4{r, g, b, 1.f};
+    }
+    uint32_t getId() const { return _Id; }
+};
+
 // cr::Triangle (triangle.hpp:16-34, triangle.cpp)
 class Triangle {
 public:
