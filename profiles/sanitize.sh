@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over a small end-to-end pass (sort, rebuild, flatten, default + reference-order traversal, shading)
 mkdir -p gpurun_out
-python -m realtimeraytracing_b200.build --force > gpurun_out/build.log 2>&1
+python -m realtimeraytracing_b200.build > gpurun_out/build.log 2>&1
 cat > /tmp/san_driver.py <<'PY'
 import sys, numpy as np
 sys.path.insert(0, '.')
@@ -22,10 +22,17 @@ with capi.Context(0) as ctx:
     rgba, hits, nr = bvh.render(cam, W, H, W, H, bounces=2, shadow=True, light=(0.0, 2 * L, -2 * L))
     mats = np.array([[1, 1, 1, 1]], np.float32)
     img = ctx.shade(a, tris, meshes, mats, wireframe=True)
+    ov = bvh.depth_overlay(cam, W, H, 5)
+    img = ctx.shade(a, tris, meshes, mats, bvh_rgba=ov)
     bvh.close()
+    for n in (1, 2, 3, 5, 9):  # every slot shape of the wide record near the root
+        t2, m2, L2 = synth.triangle_soup(n)
+        small = capi.Bvh(ctx).build(t2, m2)
+        small.trace_primary(synth.soup_camera(L2, 32, 32), 32, 32, 32, 32)
+        small.close()
 print("driver ok")
 PY
-for tool in memcheck racecheck; do
+for tool in ${TOOLS:-memcheck racecheck}; do
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|driver ok|Error|hazard" gpurun_out/sanitizer_$tool.log | head -12
 done
