@@ -591,6 +591,14 @@ def main():
             frame_e2e()
         e2e_ms, e2e_rays, _ = timed(frame_e2e, e2e_steps)
     e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+    # a ray that ran out of traversal stack would have dropped subtrees: such a run is not a measurement
+    for k, used in enumerate(bvhs if pipelined else [bvh]):
+        try:
+            dropped = used.stack_overflows()
+        except capi.RtrError:  # a BVH object this rank never filled
+            continue
+        if dropped:
+            raise RuntimeError("rank %d, BVH %d: %d rays ran out of traversal stack" % (rank, k, dropped))
     h2d = n * TRIANGLE.itemsize + MESH.itemsize + 284
     d2h = H * W * 16
 

@@ -266,6 +266,12 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* c
                            uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
                            float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
+/* The shader's private stack is 1024 entries deep (raytracer.glsl:251), the kernels' 128.  A ray that runs out of it
+ * drops subtrees; the kernels count such rays.  rtr_trace_primary / rtr_trace_rays / rtr_render (host pointers) fail
+ * with RTR_E_UNSUPPORTED instead of returning an incomplete frame; after the asynchronous _dev forms, this call waits
+ * for the ctx stream and returns the count since the last call (and clears it).  0 on every scene measured so far. */
+int rtr_bvh_stack_overflows(const rtr_bvh* bvh, uint32_t* count_out);
+
 /* ---- shading: getColor + main of raytracer.glsl (:159-179, :299-331), the reference's rgba32f frame from the hit
  * records of rtr_trace_primary.  value = (0,0,0,1) -- or, with RTR_SHADE_BVH (uIsBVHDisplayed), the pixel's colour
  * from rtr_bvh_depth_overlay; a hit adds the colour of the material of the triangle's model; with

@@ -41,7 +41,7 @@ SYMBOLS = [
     "rtr_bvh_depth_overlay", "rtr_bvh_depth_overlay_dev",
     "rtr_obj_load", "rtr_obj_parse", "rtr_obj_free", "rtr_mesh_primitive", "rtr_mesh_init", "rtr_mesh_set_model",
     "rtr_mesh_set_position", "rtr_mesh_set_scale", "rtr_mesh_set_rotation", "rtr_mesh_set_material",
-    "rtr_triangle_centroid",
+    "rtr_triangle_centroid", "rtr_bvh_stack_overflows",
 ]
 
 
@@ -152,6 +152,7 @@ def load_library():
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     f32 = C.c_float
+    L.rtr_bvh_stack_overflows.argtypes = [vp, C.POINTER(u32)]
     L.rtr_obj_load.argtypes = [C.c_char_p, u32, pp, C.POINTER(u64)]
     L.rtr_obj_parse.argtypes = [C.c_char_p, u64, u32, pp, C.POINTER(u64)]
     L.rtr_obj_free.argtypes = [vp]
@@ -549,6 +550,12 @@ class Bvh:
         out = np.zeros(self.nb_triangles, dtype=np.uint32)
         self.ctx.check(self.lib.rtr_bvh_morton_codes(self.handle, _ptr(out)))
         return out
+
+    def stack_overflows(self) -> int:
+        """Rays that ran out of traversal stack since the last call (waits for the stream); see rtr.h."""
+        n = C.c_uint32()
+        self.ctx.check(self.lib.rtr_bvh_stack_overflows(self.handle, C.byref(n)))
+        return n.value
 
     def depth_overlay(self, camera, width, height, depth: int, denom_w=0, denom_h=0) -> np.ndarray:
         """bvhColor of the shader's traversal (uDepthDisplayBVH = depth) per pixel, [height*width, 4]."""

@@ -748,6 +748,30 @@ static int order_ok(rtr_ctx* ctx, const rtr_bvh* b, uint32_t flags) {
     return RTR_OK;
 }
 
+// A ray that runs out of traversal stack (128 entries; the shader's is 1024 deep, raytracer.glsl:251) drops subtrees:
+// the kernels count such rays in TraceParams::stack_overflows.  The host-pointer entry points synchronise anyway and
+// refuse to hand such a frame back; callers of the asynchronous _dev forms ask with rtr_bvh_stack_overflows.
+static int fetch_overflows(rtr_ctx* ctx, const rtr_bvh* b, uint32_t* host_count) {
+    RTR_CUDA(ctx, cudaMemcpyAsync(host_count, &b->tparams->stack_overflows, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return RTR_OK;
+}
+static int refuse_overflows(rtr_ctx* ctx, const rtr_bvh* b, uint32_t count, const char* what) {
+    if (count == 0u) return RTR_OK;
+    cudaMemsetAsync(&b->tparams->stack_overflows, 0, sizeof(uint32_t), ctx->stream);
+    return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "%s: %u ray(s) ran out of traversal stack (128 entries); the frame is incomplete", what, count);
+}
+
+int rtr_bvh_stack_overflows(const rtr_bvh* b, uint32_t* count_out) {
+    if (!b) return RTR_E_INVALID;
+    rtr_ctx* ctx = b->ctx;
+    if (!count_out) return rtr_set_error(ctx, RTR_E_INVALID, "stack_overflows: NULL output");
+    if (!b->built || !b->tparams) return rtr_set_error(ctx, RTR_E_STATE, "stack_overflows: the BVH has not been built");
+    RTR_CHECK(fetch_overflows(ctx, b, count_out));
+    RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->stack_overflows, 0, sizeof(uint32_t), ctx->stream));
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTR_OK;
+}
+
 int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
                           uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t flags, rtr_hit* hits_dev) {
     RTR_CHECK(trace_args_ok(ctx, b, cam));
@@ -768,8 +792,10 @@ int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uin
     auto body = [&]() -> int {
         RTR_CHECK(rtr_trace_primary_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, flags, d_hits));
         RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t overflows = 0;
+        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return RTR_OK;
+        return refuse_overflows(ctx, b, overflows, "trace_primary");
     };
     const int r = body();
     staging_end(&st);
@@ -801,8 +827,10 @@ int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t
         if (t_max) RTR_CUDA(ctx, cudaMemcpyAsync(d_tmax, t_max, tb, cudaMemcpyHostToDevice, ctx->stream));
         RTR_CHECK(rtr_trace_rays_launch(ctx, b, d_rays, n_rays, any_hit, d_tmax, flags, d_hits));
         RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, hb, cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t overflows = 0;
+        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return RTR_OK;
+        return refuse_overflows(ctx, b, overflows, "trace_rays");
     };
     const int r = body();
     staging_end(&st);
@@ -961,8 +989,10 @@ int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t w
         if (rgba_out) RTR_CUDA(ctx, cudaMemcpyAsync(rgba_out, d_rgba, cb, cudaMemcpyDeviceToHost, ctx->stream));
         if (hits_out) RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, hb, cudaMemcpyDeviceToHost, ctx->stream));
         if (rays_traced) RTR_CUDA(ctx, cudaMemcpyAsync(rays_traced, d_rays, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t overflows = 0;
+        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return RTR_OK;
+        return refuse_overflows(ctx, b, overflows, "render");
     };
     const int r = body();
     staging_end(&st);

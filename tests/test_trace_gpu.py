@@ -41,6 +41,12 @@ def test_primary_rays_soup(ctx, oracle, flags):
         exp = oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H)
         assert exp["did_hit"].mean() > 0.3
         assert_hits_equal(got, exp, "soup flags=%d" % flags)
+        hits_dev = ctx.dev_alloc(got.nbytes)
+        try:  # the asynchronous form reports rays that ran out of stack on request (the host form refuses the frame)
+            bvh.trace_primary_dev(cam, W, H, hits_dev, W, H, flags=flags)
+            assert bvh.stack_overflows() == 0
+        finally:
+            ctx.dev_free(hits_dev)
     finally:
         bvh.close()
 
