@@ -22,7 +22,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -108,11 +110,12 @@ inline const char* skip_to_slash_or_blank(const char* p, const char* le) {
 }
 
 // One corner "v", "v/vt", "v//vn" or "v/vt/vn".  Index 0 (or no number) in any present field is an error, like
-// tinyobjloader's fixIndex; only the position index is kept.  nv = positions read so far (for relative indices).
-bool read_corner(const char*& p, const char* le, int nv, int* v_idx) {
+// tinyobjloader's fixIndex; only the position index is kept: v > 0 names vertex v - 1 of the file, v < 0 the |v|-th
+// last vertex read before this statement.
+bool read_corner(const char*& p, const char* le, int* v_raw) {
     const int v = bounded_atoi(p, le);
     if (v == 0) return false;
-    *v_idx = v > 0 ? v - 1 : nv + v;
+    *v_raw = v;
     p = skip_to_slash_or_blank(p, le);
     if (p >= le || *p != '/') return true;
     ++p;
@@ -131,8 +134,24 @@ bool read_corner(const char*& p, const char* le, int nv, int* v_idx) {
     return true;
 }
 
+// What one thread extracts from its piece of the text (whole lines).  Vertex references stay relative to the piece:
+// a corner is v - 1 (absolute, >= 0) or kRelative + (vertices of the piece read so far) + v for v < 0, resolved once
+// the number of vertices in the pieces before it is known.
+constexpr long long kRelative = 1ll << 40;
+struct ObjPiece {
+    const char* begin = nullptr;
+    const char* end = nullptr;
+    std::vector<float> pos;            // x y z per `v`
+    std::vector<long long> corners;    // see above, faces back to back
+    std::vector<uint32_t> face_end;    // end offset into `corners` per face
+    struct Flush { uint32_t faces_before, vertices_before; };
+    std::vector<Flush> flushes;        // `g` / `o` statements: where pending faces are triangulated
+    uint64_t lines = 0;
+    uint64_t bad_line = 0;             // 1-based line (within the piece) of the first malformed `f`, 0 = none
+};
+
 struct ObjReader {
-    std::vector<float> pos;         // x y z per `v`
+    std::vector<float> pos;         // x y z per `v`, the whole file
     std::vector<int> corners;       // position indices of the pending faces, back to back
     std::vector<uint32_t> face_end; // end offset into `corners` per pending face
     std::vector<int> tri;           // emitted triangles, three position indices each
@@ -149,15 +168,14 @@ bool inside_triangle(const float x[3], const float y[3], float tx, float ty) {
 // Splits one face into triangles the way tinyobjloader 1.2.0 does with `triangulate` on (exportFaceGroupToShape):
 // a triangle passes through; a larger polygon is projected on the two axes chosen from its first non-degenerate
 // corner and ear-clipped, starting each search where the last ear was cut, giving up after ten trips around the
-// polygon (the vertices left over are dropped).  `pos` is the vertex array AS READ SO FAR: corners that point beyond
-// it are treated as that version treats them (skipped in the setup loops, (0,0) in the ear test).
-void split_face(const int* idx, size_t n, const std::vector<float>& pos, std::vector<int>& tri) {
+// polygon (the vertices left over are dropped).  pos[0, nf) is the vertex array AS READ SO FAR: corners that point
+// beyond it are treated as that version treats them (skipped in the setup loops, (0,0) in the ear test).
+void split_face(const int* idx, size_t n, const float* pos, size_t nf, std::vector<int>& tri) {
     if (n < 3) return;
     if (n == 3) {
         tri.insert(tri.end(), idx, idx + 3);
         return;
     }
-    const size_t nf = pos.size();
     auto ok = [&](int vi, size_t comp) { return static_cast<size_t>(vi) * 3 + comp < nf; };  // negative -> huge -> false
     size_t ax0 = 1, ax1 = 2;
     for (size_t k = 0; k < n; ++k) {
@@ -221,23 +239,25 @@ void split_face(const int* idx, size_t n, const std::vector<float>& pos, std::ve
     if (rest.size() == 3) tri.insert(tri.end(), rest.begin(), rest.end());
 }
 
-void flush_faces(ObjReader& r) {
+// triangulates the pending faces against the first `visible_vertices` vertices of the file
+void flush_faces(ObjReader& r, size_t visible_vertices) {
     uint32_t begin = 0;
     for (uint32_t end : r.face_end) {
-        split_face(r.corners.data() + begin, end - begin, r.pos, r.tri);
+        split_face(r.corners.data() + begin, end - begin, r.pos.data(), visible_vertices * 3, r.tri);
         begin = end;
     }
     r.corners.clear();
     r.face_end.clear();
 }
 
-int parse_obj(const char* text, size_t len, uint32_t model_id, rtr_triangle** out_tris, uint64_t* out_n) {
-    ObjReader r;
-    r.pos.reserve(len / 24);
-    r.tri.reserve(len / 24);
-    const char* p = text;
-    const char* const eof = text + len;
-    uint64_t line_no = 0;
+// the statements of one piece of the text (runs on its own thread)
+void parse_piece(ObjPiece& pc) {
+    const size_t len = static_cast<size_t>(pc.end - pc.begin);
+    pc.pos.reserve(len / 24);
+    pc.corners.reserve(len / 16);
+    pc.face_end.reserve(len / 48);
+    const char* p = pc.begin;
+    const char* const eof = pc.end;
     while (p < eof) {
         // a line ends at LF, CR or CR LF; a NUL byte hides the rest of its line
         const char* nl = p;
@@ -246,7 +266,7 @@ int parse_obj(const char* text, size_t len, uint32_t model_id, rtr_triangle** ou
         if (next < eof) next += (*next == '\r' && next + 1 < eof && next[1] == '\n') ? 2 : 1;
         const char* le = static_cast<const char*>(memchr(p, 0, static_cast<size_t>(nl - p)));
         if (!le) le = nl;
-        ++line_no;
+        ++pc.lines;
         const char* t = p;
         p = next;
         while (t < le && is_blank(*t)) ++t;
@@ -256,22 +276,23 @@ int parse_obj(const char* text, size_t len, uint32_t model_id, rtr_triangle** ou
         if (c0 == 'v' && is_blank(c1)) {
             t += 2;
             const float x = next_real(t, le), y = next_real(t, le), z = next_real(t, le);
-            r.pos.push_back(x); r.pos.push_back(y); r.pos.push_back(z);
+            pc.pos.push_back(x); pc.pos.push_back(y); pc.pos.push_back(z);
         } else if (c0 == 'f' && is_blank(c1)) {
             t += 2;
             while (t < le && is_blank(*t)) ++t;
-            const int nv = static_cast<int>(r.pos.size() / 3);
+            const long long nv = static_cast<long long>(pc.pos.size() / 3);
             while (t < le) {
-                int vi;
-                if (!read_corner(t, le, nv, &vi))
-                    return rtr_set_error(nullptr, RTR_E_INVALID, "obj: line %llu: bad `f` corner (index 0 or not a number)",
-                                         static_cast<unsigned long long>(line_no));
-                r.corners.push_back(vi);
+                int v;
+                if (!read_corner(t, le, &v)) {
+                    pc.bad_line = pc.lines;  // tinyobjloader refuses the file here: nothing after this line matters
+                    return;
+                }
+                pc.corners.push_back(v > 0 ? static_cast<long long>(v) - 1 : kRelative + nv + v);
                 while (t < le && is_blank(*t)) ++t;
             }
-            r.face_end.push_back(static_cast<uint32_t>(r.corners.size()));
+            pc.face_end.push_back(static_cast<uint32_t>(pc.corners.size()));
         } else if ((c0 == 'g' || c0 == 'o') && is_blank(c1)) {
-            flush_faces(r);
+            pc.flushes.push_back({static_cast<uint32_t>(pc.face_end.size()), static_cast<uint32_t>(pc.pos.size() / 3)});
         }
         // `usemtl` is not a flush point here.  tinyobjloader flushes when the material ID changes, and IDs come from
         // an MTL file it resolves against the working directory (Mesh::load passes no base directory, mesh.cpp:192):
@@ -279,24 +300,128 @@ int parse_obj(const char* text, size_t len, uint32_t model_id, rtr_triangle** ou
         // Only a polygon that names vertices defined after it could tell the difference.
         // vn, vt, s, t, mtllib and unknown statements do not reach Mesh::load's output
     }
-    flush_faces(r);
+}
 
+// pieces of whole lines, about equal in bytes; a CR LF pair is never split
+std::vector<ObjPiece> cut_text(const char* text, size_t len, size_t pieces) {
+    std::vector<ObjPiece> out(pieces ? pieces : 1);
+    const char* const eof = text + len;
+    const char* p = text;
+    for (size_t k = 0; k < out.size(); ++k) {
+        out[k].begin = p;
+        const char* q = (k + 1 == out.size()) ? eof : text + len / out.size() * (k + 1);
+        if (q < p) q = p;
+        while (q < eof && q > text && q[-1] != '\n' && q[-1] != '\r') ++q;
+        if (q < eof && q > text && q[-1] == '\r' && *q == '\n') ++q;
+        if (q == text && k + 1 != out.size()) q = p;
+        out[k].end = p = q;
+    }
+    return out;
+}
+
+size_t obj_threads(size_t len) {
+    if (const char* env = getenv("RTR_OBJ_THREADS")) {  // tests cut small files into many pieces with this
+        const long n = atol(env);
+        if (n >= 1) return static_cast<size_t>(n > 256 ? 256 : n);
+    }
+    size_t n = std::thread::hardware_concurrency();
+    if (n == 0) n = 1;
+    if (n > 32) n = 32;
+    const size_t by_size = len / (1u << 20);  // a piece is worth a thread from about 1 MB
+    return by_size < 1 ? 1 : (by_size < n ? by_size : n);
+}
+
+// fn(k) for k in [0, n) on n threads (the caller's included)
+template <class F> void run_on_threads(size_t n, F fn) {
+    std::vector<std::thread> workers;
+    for (size_t k = 1; k < n; ++k) workers.emplace_back(fn, k);
+    fn(static_cast<size_t>(0));
+    for (std::thread& w : workers) w.join();
+}
+
+int parse_obj(const char* text, size_t len, uint32_t model_id, rtr_triangle** out_tris, uint64_t* out_n) {
+    // 1. the text, in parallel: numbers and corner lists of every piece
+    std::vector<ObjPiece> pieces = cut_text(text, len, obj_threads(len));
+    run_on_threads(pieces.size(), [&](size_t k) { parse_piece(pieces[k]); });
+    uint64_t lines_before = 0;
+    for (const ObjPiece& pc : pieces) {  // the first malformed `f` of the file, in file order
+        if (pc.bad_line)
+            return rtr_set_error(nullptr, RTR_E_INVALID, "obj: line %llu: bad `f` corner (index 0 or not a number)",
+                                 static_cast<unsigned long long>(lines_before + pc.bad_line));
+        lines_before += pc.lines;
+    }
+    // 2. in file order: vertex numbering, relative indices, flush points, polygons
+    ObjReader r;
+    size_t total_floats = 0, total_corners = 0;
+    for (const ObjPiece& pc : pieces) { total_floats += pc.pos.size(); total_corners += pc.corners.size(); }
+    r.pos.resize(total_floats);
+    r.tri.reserve(total_corners);
+    {
+        std::vector<size_t> at(pieces.size() + 1, 0);
+        for (size_t k = 0; k < pieces.size(); ++k) at[k + 1] = at[k] + pieces[k].pos.size();
+        run_on_threads(pieces.size(), [&](size_t k) {
+            if (!pieces[k].pos.empty()) memcpy(r.pos.data() + at[k], pieces[k].pos.data(), pieces[k].pos.size() * sizeof(float));
+        });
+    }
+    size_t vertices_before = 0;
+    for (const ObjPiece& pc : pieces) {
+        size_t next_flush = 0;
+        uint32_t begin = 0;
+        for (uint32_t f = 0; f <= pc.face_end.size(); ++f) {
+            while (next_flush < pc.flushes.size() && pc.flushes[next_flush].faces_before == f)
+                flush_faces(r, vertices_before + pc.flushes[next_flush++].vertices_before);
+            if (f == pc.face_end.size()) break;
+            const uint32_t end = pc.face_end[f];
+            if (end - begin == 3 && r.face_end.empty()) {  // a triangle with nothing pending before it passes straight through
+                for (uint32_t c = begin; c < end; ++c) {
+                    const long long v = pc.corners[c];
+                    r.tri.push_back(static_cast<int>(v >= kRelative / 2 ? v - kRelative + static_cast<long long>(vertices_before) : v));
+                }
+            } else {
+                for (uint32_t c = begin; c < end; ++c) {
+                    const long long v = pc.corners[c];
+                    r.corners.push_back(static_cast<int>(v >= kRelative / 2 ? v - kRelative + static_cast<long long>(vertices_before) : v));
+                }
+                r.face_end.push_back(static_cast<uint32_t>(r.corners.size()));
+            }
+            begin = end;
+        }
+        vertices_before += pc.pos.size() / 3;
+    }
+    flush_faces(r, vertices_before);
+
+    // 3. the records, in parallel again: every corner must name a vertex of the file (the reference reads out of bounds)
     const size_t nv = r.pos.size() / 3;
     const size_t nt = r.tri.size() / 3;
-    for (size_t i = 0; i < r.tri.size(); ++i)
-        if (r.tri[i] < 0 || static_cast<size_t>(r.tri[i]) >= nv)  // the reference reads out of bounds here
+    rtr_triangle* tris = static_cast<rtr_triangle*>(malloc((nt ? nt : 1) * sizeof(rtr_triangle)));
+    if (!tris) return rtr_set_error(nullptr, RTR_E_NOMEM, "obj: %zu triangles do not fit in host memory", nt);
+    const size_t parts = pieces.size();
+    std::vector<size_t> first_bad(parts, static_cast<size_t>(-1));
+    run_on_threads(parts, [&](size_t k) {
+        const size_t t0 = nt * k / parts, t1 = nt * (k + 1) / parts;
+        for (size_t i = t0; i < t1; ++i) {
+            rtr_triangle& out = tris[i];
+            memset(&out, 0, sizeof(out));
+            float* dst[3] = {out.p0, out.p1, out.p2};
+            for (int c = 0; c < 3; ++c) {
+                const int v = r.tri[3 * i + c];
+                if (v < 0 || static_cast<size_t>(v) >= nv) {
+                    if (first_bad[k] == static_cast<size_t>(-1)) first_bad[k] = 3 * i + c;
+                    continue;
+                }
+                const float* src = &r.pos[static_cast<size_t>(v) * 3];
+                dst[c][0] = src[0]; dst[c][1] = src[1]; dst[c][2] = src[2]; dst[c][3] = 1.f;
+            }
+            out.model_id = model_id;
+        }
+    });
+    for (size_t k = 0; k < parts; ++k)
+        if (first_bad[k] != static_cast<size_t>(-1)) {
+            const size_t i = first_bad[k];
+            free(tris);
             return rtr_set_error(nullptr, RTR_E_INVALID, "obj: triangle %zu names vertex %d of %zu", i / 3,
                                  r.tri[i] < 0 ? r.tri[i] : r.tri[i] + 1, nv);
-    rtr_triangle* tris = static_cast<rtr_triangle*>(calloc(nt ? nt : 1, sizeof(rtr_triangle)));
-    if (!tris) return rtr_set_error(nullptr, RTR_E_NOMEM, "obj: %zu triangles do not fit in host memory", nt);
-    for (size_t i = 0; i < nt; ++i) {
-        float* dst[3] = {tris[i].p0, tris[i].p1, tris[i].p2};
-        for (int k = 0; k < 3; ++k) {
-            const float* s = &r.pos[static_cast<size_t>(r.tri[3 * i + k]) * 3];
-            dst[k][0] = s[0]; dst[k][1] = s[1]; dst[k][2] = s[2]; dst[k][3] = 1.f;
         }
-        tris[i].model_id = model_id;
-    }
     *out_tris = tris;
     *out_n = nt;
     return RTR_OK;
