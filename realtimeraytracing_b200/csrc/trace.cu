@@ -530,23 +530,13 @@ inline uint32_t pixel_grid(uint32_t width, uint32_t rows) {
 constexpr uint32_t kLeafBatch = RTR_LEAF_BATCH;  // run the triangle step once this many lanes hold a parked leaf
 constexpr uint32_t kFinBatch = RTR_FIN_BATCH;    // shade/replace finished rays once this many lanes wait
 #ifndef RTR_PREFETCH
-#define RTR_PREFETCH 2   // bit 0: record of a stacked child (pair step), bit 1: record of a parked leaf, bits 2/3: wide step
+#define RTR_PREFETCH 2   // bit 0: record of a stacked child (pair step), bit 1: record of a parked leaf
 #endif
 constexpr int kPrefetch = RTR_PREFETCH;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // three-input min / max (FMNMX3, sm_100+); NaN operands are ignored like in fminf / fmaxf
 __device__ __forceinline__ float max3f(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 __device__ __forceinline__ float min3f(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// Records of the two children of the node being tested (0 = off, 1 = towards L2, 2 = towards L1).  The left child sits
-// at a + 1, so its prefetch leaves with the node's own load; the right child's index arrives with the record and its
-// prefetch overlaps the plane tests.
-#ifndef RTR_PF_LEFT
-#define RTR_PF_LEFT 0
-#endif
-#ifndef RTR_PF_RIGHT
-#define RTR_PF_RIGHT 0
-#endif
 // Wide step: test the four grandchild slots of the second record half (bvh.cuh) instead of the child pair -- half the
 // dependent fetches per ray.
 #ifndef RTR_WIDE
@@ -558,17 +548,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #define RTR_EAGER_PARK 1
 #endif
 constexpr bool kEagerPark = RTR_EAGER_PARK != 0;
-#ifndef RTR_REPARK
-#define RTR_REPARK 0
-#endif
-#ifndef RTR_SORT_LEVEL
-#define RTR_SORT_LEVEL 5   // exchanges of the four-slot ordering network: 5 = sorted, 3 = only the nearest is exact
-#endif
 constexpr bool kWide = RTR_WIDE != 0;
-template <int LEVEL> __device__ __forceinline__ void prefetch_child(const void* p) {
-    if (LEVEL == 1) prefetch_l2(p);
-    if (LEVEL == 2) prefetch_l1(p);
-}
 #ifndef RTR_WALK_STEPS
 #define RTR_WALK_STEPS 4
 #endif
@@ -849,12 +829,10 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                 } else {
                     // compressed child pair: one 256-bit load (LDG.E.256, sm_100+)
                     uint4 c0, c1;
-                    prefetch_child<RTR_PF_LEFT>(A.pairs + (size_t)a * 4 + 4);
                     ld_nc_256(A.pairs + (size_t)a * 4, c0, c1);
                     uint4 c2 = make_uint4(0u, 0u, 0u, 0u), c3 = c2;
                     const bool wide_ray = kWide && !(st & 0x40000u);
                     if (wide_ray) ld_nc_256(A.pairs + (size_t)a * 4 + 2, c2, c3);  // both halves in flight together
-                    prefetch_child<RTR_PF_RIGHT>(A.pairs + (size_t)c1.w * 4);
                     float tl = -INFINITY, fl = INFINITY, tr = -INFINITY, fr = INFINITY;
                     const uint32_t flags = c0.w >> 24;
                     bool hl, hr;
@@ -886,18 +864,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                             key[i] = sw ? kj : ki; key[j] = sw ? ki : kj;
                             wd[i] = sw ? wj : wi; wd[j] = sw ? wi : wj;
                         };
-                        cswap(0, 1); cswap(2, 3); cswap(0, 2);
-                        if (RTR_SORT_LEVEL >= 4) cswap(1, 3);
-                        if (RTR_SORT_LEVEL >= 5) cswap(1, 2);
-                        if (kPrefetch & 12) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const bool lf = (wd[k] & kLeafBit) != 0u;
-                                // bit 2: leaf records found by this step; bit 3: inner records stacked by it
-                                if (key[k] < INFINITY && ((lf && (kPrefetch & 4)) || (!lf && k > 0 && (kPrefetch & 8))))
-                                    prefetch_l2(A.pairs + (size_t)(wd[k] & ~kLeafBit) * 4);
-                            }
-                        }
+                        cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);  // a partial order is slower (+2..3 %)
                         if (sp + 3 <= kSmemStack) {  // the usual case: no overflow checks per entry
 #pragma unroll
                             for (int k = 3; k >= 1; --k)
@@ -994,10 +961,6 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         }
                     }
                     pend_node = RTR_NONE;
-                    if (RTR_REPARK && a != kDry && (a & kLeafBit) != 0u) {  // the leaf this lane was blocked on moves into the slot
-                        pend_node = a & ~kLeafBit;
-                        pop_next();
-                    }
                 }
             }
             if (want_fin || (movable == 0u && m_blocked == 0u)) break;
