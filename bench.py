@@ -182,7 +182,10 @@ def run_reference_arm(args):
         "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD, "sample": arm.describe()},
+        "config": {"workload": WORKLOAD if (args.tris, args.width, args.height, args.bounces) == (10_000_000, 3840, 2160, 2) else
+                   "%d-triangle soup, full BVH rebuild per frame + %dx%d primary + %d-bounce rays" % (
+                       args.tris, args.width, args.height, args.bounces),
+                   "sample": arm.describe()},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
