@@ -33,3 +33,16 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_our_arm_refuses_to_run_without_a_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--tris", "1000", "--width", "64", "--height", "32"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr and not r.stdout.strip()
