@@ -340,6 +340,13 @@ void rtr_mesh_set_material(rtr_mesh* m, uint32_t material_id);
 /* replaces cr::Triangle::getCentroid(triangle, model) (triangle.cpp:30-32), the point the Morton codes are taken of */
 void rtr_triangle_centroid(const rtr_triangle* t, const float model[16], float out[3]);
 
+/* replaces cr::Camera (srcCommon/scene/camera.{hpp,cpp}) for hosts that cannot include rtr_scene.hpp: the CameraGPU
+ * of a camera constructed like application.cpp:16-20 after replaying input events on it -- kind 0:
+ * ProcessMouseMovement(a, b); kind 1..6: processKeyboard(FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN with deltaTime a),
+ * _Accelerate = (b != 0).  Same code as cr::Camera of rtr_scene.hpp: bit-identical to the reference's getGpuData(). */
+int rtr_camera_gpu_data(const float eye[3], float aspect, float fov, float near_plane, float far_plane, int n_events,
+                        const int* kind, const float* a, const float* b, rtr_camera* out);
+
 /* ---- multi-GPU (one process per GPU; NCCL resolved at run time with dlopen("libnccl.so.2"),
  * so inside a torch process it is the very library torch.distributed already loaded) ---- */
 #define RTR_NCCL_UNIQUE_ID_BYTES 128

@@ -106,7 +106,8 @@ static_assert(sizeof(CameraGPU) == sizeof(rtr_camera), "CameraGPU layout");
 // (lookAtRH matrix_transform.inl:153-173, perspectiveRH_NO matrix_clip_space.inl:249-262, inverse
 // func_matrix.inl:347-405, normalize = v * (1 / sqrt(dot)), dot = (x + y) + z, radians = deg * 0.0174532925...f)
 // so that getGpuData() is bit-identical to the reference's on the same libm
-// (tests/test_camera_cpu.py compares against the reference's own camera.cpp, oracle/_ref/libref_camera.so).
+// (tests/testsSortGPU/testCamera.cpp and tests/test_camera_cpu.py compare against the reference's own camera.cpp,
+// oracle/_ref/libref_camera.so).
 // Compile without FMA contraction (-ffp-contract=off, or no -march that enables FMA).
 enum CameraMovement { FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN };
 

@@ -41,7 +41,7 @@ SYMBOLS = [
     "rtr_bvh_depth_overlay", "rtr_bvh_depth_overlay_dev",
     "rtr_obj_load", "rtr_obj_parse", "rtr_obj_free", "rtr_mesh_primitive", "rtr_mesh_init", "rtr_mesh_set_model",
     "rtr_mesh_set_position", "rtr_mesh_set_scale", "rtr_mesh_set_rotation", "rtr_mesh_set_material",
-    "rtr_triangle_centroid", "rtr_bvh_stack_overflows",
+    "rtr_triangle_centroid", "rtr_bvh_stack_overflows", "rtr_camera_gpu_data",
 ]
 
 
@@ -153,6 +153,7 @@ def load_library():
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
     f32 = C.c_float
     L.rtr_bvh_stack_overflows.argtypes = [vp, C.POINTER(u32)]
+    L.rtr_camera_gpu_data.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp]
     L.rtr_obj_load.argtypes = [C.c_char_p, u32, pp, C.POINTER(u64)]
     L.rtr_obj_parse.argtypes = [C.c_char_p, u64, u32, pp, C.POINTER(u64)]
     L.rtr_obj_free.argtypes = [vp]
@@ -220,6 +221,17 @@ def parse_obj(text, model_id: int = 0) -> np.ndarray:
     out, n = C.c_void_p(), C.c_uint64()
     _check_host(L.rtr_obj_parse(data, len(data), model_id, C.byref(out), C.byref(n)))
     return _take_triangles(out, n)
+
+
+def camera_gpu_data(eye, aspect: float, fov: float = 45.0, near: float = 0.1, far: float = 200.0, events=()) -> np.ndarray:
+    """cr::Camera::getGpuData() (camera.cpp:23-34) after replaying `events` = [(kind, a, b), ...]; see rtr.h."""
+    e = np.ascontiguousarray(eye, dtype=np.float32).reshape(3)
+    kind = np.array([ev[0] for ev in events], dtype=np.int32)
+    a = np.array([ev[1] for ev in events], dtype=np.float32)
+    b = np.array([ev[2] for ev in events], dtype=np.float32)
+    out = np.zeros(1, dtype=CAMERA)
+    _check_host(load_library().rtr_camera_gpu_data(_ptr(e), aspect, fov, near, far, len(events), _ptr(kind), _ptr(a), _ptr(b), _ptr(out)))
+    return out
 
 
 PRIMITIVE_TRIANGLE, PRIMITIVE_SQUARE, PRIMITIVE_CUBE, PRIMITIVE_SPHERE = 0, 1, 2, 3

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "../../include/rtr_scene.hpp"  // cr::Camera: the same code a C++ caller compiles
 
 namespace {
 
@@ -569,6 +570,26 @@ void rtr_triangle_centroid(const rtr_triangle* t, const float model[16], float o
     for (int k = 0; k < 4; ++k) s[k] = (t->p0[k] + t->p1[k]) + t->p2[k];
     for (int row = 0; row < 3; ++row)
         out[row] = ((sm[row] * s[0] + sm[4 + row] * s[1]) + (sm[8 + row] * s[2] + sm[12 + row] * s[3]));
+}
+
+// cr::Camera for callers that cannot include rtr_scene.hpp (the Python mirror): a camera made like
+// application.cpp:16-20, the input events replayed on it -- kind 0: ProcessMouseMovement(a, b); kind 1..6:
+// processKeyboard(FORWARD..DOWN, a) with _Accelerate = (b != 0) -- then getGpuData() (camera.cpp:23-34).
+int rtr_camera_gpu_data(const float eye[3], float aspect, float fov, float near_plane, float far_plane, int n_events,
+                        const int* kind, const float* a, const float* b, rtr_camera* out) {
+    if (!eye || !out || n_events < 0 || (n_events && (!kind || !a || !b)))
+        return rtr_set_error(nullptr, RTR_E_INVALID, "camera_gpu_data: NULL argument");
+    cr::Camera cam(eye, aspect, fov, near_plane, far_plane);
+    for (int i = 0; i < n_events; ++i) {
+        if (kind[i] == 0) cam.ProcessMouseMovement(a[i], b[i]);
+        else if (kind[i] >= 1 && kind[i] <= 6) {
+            cam._Accelerate = b[i] != 0.f;
+            cam.processKeyboard(static_cast<cr::CameraMovement>(kind[i] - 1), a[i]);
+        } else return rtr_set_error(nullptr, RTR_E_INVALID, "camera_gpu_data: event %d has kind %d", i, kind[i]);
+    }
+    const cr::CameraGPU g = cam.getGpuData();
+    memcpy(out, &g, sizeof(g));
+    return RTR_OK;
 }
 
 }  // extern "C"

@@ -60,6 +60,30 @@ def getBVH_NodesToGPUData(bvh: BVH) -> np.ndarray:
     return bvh.handle.flat_nodes()
 
 
+FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN = range(6)  # cr::CameraMovement, camera.hpp:10-17
+
+
+class Camera:
+    """cr::Camera (srcCommon/scene/camera.hpp:35-106): keeps the construction arguments and the input events and lets
+    librtr_b200 replay them through the same code as the C++ shim's cr::Camera, so getGpuData() is the reference's
+    CameraGPU bit for bit (tests/test_camera_cpu.py)."""
+
+    def __init__(self, position, aspectRatio: float, fov: float = 45.0, near: float = 0.1, far: float = 200.0):
+        self._position = tuple(float(v) for v in position)
+        self._AspectRatio, self._Fov, self._Near, self._Far = float(aspectRatio), float(fov), float(near), float(far)
+        self._Accelerate = False
+        self._events = []
+
+    def processKeyboard(self, direction: int, deltaTime: float):
+        self._events.append((int(direction) + 1, float(deltaTime), 1.0 if self._Accelerate else 0.0))
+
+    def ProcessMouseMovement(self, xoffset: float, yoffset: float):
+        self._events.append((0, float(xoffset), float(yoffset)))
+
+    def getGpuData(self) -> np.ndarray:
+        return capi.camera_gpu_data(self._position, self._AspectRatio, self._Fov, self._Near, self._Far, self._events)
+
+
 class Mesh:
     """cr::Mesh (srcCommon/scene/geometry/mesh.hpp:17-44): a triangle list, a MeshModelGPU and the id every triangle
     of the mesh carries in _ModelId.  All arithmetic is librtr_b200's (rtr_obj_load / rtr_mesh_*), so the records are
@@ -184,4 +208,4 @@ class Scene:
         return getBVH_NodesToGPUData(self._BVH)
 
 
-__all__ = ["BVH", "BVH_Params", "Scene", "Mesh", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]
+__all__ = ["BVH", "BVH_Params", "Scene", "Mesh", "Camera", "FORWARD", "BACKWARD", "LEFT", "RIGHT", "UP", "DOWN", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]
