@@ -20,6 +20,7 @@ from .layouts import MESH, NONE, TRIANGLE
 
 MAX_NB_TRIANGLES = 2 << 15  # triangle.hpp:21
 MAX_NB_MESHES = 2 << 5      # mesh.hpp:26
+MAX_NB_MATERIALS = 2 << 15  # material.hpp:19
 
 
 class BVH_Params:
@@ -158,6 +159,8 @@ class Scene:
         self._NbMeshes = 0
         self._BVH = None
         self._reference_padding = reference_padding
+        self._Materials = []  # [r, g, b, a] float32 each
+        self._NbMaterials = 0
 
     def addMesh(self, triangles, model=None, material_id: int = 0):
         """scene.cpp:42-47.  A `Mesh` is taken as it is (its triangles carry Mesh::_Id, which is the mesh slot only
@@ -179,6 +182,32 @@ class Scene:
         self._Meshes.append((tris, mesh))
         self._NbMeshes += 1
         self._NbTriangles += tris.size if not self._reference_padding else min(tris.size, MAX_NB_TRIANGLES)
+
+    def addMaterial(self, color):
+        """scene.cpp:57-61"""
+        if len(self._Materials) == MAX_NB_MATERIALS:
+            return
+        self._Materials.append(np.asarray(color, dtype=np.float32).reshape(4).copy())
+        self._NbMaterials += 1
+
+    def addRandomMaterial(self):
+        """scene.cpp:63-67 + material.cpp:17-27: three draws of the C library's rand()."""
+        import ctypes
+        libc = ctypes.CDLL(None)
+        libc.rand.restype = ctypes.c_int
+        rand_max = np.float32(2147483647)  # RAND_MAX of glibc
+        rgb = [np.float32(libc.rand()) / rand_max for _ in range(3)]
+        self.addMaterial(rgb + [1.0])
+
+    def getMaterialToGPUData(self) -> np.ndarray:
+        """scene.cpp:42-48: [n, 4]; with reference_padding MAX_NB_MATERIALS entries, the unused ones a default
+        MaterialGPU = (1, 1, 1, 1) (material.hpp:10)."""
+        mats = np.stack(self._Materials) if self._Materials else np.zeros((0, 4), dtype=np.float32)
+        if not self._reference_padding:
+            return mats
+        out = np.ones((MAX_NB_MATERIALS, 4), dtype=np.float32)
+        out[:mats.shape[0]] = mats
+        return out
 
     def getTriangleToGPUData(self) -> np.ndarray:
         """scene.cpp:26-40 (zero padded to MAX_NB_TRIANGLES only with reference_padding)."""
@@ -208,4 +237,4 @@ class Scene:
         return getBVH_NodesToGPUData(self._BVH)
 
 
-__all__ = ["BVH", "BVH_Params", "Scene", "Mesh", "Camera", "FORWARD", "BACKWARD", "LEFT", "RIGHT", "UP", "DOWN", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "NONE"]
+__all__ = ["BVH", "BVH_Params", "Scene", "Mesh", "Camera", "FORWARD", "BACKWARD", "LEFT", "RIGHT", "UP", "DOWN", "getBVH_NodesToGPUData", "MAX_NB_TRIANGLES", "MAX_NB_MESHES", "MAX_NB_MATERIALS", "NONE"]
