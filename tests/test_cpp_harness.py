@@ -51,6 +51,21 @@ def test_mesh_mirror_is_bit_identical_to_the_reference(executables):
     assert "0 mismatches" in r.stdout and "%d cases" % (len(objs) + 4 + 2000) in r.stdout
 
 
+def test_shim_compiles_with_glm_types(tmp_path):
+    """RTR_SCENE_USE_GLM: cr::Mesh / cr::Triangle / cr::Material / cr::Camera with glm::vec / glm::mat members."""
+    glm = "/root/reference/srcVulkan/dep/slang/external/glm"
+    if not os.path.isdir(glm):
+        pytest.skip("no GLM tree here")
+    build.build()
+    exe = str(tmp_path / "glmMode")
+    libdir = os.path.join(ROOT, "realtimeraytracing_b200", "lib")
+    out = subprocess.run(["/usr/bin/g++", "-std=c++20", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                          "-I" + glm, os.path.join(HARNESS, "glmMode.cpp"), "-o", exe, "-L" + libdir, "-lrtr_b200",
+                          "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert subprocess.run([exe]).returncode == 0
+
+
 def test_cpp_harness_compiles_and_links(executables):
     for t, path in executables.items():
         assert os.path.exists(path), t
