@@ -115,10 +115,65 @@ struct rtr_bvh {
 // leaves get there, so they may err on the side of visiting -- never on the side of skipping.
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ int trav_ilogb(double x) {  // floor(log2 x) of a positive normal double
-    return (int)((__double_as_longlong(x) >> 52) & 0x7FF) - 1023;
+// The encoder and the decoder of the traversal records are __host__ __device__: the kernels use the intrinsics, and
+// tests/host/trav_records_check.cu runs the very same functions on the CPU (directed rounding through <cfenv>, the
+// fused multiply-add through fmaf) to check their contract -- "the reference's slab test passes on the exact box ==>
+// the compressed test passes, with an entry distance that is not larger" -- on millions of random boxes and rays.
+#ifndef __CUDA_ARCH__
+#include <cfenv>
+#include <cmath>
+#include <cstring>
+#endif
+#define TRAV_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+TRAV_HD long long trav_d2ll(double x) { return __double_as_longlong(x); }
+TRAV_HD double trav_ll2d(long long x) { return __longlong_as_double(x); }
+TRAV_HD uint32_t trav_f2u(float x) { return __float_as_uint(x); }
+TRAV_HD float trav_u2f(uint32_t x) { return __uint_as_float(x); }
+TRAV_HD float trav_sub_rd(float a, float b) { return __fsub_rd(a, b); }
+TRAV_HD float trav_sub_ru(float a, float b) { return __fsub_ru(a, b); }
+TRAV_HD float trav_mul_rd(float a, float b) { return __fmul_rd(a, b); }
+TRAV_HD float trav_mul_ru(float a, float b) { return __fmul_ru(a, b); }
+TRAV_HD int trav_f2i_rd(float x) { return __float2int_rd(x); }
+TRAV_HD int trav_f2i_ru(float x) { return __float2int_ru(x); }
+TRAV_HD float trav_sub(float a, float b) { return __fsub_rn(a, b); }
+TRAV_HD float trav_add(float a, float b) { return __fadd_rn(a, b); }
+TRAV_HD float trav_mul(float a, float b) { return __fmul_rn(a, b); }
+TRAV_HD float trav_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+TRAV_HD uint32_t trav_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#else
+inline long long trav_d2ll(double x) { long long r; std::memcpy(&r, &x, 8); return r; }
+inline double trav_ll2d(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
+inline uint32_t trav_f2u(float x) { uint32_t r; std::memcpy(&r, &x, 4); return r; }
+inline float trav_u2f(uint32_t x) { float r; std::memcpy(&r, &x, 4); return r; }
+template <class F> inline float trav_rounded(int mode, F op) {  // one fp32 operation in the given rounding mode
+    const int old = std::fegetround();
+    std::fesetround(mode);
+    volatile float r = op();
+    std::fesetround(old);
+    return r;
 }
-__device__ __forceinline__ double trav_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+inline float trav_sub_rd(float a, float b) { volatile float x = a, y = b; return trav_rounded(FE_DOWNWARD, [&] { return x - y; }); }
+inline float trav_sub_ru(float a, float b) { volatile float x = a, y = b; return trav_rounded(FE_UPWARD, [&] { return x - y; }); }
+inline float trav_mul_rd(float a, float b) { volatile float x = a, y = b; return trav_rounded(FE_DOWNWARD, [&] { return x * y; }); }
+inline float trav_mul_ru(float a, float b) { volatile float x = a, y = b; return trav_rounded(FE_UPWARD, [&] { return x * y; }); }
+inline int trav_f2i_rd(float x) { return (int)std::floor(x); }
+inline int trav_f2i_ru(float x) { return (int)std::ceil(x); }
+inline float trav_sub(float a, float b) { volatile float r = a - b; return r; }
+inline float trav_add(float a, float b) { volatile float r = a + b; return r; }
+inline float trav_mul(float a, float b) { volatile float r = a * b; return r; }
+inline float trav_fma(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline uint32_t trav_prmt(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, default mode: result byte i = byte sel[4i+2:4i] of {b, a}
+    const unsigned long long both = ((unsigned long long)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((both >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+}
+#endif
+TRAV_HD int trav_ilogb(double x) {  // floor(log2 x) of a positive normal double
+    return (int)((trav_d2ll(x) >> 52) & 0x7FF) - 1023;
+}
+TRAV_HD double trav_pow2(int e) { return trav_ll2d((long long)(e + 1023) << 52); }
 
 // One axis of a node's grid: step 2^e with origin + 255 * step >= hi (the extent is taken in double, where hi - lo of
 // two fp32 values is exact); the step is kept within 2^-40 of the origin's magnitude.
@@ -126,7 +181,7 @@ struct TravAxis {
     double lo, step, inv_step;
     uint32_t ebyte;
 };
-__device__ __forceinline__ TravAxis trav_axis_frame(float nlo_f, float nhi_f, bool& ok) {
+TRAV_HD TravAxis trav_axis_frame(float nlo_f, float nhi_f, bool& ok) {
     const double lo = nlo_f, hi = nhi_f;
     const double ext = hi - lo;
     int e = -100;
@@ -150,20 +205,20 @@ __device__ __forceinline__ TravAxis trav_axis_frame(float nlo_f, float nhi_f, bo
 // a max plane hold in exact arithmetic -- no check in higher precision is needed, and at worst the byte is one step
 // looser than the exactly rounded one.  (An earlier version did this in double with a verification pass: +0.2 ms per
 // 10 M-triangle rebuild for the same traversal time.)
-__device__ __forceinline__ uint32_t trav_axis_quad_f32(const TravAxis& f, float alo, float ahi, float blo, float bhi, bool& ok) {
+TRAV_HD uint32_t trav_axis_quad_f32(const TravAxis& f, float alo, float ahi, float blo, float bhi, bool& ok) {
     const float lo = (float)f.lo, inv_step = (float)f.inv_step;  // both exact: the origin is an fp32 value, the step 2^e, |e| <= 100
     auto down = [&](float x) -> uint32_t {
-        const float t = __fmul_rd(__fsub_rd(x, lo), inv_step);
-        return (uint32_t)__float2int_rd(fminf(fmaxf(t, 0.f), 255.f));
+        const float t = trav_mul_rd(trav_sub_rd(x, lo), inv_step);
+        return (uint32_t)trav_f2i_rd(fminf(fmaxf(t, 0.f), 255.f));
     };
     auto up = [&](float x) -> uint32_t {
-        const float t = __fmul_ru(__fsub_ru(x, lo), inv_step);
+        const float t = trav_mul_ru(trav_sub_ru(x, lo), inv_step);
         if (!(t <= 255.5f)) ok = false;  // beyond the grid (never for a box inside the node) or NaN
-        return (uint32_t)__float2int_ru(fminf(fmaxf(t, 0.f), 255.f));
+        return (uint32_t)trav_f2i_ru(fminf(fmaxf(t, 0.f), 255.f));
     };
     return down(alo) | (up(ahi) << 8) | (down(blo) << 16) | (up(bhi) << 24);
 }
-__device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
+TRAV_HD void trav_encode_axis(float nlo_f, float nhi_f, float llo, float lhi, float rlo, float rhi,
                                                  uint32_t& ebyte, uint32_t& quad, bool& ok) {
     const TravAxis f = trav_axis_frame(nlo_f, nhi_f, ok);
     ebyte = f.ebyte;
@@ -171,7 +226,7 @@ __device__ __forceinline__ void trav_encode_axis(float nlo_f, float nhi_f, float
 }
 
 // node box n, child boxes l and r as (min.xyz, max.x)(max.y, max.z) float4 + float2
-__device__ __forceinline__ void trav_encode_inner(const float4 nlo, const float2 nhi, const float4 llo, const float2 lhi,
+TRAV_HD void trav_encode_inner(const float4 nlo, const float2 nhi, const float4 llo, const float2 lhi,
                                                   const float4 rlo, const float2 rhi, bool lleaf, bool rleaf,
                                                   uint32_t right, uint4& o0, uint4& o1) {
     uint32_t ex, ey, ez, qx, qy, qz;
@@ -180,13 +235,13 @@ __device__ __forceinline__ void trav_encode_inner(const float4 nlo, const float2
     trav_encode_axis(nlo.y, nhi.x, llo.y, lhi.x, rlo.y, rhi.x, ey, qy, ok);
     trav_encode_axis(nlo.z, nhi.y, llo.z, lhi.y, rlo.z, rhi.y, ez, qz, ok);
     const uint32_t flags = (lleaf ? 1u : 0u) | (rleaf ? 2u : 0u) | (ok ? 0u : 4u);
-    o0 = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z),
+    o0 = make_uint4(trav_f2u(nlo.x), trav_f2u(nlo.y), trav_f2u(nlo.z),
                     ex | (ey << 8) | (ez << 16) | (flags << 24));
     o1 = make_uint4(qx, qy, qz, right);
 }
 // Second half of an inner record: the four GRANDCHILD slots on the node's own grid (see the layout above).
 // box k = (min.xyz, max.x)(max.y, max.z); an unused slot repeats its sibling.  ok = false: the node keeps to pair steps.
-__device__ __forceinline__ void trav_encode_quads(const float4 nlo, const float2 nhi, const float4 lo[4], const float2 hi[4],
+TRAV_HD void trav_encode_quads(const float4 nlo, const float2 nhi, const float4 lo[4], const float2 hi[4],
                                                   uint32_t idx1, uint32_t idx3, uint4& o2, uint4& o3, bool& ok) {
     const TravAxis fx = trav_axis_frame(nlo.x, nlo.w, ok);
     const TravAxis fy = trav_axis_frame(nlo.y, nhi.x, ok);
@@ -195,6 +250,50 @@ __device__ __forceinline__ void trav_encode_quads(const float4 nlo, const float2
                     trav_axis_quad_f32(fz, lo[0].z, hi[0].y, lo[1].z, hi[1].y, ok), idx1);
     o3 = make_uint4(trav_axis_quad_f32(fx, lo[2].x, lo[2].w, lo[3].x, lo[3].w, ok), trav_axis_quad_f32(fy, lo[2].y, hi[2].x, lo[3].y, hi[3].x, ok),
                     trav_axis_quad_f32(fz, lo[2].z, hi[2].y, lo[3].z, hi[3].y, ok), idx3);
+}
+
+// ---- decoder side (trace.cu) ----
+// One axis of the compressed test.  With the node origin c, grid step s = 2^e, plane byte q and the ray (o, j = 1/d):
+//     a = s*j (exact), b = fl(fl(c - o)*j), x = 2^23 + q (exact, built by PRMT), t = fl(x*a + fl(fl(b -+ m) - 2^23*a))
+// with the margin m = 0.52|a| + 2e-6|b| + 1e-30 (derivation in trace.cu).  The bytes (lo, hi) of a slot become
+// (near, far) by a byte swap when j < 0.
+// pair step: quad = (Llo, Lhi, Rlo, Rhi); updates (near, far) of the left and of the right child
+TRAV_HD void trav_axis_planes2(float c, uint32_t ebyte, uint32_t quad, float o, float j,
+                               float& tnl, float& tfl, float& tnr, float& tfr) {
+    const float step = trav_u2f(ebyte << 23);
+    const float sa = trav_mul(step, j);
+    const float sb = trav_mul(trav_sub(c, o), j);
+    const float m = trav_fma(fabsf(sa), 0.52f, trav_fma(fabsf(sb), 2e-6f, 1e-30f));
+    const float bn = trav_fma(-8388608.f, sa, trav_sub(sb, m));
+    const float bf = trav_fma(-8388608.f, sa, trav_add(sb, m));
+    // bytes (Llo, Lhi, Rlo, Rhi) -> (Lnear, Lfar, Rnear, Rfar)
+    const uint32_t w = trav_prmt(quad, quad, j < 0.f ? 0x2301u : 0x3210u);
+    const float x0 = trav_u2f(trav_prmt(w, 0x4B000000u, 0x7650u));
+    const float x1 = trav_u2f(trav_prmt(w, 0x4B000000u, 0x7651u));
+    const float x2 = trav_u2f(trav_prmt(w, 0x4B000000u, 0x7652u));
+    const float x3 = trav_u2f(trav_prmt(w, 0x4B000000u, 0x7653u));
+    tnl = fmaxf(tnl, trav_fma(x0, sa, bn)); tfl = fminf(tfl, trav_fma(x1, sa, bf));
+    tnr = fmaxf(tnr, trav_fma(x2, sa, bn)); tfr = fminf(tfr, trav_fma(x3, sa, bf));
+}
+// wide step: quads (S0lo, S0hi, S1lo, S1hi) and (S2lo, S2hi, S3lo, S3hi); returns this axis' entry / exit distances of
+// the four slots, the caller combines the axes
+TRAV_HD void trav_axis_vals4(float c, uint32_t ebyte, uint32_t qa, uint32_t qb, float o, float j, float (&vn)[4], float (&vf)[4]) {
+    const float step = trav_u2f(ebyte << 23);
+    const float sa = trav_mul(step, j);
+    const float sb = trav_mul(trav_sub(c, o), j);
+    const float m = trav_fma(fabsf(sa), 0.52f, trav_fma(fabsf(sb), 2e-6f, 1e-30f));
+    const float bn = trav_fma(-8388608.f, sa, trav_sub(sb, m));
+    const float bf = trav_fma(-8388608.f, sa, trav_add(sb, m));
+    const uint32_t sel = j < 0.f ? 0x2301u : 0x3210u;
+    const uint32_t wa = trav_prmt(qa, qa, sel), wb = trav_prmt(qb, qb, sel);
+    vn[0] = trav_fma(trav_u2f(trav_prmt(wa, 0x4B000000u, 0x7650u)), sa, bn);
+    vf[0] = trav_fma(trav_u2f(trav_prmt(wa, 0x4B000000u, 0x7651u)), sa, bf);
+    vn[1] = trav_fma(trav_u2f(trav_prmt(wa, 0x4B000000u, 0x7652u)), sa, bn);
+    vf[1] = trav_fma(trav_u2f(trav_prmt(wa, 0x4B000000u, 0x7653u)), sa, bf);
+    vn[2] = trav_fma(trav_u2f(trav_prmt(wb, 0x4B000000u, 0x7650u)), sa, bn);
+    vf[2] = trav_fma(trav_u2f(trav_prmt(wb, 0x4B000000u, 0x7651u)), sa, bf);
+    vn[3] = trav_fma(trav_u2f(trav_prmt(wb, 0x4B000000u, 0x7652u)), sa, bn);
+    vf[3] = trav_fma(trav_u2f(trav_prmt(wb, 0x4B000000u, 0x7653u)), sa, bf);
 }
 #endif
 

@@ -717,43 +717,13 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             break;
         }
     };
-    // one axis of the compressed pair test: updates (near, far) of the left and of the right child
+    // one axis of the compressed tests (bvh.cuh: the same functions the host-side contract check runs)
     auto axis_planes = [&](float c, uint32_t ebyte, uint32_t quad, float o, float j,
                            float& tnl, float& tfl, float& tnr, float& tfr) {
-        const float step = __uint_as_float(ebyte << 23);
-        const float sa = __fmul_rn(step, j);
-        const float sb = __fmul_rn(__fsub_rn(c, o), j);
-        const float m = __fmaf_rn(fabsf(sa), 0.52f, __fmaf_rn(fabsf(sb), 2e-6f, 1e-30f));
-        const float bn = __fmaf_rn(-8388608.f, sa, __fsub_rn(sb, m));
-        const float bf = __fmaf_rn(-8388608.f, sa, __fadd_rn(sb, m));
-        // bytes (Llo, Lhi, Rlo, Rhi) -> (Lnear, Lfar, Rnear, Rfar)
-        const uint32_t w = __byte_perm(quad, quad, j < 0.f ? 0x2301u : 0x3210u);
-        const float x0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u));
-        const float x1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651u));
-        const float x2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652u));
-        const float x3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653u));
-        tnl = fmaxf(tnl, __fmaf_rn(x0, sa, bn)); tfl = fminf(tfl, __fmaf_rn(x1, sa, bf));
-        tnr = fmaxf(tnr, __fmaf_rn(x2, sa, bn)); tfr = fminf(tfr, __fmaf_rn(x3, sa, bf));
+        trav_axis_planes2(c, ebyte, quad, o, j, tnl, tfl, tnr, tfr);
     };
-    // the same for the four slots of the wide step: quads (S0lo, S0hi, S1lo, S1hi) and (S2lo, S2hi, S3lo, S3hi);
-    // returns this axis' entry / exit distances, the caller combines the axes with three-input min / max
     auto axis_vals4 = [&](float c, uint32_t ebyte, uint32_t qa, uint32_t qb, float o, float j, float (&vn)[4], float (&vf)[4]) {
-        const float step = __uint_as_float(ebyte << 23);
-        const float sa = __fmul_rn(step, j);
-        const float sb = __fmul_rn(__fsub_rn(c, o), j);
-        const float m = __fmaf_rn(fabsf(sa), 0.52f, __fmaf_rn(fabsf(sb), 2e-6f, 1e-30f));
-        const float bn = __fmaf_rn(-8388608.f, sa, __fsub_rn(sb, m));
-        const float bf = __fmaf_rn(-8388608.f, sa, __fadd_rn(sb, m));
-        const uint32_t sel = j < 0.f ? 0x2301u : 0x3210u;
-        const uint32_t wa = __byte_perm(qa, qa, sel), wb = __byte_perm(qb, qb, sel);
-        vn[0] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650u)), sa, bn);
-        vf[0] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7651u)), sa, bf);
-        vn[1] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7652u)), sa, bn);
-        vf[1] = __fmaf_rn(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7653u)), sa, bf);
-        vn[2] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u)), sa, bn);
-        vf[2] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7651u)), sa, bf);
-        vn[3] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7652u)), sa, bn);
-        vf[3] = __fmaf_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7653u)), sa, bf);
+        trav_axis_vals4(c, ebyte, qa, qb, o, j, vn, vf);
     };
     // decoded planes of one axis, rounded outwards: min planes down, max planes up
     auto decode_axis = [&](float c, uint32_t ebyte, uint32_t quad, float& llo, float& lhi, float& rlo, float& rhi) {
