@@ -242,7 +242,10 @@ int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* ca
                           uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
                           uint32_t row0, uint32_t row1, uint32_t flags, rtr_hit* hits_dev /* [(row1-row0)*width] */);
 /* explicit ray batches (getClosestHitBVH semantics); any_hit != 0: did_hit = 1 iff a hit with
- * t < t_max[i] exists (t_max NULL = +inf), other fields zero */
+ * t < t_max[i] exists (t_max NULL = +inf), other fields zero.
+ * Directions: the shader's rays are unit vectors and the default order's pruning margin is derived for them; it holds
+ * with room up to |direction| = 8.  rtr_trace_rays refuses longer directions in the default order (RTR_E_UNSUPPORTED;
+ * RTR_TRACE_REFERENCE_ORDER takes any length); the caller of rtr_trace_rays_dev is responsible for the same. */
 int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays, uint64_t n_rays, int any_hit,
                    const float* t_max, uint32_t flags, rtr_hit* hits_out);
 int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays_dev, uint64_t n_rays, int any_hit,

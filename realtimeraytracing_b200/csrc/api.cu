@@ -816,6 +816,19 @@ int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t
     RTR_CHECK(order_ok(ctx, b, flags));
     if (n_rays == 0) return RTR_OK;
     if (!hits_out) return rtr_set_error(ctx, RTR_E_INVALID, "trace_rays: NULL output");
+    if (!(flags & RTR_TRACE_REFERENCE_ORDER)) {
+        // The default order prunes with a bound on the rounding error of a computed hit distance that is derived for
+        // the shader's rays, which are unit vectors (getRay normalises, raytracer.glsl:92-100); the error grows with |d|
+        // (measured: 3 % of the bound at |d| = 1, 25 % at 10, beyond it near 40; tests/test_prune_bound_cpu.py).
+        for (uint64_t i = 0; i < n_rays; ++i) {
+            const float* d = rays[i].direction;
+            const float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (d2 > 64.f && d2 < INFINITY)
+                return rtr_set_error(ctx, RTR_E_UNSUPPORTED,
+                                     "trace_rays: ray %llu has |direction| = %g; the default order needs |direction| <= 8 "
+                                     "(normalise it, or trace with RTR_TRACE_REFERENCE_ORDER)", (unsigned long long)i, sqrtf(d2));
+        }
+    }
     const size_t rb = n_rays * sizeof(rtr_ray), hb = n_rays * sizeof(rtr_hit), tb = t_max ? n_rays * 4 : 0;
     Staging st;
     RTR_CHECK(staging_begin(ctx, rb + hb + tb + 1024, 0, &st));

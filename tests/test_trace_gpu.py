@@ -319,3 +319,24 @@ def test_tiny_trees_through_the_wide_step(ctx, oracle, n):
         assert np.array_equal(occ["did_hit"], oracle.any_hit(flat, tris, meshes, rays, tmax))
     finally:
         bvh.close()
+
+
+def test_long_directions_are_refused_in_the_default_order(ctx):
+    """The pruning margin is derived for the shader's unit directions (tests/test_prune_bound_cpu.py): rtr_trace_rays
+    refuses |d| > 8 unless the by-the-letter order is asked for."""
+    tris, meshes, L = scenes.soup(2000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        rays = np.zeros(64, dtype=RAY)
+        rays["o"][:, 2] = -2.0 * L
+        rays["o"][:, 3] = 1.0
+        rays["d"][:, 2] = 1.0
+        rays["d"][5, :3] = (0.0, 30.0, 40.0)
+        with pytest.raises(capi.RtrError) as e:
+            bvh.trace_rays(rays)
+        assert e.value.code == -5 and "ray 5" in str(e.value)
+        assert bvh.trace_rays(rays, flags=capi.TRACE_REFERENCE_ORDER).size == 64
+        rays["d"][5, :3] = (0.0, 3.0, 4.0)
+        assert bvh.trace_rays(rays).size == 64
+    finally:
+        bvh.close()
