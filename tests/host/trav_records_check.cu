@@ -48,6 +48,7 @@ static uint32_t shrink(uint32_t quad) {
 int main(int argc, char** argv) {
     const long cases = argc > 1 ? std::atol(argv[1]) : 400000;
     const bool broken = argc > 2 && std::string(argv[2]) == "--shrink";
+    const bool wide = argc > 2 && std::string(argv[2]) == "--wide";  // scene scales 1e-25 ... 1e14: some nodes are unencodable
     std::mt19937_64 rng(20240611);
     auto uni = [&](double a, double b) { return std::uniform_real_distribution<double>(a, b)(rng); };
     auto logu = [&](double a, double b) { return std::exp(uni(std::log(a), std::log(b))); };
@@ -55,7 +56,7 @@ int main(int argc, char** argv) {
     for (long c = 0; c < cases; ++c) {
         // a node somewhere, of some size; four boxes inside it (some flat, some touching its faces, some the node itself)
         Box node;
-        const double scale = logu(1e-3, 1e4);
+        const double scale = wide ? logu(1e-25, 1e14) : logu(1e-3, 1e4);
         for (int k = 0; k < 3; ++k) {
             const double centre = uni(-1.0, 1.0) * scale * (c % 3 == 0 ? 100.0 : 1.0);
             const double ext = scale * logu(1e-4, 1.0);

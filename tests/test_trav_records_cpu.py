@@ -40,3 +40,11 @@ def test_compressed_tests_never_reject_what_the_reference_accepts(checker):
 def test_the_check_notices_a_shrunk_encoding(checker):
     r = subprocess.run([checker, "50000", "--shrink"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 1 and " 0 violations" not in r.stdout
+
+
+def test_extreme_magnitudes_are_flagged_not_misencoded(checker):
+    """Scene scales from 1e-25 to 1e14: nodes the grid cannot represent carry the 'no culling here' flag (the check
+    counts them as skipped) and every other node still satisfies the obligation."""
+    r = subprocess.run([checker, "200000", "--wide"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 violations" in r.stdout and " 0 unencodable" not in r.stdout
