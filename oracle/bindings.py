@@ -104,6 +104,8 @@ class Oracle:
         L.orc_ray_triangle.argtypes = [vp, vp, vp, u32, vp]
         L.orc_intersect_box.argtypes = [vp, vp]
         L.orc_intersect_box.restype = u32
+        L.orc_intersect_box_edge.argtypes = [vp, vp, i32]
+        L.orc_intersect_box_edge.restype = u32
         L.orc_closest_hit_bvh.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orc_closest_hit_brute.argtypes = [vp, vp, u32, vp, vp]
         L.orc_any_hit_bvh.argtypes = [vp, C.c_float, vp, vp, vp]
@@ -250,6 +252,22 @@ class Oracle:
         self.lib.orc_trace_rays(_p(flat), _p(tris), _p(meshes), _p(rays), rays.size, _p(hits), threads)
         return hits
 
+    def ray_triangle(self, tris, meshes, rays, tri_index):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.size, dtype=HIT)
+        for i in range(rays.size):
+            self.lib.orc_ray_triangle(_p(rays[i:i + 1]), _p(tris), _p(meshes), int(tri_index[i]), _p(out[i:i + 1]))
+        return out
+
+    def intersect_box_edge(self, flat, rays, node_index, display_depth):
+        rays = np.ascontiguousarray(rays)
+        flat = np.ascontiguousarray(flat)
+        out = np.zeros(rays.size, dtype=np.uint32)
+        for i in range(rays.size):
+            out[i] = self.lib.orc_intersect_box_edge(_p(rays[i:i + 1]), _p(flat[int(node_index[i]):int(node_index[i]) + 1]),
+                                                     display_depth)
+        return out
+
     def closest_hit_brute(self, tris, meshes, rays):
         rays = np.ascontiguousarray(rays)
         hits = np.zeros(rays.size, dtype=HIT)
@@ -365,3 +383,124 @@ class Reference:
             return ReferenceBvh(n, codes, idx, clusters, parent, left, right, is_leaf, ms)
         finally:
             self.lib.ref_bvh_destroy(h)
+
+
+def raytracer_available(variant: str = "glm") -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libref_raytracer_%s.so" % variant))
+
+
+class ReferenceRaytracer:
+    """The reference's own raytracer.glsl, compiled as C++ through its vendored GLM (oracle/ref_raytracer.cpp).
+
+    variant: "glm"  -- glm::normalize, undefined Hit w := +inf (guarded misses, Q6)
+             "div"  -- normalize := v / sqrt(dot(v, v)) (what oracle + kernels pin): bit-equal to rtr_oracle.c
+             "zero" -- glm::normalize, undefined := 0 (the letter of raytracer.glsl:279 on zeroed registers)
+    One scene / camera is bound per instance (the shader's SSBOs and uniforms are globals of the library)."""
+
+    def __init__(self, variant: str = "glm"):
+        path = os.path.join(REF_DIR, "libref_raytracer_%s.so" % variant)
+        if not os.path.exists(path):
+            if not os.path.isdir(REFERENCE_ROOT):
+                raise FileNotFoundError(path)
+            subprocess.check_call(["make", "-s", "-C", HERE, path])
+        L = C.CDLL(path)
+        self.lib = L
+        self.variant = variant
+        vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
+        L.ref_rt_variant.restype = C.c_char_p
+        L.ref_rt_undefined_w.restype = f32
+        L.ref_rt_set_scene.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32]
+        L.ref_rt_set_scene.restype = i32
+        L.ref_rt_set_camera.argtypes = [vp]
+        L.ref_rt_set_flags.argtypes = [i32, i32, i32]
+        L.ref_rt_get_ray.argtypes = [f32, f32, vp]
+        L.ref_rt_ray_triangle.argtypes = [vp, vp, u64, vp]
+        L.ref_rt_intersect_bvh.argtypes = [vp, vp, u64, vp]
+        L.ref_rt_closest_hit_bvh.argtypes = [vp, u64, vp, vp]
+        L.ref_rt_all_hits.argtypes = [vp, u64, vp]
+        L.ref_rt_get_color.argtypes = [vp, vp, u64, vp]
+        L.ref_rt_dispatch.argtypes = [u32, u32, u32, u32, vp]
+        self._keep = None
+
+    def set_scene(self, tris, meshes, flat, materials=None, model_stride=68):
+        tris = np.ascontiguousarray(tris)
+        meshes = np.ascontiguousarray(meshes)
+        flat = np.ascontiguousarray(flat)
+        if materials is None:
+            materials = np.ones((1, 4), dtype=np.float32)
+        materials = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 4)
+        assert tris.dtype.itemsize == 64 and meshes.dtype.itemsize == 68 and flat.dtype.itemsize == 48
+        rc = self.lib.ref_rt_set_scene(_p(tris), tris.size, _p(meshes), meshes.size, model_stride,
+                                       _p(materials), materials.shape[0], _p(flat), flat.size)
+        assert rc == 0
+        self.nb_tris = tris.size
+
+    def set_camera(self, cam):
+        cam = np.ascontiguousarray(cam)
+        assert cam.dtype.itemsize == 284
+        self.lib.ref_rt_set_camera(_p(cam))
+
+    def set_flags(self, depth_display_bvh=-1, is_bvh_displayed=False, wireframe=False):
+        self.lib.ref_rt_set_flags(int(depth_display_bvh), int(bool(is_bvh_displayed)), int(bool(wireframe)))
+
+    def get_ray(self, pos_x, pos_y):
+        out = np.zeros(1, dtype=RAY)
+        self.lib.ref_rt_get_ray(C.c_float(pos_x), C.c_float(pos_y), _p(out))
+        return out[0]
+
+    def primary_rays(self, width, height, denom_w=None, denom_h=None):
+        """The rays main() builds: pos = (x / denom_w, y / denom_h), float division as at raytracer.glsl:304-305."""
+        denom_w = width if denom_w is None else denom_w
+        denom_h = height if denom_h is None else denom_h
+        rays = np.zeros(width * height, dtype=RAY)
+        one = np.zeros(1, dtype=RAY)
+        for y in range(height):
+            py = np.float32(y) / np.float32(denom_h)
+            for x in range(width):
+                px = np.float32(x) / np.float32(denom_w)
+                self.lib.ref_rt_get_ray(C.c_float(px), C.c_float(py), _p(one))
+                rays[y * width + x] = one[0]
+        return rays
+
+    def ray_triangle(self, rays, tri_index):
+        rays = np.ascontiguousarray(rays)
+        tri_index = np.ascontiguousarray(tri_index, dtype=np.uint32)
+        out = np.zeros(rays.size, dtype=HIT)
+        self.lib.ref_rt_ray_triangle(_p(rays), _p(tri_index), rays.size, _p(out))
+        return out
+
+    def intersect_bvh(self, rays, node_index):
+        rays = np.ascontiguousarray(rays)
+        node_index = np.ascontiguousarray(node_index, dtype=np.uint32)
+        out = np.zeros(rays.size, dtype=np.uint32)
+        self.lib.ref_rt_intersect_bvh(_p(rays), _p(node_index), rays.size, _p(out))
+        return out
+
+    def closest_hit_bvh(self, rays, want_bvh_color=False):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.size, dtype=HIT)
+        col = np.zeros((rays.size, 4), dtype=np.float32) if want_bvh_color else None
+        self.lib.ref_rt_closest_hit_bvh(_p(rays), rays.size, _p(out), None if col is None else _p(col))
+        return (out, col) if want_bvh_color else out
+
+    def all_hits(self, rays):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(rays.size, dtype=HIT)
+        self.lib.ref_rt_all_hits(_p(rays), rays.size, _p(out))
+        return out
+
+    def get_color(self, hits, bvh_color=None):
+        hits = np.ascontiguousarray(hits)
+        out = np.zeros((hits.size, 4), dtype=np.float32)
+        b = None if bvh_color is None else np.ascontiguousarray(bvh_color, dtype=np.float32)
+        self.lib.ref_rt_get_color(_p(hits), None if b is None else _p(b), hits.size, _p(out))
+        return out
+
+    def dispatch(self, width, height, groups_x=None, groups_y=None, fill=np.nan):
+        """glDispatchCompute(floor(W/16), floor(H/16), 1) (application.cpp:225-245) -> rgba [H, W, 4];
+        pixels no invocation stores keep `fill`."""
+        groups_x = width // 16 if groups_x is None else groups_x
+        groups_y = height // 16 if groups_y is None else groups_y
+        img = np.full((height, width, 4), fill, dtype=np.float32)
+        self.lib.ref_rt_dispatch(groups_x, groups_y, width, height, _p(img))
+        return img

@@ -822,7 +822,7 @@ void orc_shade(const orc_hit* hits, uint64_t n, const orc_triangle* tris, const 
 
 /* raytracer.glsl:182-237 with its return code 2: the ray enters the box within BVH_LINE_WIDTH / (depth + 1) of two of
  * its three slab pairs (a box edge, drawn as a line by the overlay) */
-static uint32_t intersect_box_edge(const orc_ray* ray, const orc_node* node, int display_depth) {
+uint32_t orc_intersect_box_edge(const orc_ray* ray, const orc_node* node, int display_depth) {
     float tMin, tMax;
     float ix = 1.0f / ray->direction[0];
     float tx1 = (node->bmin[0] - ray->origin[0]) * ix;
@@ -878,7 +878,7 @@ void orc_depth_overlay(const orc_node* flat, const orc_camera* cam, uint32_t wid
                 --sp;
                 const uint32_t idx = stack[sp], d = depth[sp];
                 const orc_node* nd = &flat[idx];
-                const uint32_t code = intersect_box_edge(&ray, nd, display_depth);
+                const uint32_t code = orc_intersect_box_edge(&ray, nd, display_depth);
                 if (code != 0) {
                     if ((int)d == display_depth) memcpy(c, code == 2 ? kLine : kBox, 16);
                     if (!(nd->left == 0 && nd->right == 0) && sp + 2 <= 1024) {

@@ -11,10 +11,16 @@
  * unmodified into oracle/_ref/ (see oracle/Makefile, tests/test_oracle_golden_cpu.py)
  * and against the committed fixtures in tests/golden/ generated from that build.
  * The sort pre-pass helpers are pinned against the known-answer vectors of the
- * reference's tests/testsSortGPU.  The traversal half restates raytracer.glsl,
- * which cannot be compiled or run here and has no reference test vectors:
- * for traversal the oracle is "parity unpinned" by the reference's tests; it is
- * cross-checked against the brute-force getAllHits semantics only.
+ * reference's tests/testsSortGPU.  The traversal half (ray generation, slab test,
+ * ray/triangle, stack traversal, getAllHits, getColor, the depth overlay, main's
+ * pixel mapping) is PINNED against the reference's own raytracer.glsl compiled as
+ * C++ through the reference's vendored GLM (oracle/ref_raytracer.cpp + glsl2cpp.sed
+ * -> oracle/_ref/libref_raytracer_*.so) and against tests/golden/raytracer_golden.npz
+ * generated from that library: bit for bit with normalize := v / sqrt(dot(v, v))
+ * (tests/test_raytracer_pin_cpu.py), within 1e-5 relative with glm::normalize.
+ * Documented deviations: Q6 (guarded misses, as the shader's own getAllHits) and Q11
+ * (IEEE fminf/fmaxf where a zero direction component meets a slab plane: NaN).
+ * Secondary rays (orc_render) do not exist in the reference and are defined here.
  *
  * All citations are relative to /root/reference.
  */
@@ -150,6 +156,8 @@ void orc_get_ray(const orc_camera* cam, uint32_t x, uint32_t y,
 void orc_ray_triangle(const orc_ray* ray, const orc_triangle* tris,
                       const orc_mesh* meshes, uint32_t tri_index, orc_hit* out);
 uint32_t orc_intersect_box(const orc_ray* ray, const orc_node* node);
+/* the same with the shader's return code 2 (entry point near a box edge, :222-233; threshold 0.05 / (display_depth + 1)) */
+uint32_t orc_intersect_box_edge(const orc_ray* ray, const orc_node* node, int display_depth);
 void orc_closest_hit_bvh(const orc_ray* ray, const orc_node* flat,
                          const orc_triangle* tris, const orc_mesh* meshes,
                          orc_hit* out, uint64_t* nodes_visited);
