@@ -640,10 +640,10 @@ def main():
             if name in ALGO_BYTES:
                 gbs = ALGO_BYTES[name](n) * cnt / (tot * 1e-3) / 1e9
                 kern[name]["algorithmic_GBps"] = gbs
-        if "ploc_iteration_kernel" in kern:
+        if "ploc_loop_kernel" in kern:
             big = active[active > 1024].astype(np.float64)
-            kern["ploc_iteration_kernel"]["algorithmic_GBps"] = float(
-                (big * 40).sum() + (merges[: big.size].astype(np.float64) * 64).sum()) / (kern["ploc_iteration_kernel"]["ms_total"] * 1e-3) / 1e9
+            kern["ploc_loop_kernel"]["algorithmic_GBps"] = float(
+                (big * 40).sum() + (merges[: big.size].astype(np.float64) * 64).sum()) / (kern["ploc_loop_kernel"]["ms_total"] * 1e-3) / 1e9
         extras["kernels"] = kern
         peaks = {}
         try:

@@ -35,7 +35,7 @@ def build_oracle(force: bool = False) -> str:
     return ORACLE_SO
 
 
-def build_reference(caps=(65536, 1048576)) -> bool:
+def build_reference(caps=(65536, 1048576, 16777216)) -> bool:
     """Compile the reference's own bvh.cpp into oracle/_ref (only where /root/reference exists)."""
     if not os.path.isdir(REFERENCE_ROOT):
         return False
@@ -101,6 +101,7 @@ class Oracle:
         L.orc_hash_flat_nodes.argtypes = [vp, u32]
         L.orc_hash_flat_nodes.restype = u64
         L.orc_get_ray.argtypes = [vp, u32, u32, u32, u32, vp]
+        L.orc_get_rays.argtypes = [vp, u32, u32, u32, u32, vp]
         L.orc_ray_triangle.argtypes = [vp, vp, vp, u32, vp]
         L.orc_intersect_box.argtypes = [vp, vp]
         L.orc_intersect_box.restype = u32
@@ -231,11 +232,7 @@ class Oracle:
     # ---- traversal ----
     def get_rays(self, cam, width, height, denom_w, denom_h):
         rays = np.zeros(width * height, dtype=RAY)
-        one = np.zeros(1, dtype=RAY)
-        for y in range(height):
-            for x in range(width):
-                self.lib.orc_get_ray(_p(cam), x, y, denom_w, denom_h, _p(one))
-                rays[y * width + x] = one[0]
+        self.lib.orc_get_rays(_p(cam), width, height, denom_w, denom_h, _p(rays))
         return rays
 
     def trace_primary(self, flat, tris, meshes, cam, width, height, denom_w=None, denom_h=None, threads=0):
@@ -409,11 +406,14 @@ class ReferenceRaytracer:
         vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
         L.ref_rt_variant.restype = C.c_char_p
         L.ref_rt_undefined_w.restype = f32
+        L.ref_rt_set_threads.argtypes = [i32]
+        L.ref_rt_set_threads(os.cpu_count() or 1)   # the tests pin OMP_NUM_THREADS=1 for the reference's bvh.cpp (Q3)
         L.ref_rt_set_scene.argtypes = [vp, u32, vp, u32, u32, vp, u32, vp, u32]
         L.ref_rt_set_scene.restype = i32
         L.ref_rt_set_camera.argtypes = [vp]
         L.ref_rt_set_flags.argtypes = [i32, i32, i32]
         L.ref_rt_get_ray.argtypes = [f32, f32, vp]
+        L.ref_rt_trace_primary.argtypes = [u32, u32, u32, u32, vp, vp]
         L.ref_rt_ray_triangle.argtypes = [vp, vp, u64, vp]
         L.ref_rt_intersect_bvh.argtypes = [vp, vp, u64, vp]
         L.ref_rt_closest_hit_bvh.argtypes = [vp, u64, vp, vp]
@@ -461,6 +461,15 @@ class ReferenceRaytracer:
                 self.lib.ref_rt_get_ray(C.c_float(px), C.c_float(py), _p(one))
                 rays[y * width + x] = one[0]
         return rays
+
+    def trace_primary(self, width, height, denom_w=None, denom_h=None, want_rays=False):
+        """getClosestHitBVH of every pixel's getRay (whole frame, OpenMP over rows)."""
+        denom_w = (width // 16) * 16 if denom_w is None else denom_w
+        denom_h = (height // 16) * 16 if denom_h is None else denom_h
+        hits = np.zeros(width * height, dtype=HIT)
+        rays = np.zeros(width * height, dtype=RAY) if want_rays else None
+        self.lib.ref_rt_trace_primary(width, height, denom_w, denom_h, _p(hits), None if rays is None else _p(rays))
+        return (hits, rays) if want_rays else hits
 
     def ray_triangle(self, rays, tri_index):
         rays = np.ascontiguousarray(rays)

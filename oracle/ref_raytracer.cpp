@@ -32,6 +32,7 @@
 #include <limits>
 #include <vector>
 #include <cmath>
+#include <omp.h>
 
 #define GLM_FORCE_SWIZZLE
 #include <glm/glm.hpp>
@@ -88,6 +89,9 @@ std::vector<shader::Model> g_models;
 std::vector<shader::Material> g_materials;
 std::vector<shader::BVH_Node> g_nodes;
 
+int g_threads = 0;  // 0: omp_get_max_threads(); set per library so the process-wide OpenMP setting is left alone
+inline int threads() { return g_threads > 0 ? g_threads : omp_get_max_threads(); }
+
 struct HostRay { float o[4], d[4]; };
 struct HostHit { float b0, b1, b2, t; uint32_t did_hit, tri; };
 
@@ -115,6 +119,7 @@ const char* ref_rt_variant() {
 #endif
 }
 float ref_rt_undefined_w() { return RTR_UNDEFINED_W; }
+void ref_rt_set_threads(int n) { g_threads = n; }
 
 // The four SSBOs of scene.cpp:112-176, decoded from the HOST byte layouts exactly as std430 would read them:
 // triangles at stride 64 (the shader's struct names the second vec4 _P2 and the third _P1, Q8 -- the memory order
@@ -206,23 +211,43 @@ void ref_rt_get_ray(float pos_x, float pos_y, HostRay* out) {
     for (int k = 0; k < 4; ++k) { out->o[k] = r._Origin[k]; out->d[k] = r._Direction[k]; }
 }
 
+// The closest hits of a whole frame: pos as main() computes it (:303-305 restated here in two lines -- ref_rt_dispatch
+// below runs main() itself and pins them), then getRay and getClosestHitBVH verbatim.  Pixels outside
+// [0, denom_w) x [0, denom_h) have no invocation (Q5) and keep a zero record.  rays_out is nullable.
+void ref_rt_trace_primary(uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h, HostHit* hits_out,
+                          HostRay* rays_out) {
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads())
+    for (int64_t y = 0; y < (int64_t)height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            const size_t i = (size_t)y * width + x;
+            std::memset(&hits_out[i], 0, sizeof(HostHit));
+            if (rays_out) std::memset(&rays_out[i], 0, sizeof(HostRay));
+            if (x >= denom_w || (uint32_t)y >= denom_h) continue;
+            shader::vec2 pos(float(int(x)) / denom_w, float(int(y)) / denom_h);
+            shader::Ray r = shader::getRay(pos);
+            shader::vec4 c(0.f, 0.f, 0.f, 0.f);
+            from_hit(shader::getClosestHitBVH(r, 0u, c), hits_out[i]);
+            if (rays_out) for (int k = 0; k < 4; ++k) { rays_out[i].o[k] = r._Origin[k]; rays_out[i].d[k] = r._Direction[k]; }
+        }
+}
+
 // rayTriangleIntersection, :102-147
 void ref_rt_ray_triangle(const HostRay* rays, const uint32_t* tri_index, uint64_t n, HostHit* out) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads())
     for (int64_t i = 0; i < (int64_t)n; ++i)
         from_hit(shader::rayTriangleIntersection(to_ray(rays[i]), tri_index[i]), out[i]);
 }
 
 // intersectBVH, :182-237 (0 / 1 / 2) on node node_index[i] of the bound node array
 void ref_rt_intersect_bvh(const HostRay* rays, const uint32_t* node_index, uint64_t n, uint32_t* out) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(threads())
     for (int64_t i = 0; i < (int64_t)n; ++i)
         out[i] = shader::intersectBVH(to_ray(rays[i]), shader::uBVH_Nodes[node_index[i]]);
 }
 
 // getClosestHitBVH(ray, 0, bvhColor), :246-295; bvh_color_out (nullable): 4 floats per ray, starting from (0,0,0,0) (:321)
 void ref_rt_closest_hit_bvh(const HostRay* rays, uint64_t n, HostHit* out, float* bvh_color_out) {
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         shader::vec4 c(0.f, 0.f, 0.f, 0.f);
         from_hit(shader::getClosestHitBVH(to_ray(rays[i]), 0u, c), out[i]);
@@ -232,7 +257,7 @@ void ref_rt_closest_hit_bvh(const HostRay* rays, uint64_t n, HostHit* out, float
 
 // getAllHits, :149-157 -- the shader's own brute-force path (disabled at :309-312), no undefined reads
 void ref_rt_all_hits(const HostRay* rays, uint64_t n, HostHit* out) {
-#pragma omp parallel for schedule(dynamic, 16)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         shader::Hit closest = RTR_UNDEFINED_HIT;
         closest._DidHit = 0;  // :308
@@ -263,7 +288,7 @@ void ref_rt_dispatch(uint32_t groups_x, uint32_t groups_y, uint32_t width, uint3
     shader::oImage.height = height;
     shader::gl_NumWorkGroups = shader::uvec3(groups_x, groups_y, 1);
     const int64_t ny = 16 * (int64_t)groups_y, nx = 16 * (int64_t)groups_x;
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads())
     for (int64_t y = 0; y < ny; ++y)
         for (int64_t x = 0; x < nx; ++x) {
             shader::gl_GlobalInvocationID = shader::uvec3((uint32_t)x, (uint32_t)y, 0);

@@ -526,6 +526,17 @@ void orc_get_ray(const orc_camera* cam, uint32_t x, uint32_t y,
     ray->direction[3] = 0.f;
 }
 
+/* every pixel's ray, row-major; pixels outside the denominators (Q5) keep a zero record */
+void orc_get_rays(const orc_camera* cam, uint32_t width, uint32_t height,
+                  uint32_t denom_w, uint32_t denom_h, orc_ray* out) {
+    for (uint32_t y = 0; y < height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            orc_ray* r = &out[(size_t)y * width + x];
+            memset(r, 0, sizeof(*r));
+            if (x < denom_w && y < denom_h) orc_get_ray(cam, x, y, denom_w, denom_h, r);
+        }
+}
+
 /* world-space vertices in SHADER naming (Q8): shader _P1 = host _P2, shader _P2 = host _P1 */
 static void shader_vertices(const orc_triangle* t, const orc_mesh* meshes,
                             float p0[4], float p1[4], float p2[4]) {

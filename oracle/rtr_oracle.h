@@ -153,6 +153,8 @@ uint64_t orc_hash_flat_nodes(const orc_node* flat, uint32_t nb_nodes);
 /* ---- traversal (raytracer.glsl:92-147,182-295,299-331) ---- */
 void orc_get_ray(const orc_camera* cam, uint32_t x, uint32_t y,
                  uint32_t denom_w, uint32_t denom_h, orc_ray* out);
+void orc_get_rays(const orc_camera* cam, uint32_t width, uint32_t height,
+                  uint32_t denom_w, uint32_t denom_h, orc_ray* out /* [height*width] */);
 void orc_ray_triangle(const orc_ray* ray, const orc_triangle* tris,
                       const orc_mesh* meshes, uint32_t tri_index, orc_hit* out);
 uint32_t orc_intersect_box(const orc_ray* ray, const orc_node* node);

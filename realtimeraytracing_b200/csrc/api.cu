@@ -65,14 +65,14 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 
 void bvh_free_arrays(rtr_bvh* b) {
     void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->order, b->codes64, b->cin, b->cout, b->tile_status,
-                    b->state, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
+                    b->state, b->ctl, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
                     b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     b->codes = b->tri_idx = b->isize = b->ipos = b->order = b->cin = b->cout = nullptr;
     b->codes64 = nullptr; b->codes64_cap = 0;
     b->node = nullptr;
-    b->tile_status = nullptr; b->state = nullptr;
+    b->tile_status = nullptr; b->state = nullptr; b->ctl = nullptr;
     b->trace_active = b->trace_merges = b->iter_first_id = nullptr;
     b->bounds12 = nullptr; b->ordered6 = nullptr; b->flat = nullptr; b->tparams = nullptr;
     b->tris_own = nullptr; b->meshes_own = nullptr; b->tris_own_cap = b->meshes_own_cap = 0;
@@ -103,7 +103,8 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     RTR_CHECK(dev_alloc(ctx, &b->cin, cap));
     RTR_CHECK(dev_alloc(ctx, &b->cout, cap));
     RTR_CHECK(dev_alloc(ctx, &b->tile_status, tiles));
-    RTR_CHECK(dev_alloc(ctx, &b->state, 2));
+    RTR_CHECK(dev_alloc(ctx, &b->state, 3));
+    RTR_CHECK(dev_alloc(ctx, &b->ctl, 4));
     RTR_CHECK(dev_alloc(ctx, &b->trace_active, kMaxPlocIterations));
     RTR_CHECK(dev_alloc(ctx, &b->trace_merges, kMaxPlocIterations));
     RTR_CHECK(dev_alloc(ctx, &b->iter_first_id, kMaxPlocIterations + 1));
@@ -145,6 +146,7 @@ int bvh_build_common(rtr_ctx* ctx, const rtr_triangle* tris_dev, uint32_t n, uin
 template <typename F>
 int with_bvh(rtr_bvh* b, bool need_build_arrays, F&& f) {
     if (!b) return RTR_E_INVALID;
+    RTR_CHECK(rtr_bvh_finish(b));
     if (!b->built) return rtr_set_error(b->ctx, RTR_E_STATE, "BVH has not been built");
     if (need_build_arrays && b->adopted)
         return rtr_set_error(b->ctx, RTR_E_STATE, "adopted BVH has no build arrays (flat nodes only)");
@@ -586,8 +588,7 @@ static int build_host_impl(rtr_ctx* ctx, const rtr_triangle* tris, uint32_t n, u
         RTR_CUDA(ctx, cudaMemcpyAsync(b->tris_own, tris, (size_t)array_len * sizeof(rtr_triangle), cudaMemcpyHostToDevice, ctx->stream));
         RTR_CUDA(ctx, cudaMemcpyAsync(b->meshes_own, meshes, (size_t)nb_meshes * sizeof(rtr_mesh), cudaMemcpyHostToDevice, ctx->stream));
         RTR_CHECK(bvh_build_common(ctx, b->tris_own, n, array_len, b->meshes_own, nb_meshes, radius, b));
-        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return RTR_OK;
+        return rtr_bvh_finish(b);  // synchronous like the reference ctor (bvh.cpp:22): waits and reports
     };
     const int r = body();
     if (r != RTR_OK && fresh) { rtr_bvh_destroy(b); return r; }
@@ -655,6 +656,7 @@ int rtr_bvh_enable_stage_timing(rtr_bvh* b, int enable) {
 
 int rtr_bvh_stage_ms(rtr_bvh* b, float out[6]) {
     if (!b || !out) return RTR_E_INVALID;
+    RTR_CHECK(rtr_bvh_finish(b));
     if (!b->timing || !b->built || b->adopted) return rtr_set_error(b->ctx, RTR_E_STATE, "stage timing not enabled for the last build");
     RTR_CUDA(b->ctx, cudaEventSynchronize(b->ev[5]));
     for (int i = 0; i < 5; ++i) RTR_CUDA(b->ctx, cudaEventElapsedTime(&out[i], b->ev[i], b->ev[i + 1]));
@@ -765,6 +767,7 @@ int rtr_bvh_stack_overflows(const rtr_bvh* b, uint32_t* count_out) {
     if (!b) return RTR_E_INVALID;
     rtr_ctx* ctx = b->ctx;
     if (!count_out) return rtr_set_error(ctx, RTR_E_INVALID, "stack_overflows: NULL output");
+    RTR_CHECK(rtr_bvh_finish(const_cast<rtr_bvh*>(b)));
     if (!b->built || !b->tparams) return rtr_set_error(ctx, RTR_E_STATE, "stack_overflows: the BVH has not been built");
     RTR_CHECK(fetch_overflows(ctx, b, count_out));
     RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->stack_overflows, 0, sizeof(uint32_t), ctx->stream));
@@ -782,6 +785,7 @@ int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam,
 
 int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height,
                       uint32_t denom_w, uint32_t denom_h, uint32_t flags, rtr_hit* hits_out) {
+    if (b) RTR_CHECK(rtr_bvh_finish(const_cast<rtr_bvh*>(b)));  // a build submitted with rtr_bvh_build_dev may still owe its verdict
     RTR_CHECK(trace_args_ok(ctx, b, cam));
     RTR_CHECK(order_ok(ctx, b, flags));
     if (!hits_out) return rtr_set_error(ctx, RTR_E_INVALID, "trace_primary: NULL output");
@@ -812,6 +816,7 @@ int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays_dev, 
 
 int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t n_rays, int any_hit, const float* t_max,
                    uint32_t flags, rtr_hit* hits_out) {
+    if (b) RTR_CHECK(rtr_bvh_finish(const_cast<rtr_bvh*>(b)));  // a build submitted with rtr_bvh_build_dev may still owe its verdict
     RTR_CHECK(trace_args_ok(ctx, b, n_rays ? (const void*)rays : (const void*)b));
     RTR_CHECK(order_ok(ctx, b, flags));
     if (n_rays == 0) return RTR_OK;
@@ -983,6 +988,7 @@ int rtr_bvh_depth_overlay(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam,
 int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t width, uint32_t height, uint32_t denom_w,
                uint32_t denom_h, uint32_t row0, uint32_t row1, uint32_t bounces, int shadow, const float light_pos[3],
                uint32_t flags, float* rgba_out, rtr_hit* hits_out, uint64_t* rays_traced) {
+    if (b) RTR_CHECK(rtr_bvh_finish(const_cast<rtr_bvh*>(b)));  // a build submitted with rtr_bvh_build_dev may still owe its verdict
     RTR_CHECK(trace_args_ok(ctx, b, cam));
     RTR_CHECK(order_ok(ctx, b, flags));
     if (shadow && !light_pos) return rtr_set_error(ctx, RTR_E_INVALID, "render: shadow rays need a light position");

@@ -56,7 +56,8 @@ struct rtr_bvh {
     uint32_t* cin = nullptr;       // [cap] active list, ping
     uint32_t* cout = nullptr;      // [cap] active list, pong
     uint64_t* tile_status = nullptr;  // [ceil(cap/tile)] decoupled look-back words
-    PlocState* state = nullptr;    // [2]
+    PlocState* state = nullptr;    // [3]: loop state by iteration parity, [2] = final (see ploc.cu)
+    uint32_t* ctl = nullptr;       // [4] barrier counters of the persistent build kernels
     uint32_t* trace_active = nullptr;   // [kMaxPlocIterations]
     uint32_t* trace_merges = nullptr;   // [kMaxPlocIterations]
     uint32_t* iter_first_id = nullptr;  // [kMaxPlocIterations + 1] first cluster id created by iteration i
@@ -82,8 +83,8 @@ struct rtr_bvh {
     const uint4* pairs_view = nullptr;
 
     // host mirrors of the last build
-    uint32_t iterations = 0;
-    std::vector<uint32_t> h_first_id;  // [iterations + 1]
+    uint32_t iterations = 0;       // valid after rtr_bvh_finish
+    bool finish_pending = false;   // the last build's verdict has not been read back yet
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -299,6 +300,7 @@ TRAV_HD void trav_axis_vals4(float c, uint32_t ebyte, uint32_t qa, uint32_t qb, 
 
 // ploc.cu
 int rtr_bvh_run_build(rtr_bvh* b);
+int rtr_bvh_finish(rtr_bvh* b);  // waits for the last build's verdict (converged? iterations) if it is still pending
 int rtr_bvh_export_clusters(rtr_bvh* b, rtr_node* clusters_dev, uint32_t* parent_dev, uint32_t* left_dev,
                             uint32_t* right_dev, uint8_t* is_leaf_dev);
 int rtr_bvh_compute_trace_params(rtr_bvh* b);

@@ -23,6 +23,9 @@ struct rtr_ctx {
     int reserved_sms = 0;  // SMs the persistent traversal leaves free (rtr_ctx_reserve_sms)
     uint32_t* sm_table = nullptr;  // 2 x [1 + 1024], per launch: SMs claimed so far, then one state word per %smid
     uint32_t sm_table_turn = 0;
+    int ploc_ctas_per_sm[2] = {0, 0};  // persistent PLOC loop kernel (full radius / masked radius), resident CTAs per SM
+    int flatten_ctas_per_sm = 0;
+    int trace_ctas_per_sm = 0;     // resident CTAs per SM of the persistent traversal kernel on this device (0: not asked yet)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     uint64_t launches = 0;

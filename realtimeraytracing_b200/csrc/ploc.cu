@@ -46,7 +46,6 @@ constexpr int kStage = kEval + 2 * kR;           // positions staged (tile + 2 k
 constexpr int kStageQ = kStage / kPP;            // staged arrays are stored [e % kPP][e / kPP] (conflict free)
 constexpr int kStagePT = (kStage + kPT - 1) / kPT;  // staged positions gathered per thread
 constexpr uint32_t kTailN = 1024;
-constexpr int kChunk = 8;                        // iteration launches between host checks
 static_assert(kR % kPP == 0 && kR == 16 && kPP == 4, "search geometry is written for +-16 and 4 positions per thread");
 static_assert(kTileT == kEval - 2 * kR, "tile geometry");
 static_assert(kStage % kPP == 0, "staging layout");
@@ -219,10 +218,15 @@ edge_bound_kernel(const rtr_triangle* __restrict__ tris, const rtr_mesh* __restr
     publish_edge_bound(e2, tparams);
 }
 
-__global__ void ploc_state_init_kernel(PlocState* state, uint32_t n, uint32_t* iter_first_id) {
+// state[0/1]: the loop state, double buffered by iteration parity; state[2]: where the loop kernel leaves off
+// and the tail kernel finishes (what the flatten and rtr_bvh_finish read); ctl[0/1]: barrier counters of the
+// two persistent kernels
+__global__ void ploc_state_init_kernel(PlocState* state, uint32_t n, uint32_t* iter_first_id, uint32_t* ctl) {
     state[0].n_active = n; state[0].total = n; state[0].iter = 0; state[0].tile_counter = 0;
     state[1] = state[0];
+    state[2] = state[0];
     iter_first_id[0] = n;
+    ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -276,36 +280,19 @@ __device__ __forceinline__ void search_block(const Smem& s, int dl, int e0, int 
 
 // FULL: radius == 16, the reference's PlocParams::_SEARCH_RADIUS (bvh.hpp:66); otherwise candidates farther
 // than `radius` positions away are masked out.
+//
+// One tile of one iteration: the positions [tile * kTileT, (tile + 1) * kTileT) of the active list are decided.
+// `cur` state values (n, total, iter) are passed in; the tile that closes the look-back chain writes `nxt`.
 template <bool FULL>
-__global__ void __launch_bounds__(kPT, RTR_PLOC_MINB)
-ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
-                      uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
-                      float4* __restrict__ node, uint32_t* __restrict__ isize,
-                      PlocState* __restrict__ state, uint64_t* __restrict__ tile_status,
-                      uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
-                      uint32_t* __restrict__ iter_first_id) {
-    __shared__ IterSmem s;
-
+__device__ __forceinline__ void ploc_process_tile(IterSmem& s, const uint32_t tile, const uint32_t tiles,
+                                                  const uint32_t n, const uint32_t total, const uint32_t iter,
+                                                  const uint32_t n_leaves, const int radius,
+                                                  const uint32_t* __restrict__ cin, uint32_t* __restrict__ cout,
+                                                  float4* __restrict__ node, uint32_t* __restrict__ isize,
+                                                  PlocState* __restrict__ nxt, uint64_t* __restrict__ tile_status,
+                                                  uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
+                                                  uint32_t* __restrict__ iter_first_id) {
     const int tid = (int)threadIdx.x;
-    PlocState* cur = &state[launch_idx & 1u];
-    PlocState* nxt = &state[(launch_idx + 1u) & 1u];
-    const uint32_t n = cur->n_active, total = cur->total, iter = cur->iter;
-    if (n <= kTailN) {  // finished (or the tail kernel's job): carry the state to the next launch
-        if (blockIdx.x == 0 && tid == 0) {
-            nxt->n_active = n; nxt->total = total; nxt->iter = iter; nxt->tile_counter = 0;
-        }
-        return;
-    }
-    const uint32_t tiles = (n + kTileT - 1) / kTileT;
-    // the grid is sized for an upper bound of n that the host refreshes every kChunk launches: surplus CTAs
-    // leave without touching the tile counter
-    if (blockIdx.x >= tiles) return;
-    const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
-    uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
-    // tiles are handed out in start order, so the look-back below only ever waits on running tiles
-    if (tid == 0) s.tile = atomicAdd(&cur->tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = s.tile;  // < tiles: exactly `tiles` CTAs draw a number
     const int t0 = (int)(tile * kTileT);
     const int base = t0 - 2 * kR;  // position of staged slot 0
 
@@ -317,7 +304,7 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
 #pragma unroll
         for (int r = 0; r < kStagePT; ++r) {
             const int e = tid + r * kPT, pos = base + e;
-            sid[r] = (e < kStage && pos >= 0 && pos < (int)n) ? cin[pos] : RTR_NONE;
+            sid[r] = (e < kStage && pos >= 0 && pos < (int)n) ? __ldcg(cin + pos) : RTR_NONE;
         }
         Box sb[kStagePT];
 #pragma unroll
@@ -483,8 +470,8 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
                 store_box(node, new_id,
                           make_float4(fminf(lo[i].x, plo.x), fminf(lo[i].y, plo.y), fminf(lo[i].z, plo.z), fmaxf(lo[i].w, plo.w)),
                           make_float4(fmaxf(hi[i].x, phi.x), fmaxf(hi[i].y, phi.y), __uint_as_float(cl), __uint_as_float(cr)));
-                const uint32_t sl = cl < n_leaves ? 1u : isize[cl - n_leaves];
-                const uint32_t sr = cr < n_leaves ? 1u : isize[cr - n_leaves];
+                const uint32_t sl = cl < n_leaves ? 1u : __ldcg(isize + (cl - n_leaves));  // written by other SMs in earlier iterations
+                const uint32_t sr = cr < n_leaves ? 1u : __ldcg(isize + (cr - n_leaves));
                 isize[new_id - n_leaves] = sl + sr + 1u;
                 out_id = new_id;
                 ++ex_lo_local;
@@ -492,6 +479,67 @@ ploc_iteration_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
             if (!is_hi[i]) cout[(uint32_t)(base + q) - (hi_base + ex_hi_local)] = out_id;
             else ++ex_hi_local;
         }
+    }
+}
+
+
+// grid-wide barrier of the persistent kernels below (cooperative launch: every CTA is resident).  `counter` only
+// grows: barrier k is passed once it reaches gridDim.x * k.  The fences order this CTA's writes before its arrival
+// and invalidate the SM's L1 after the wait (data written by other SMs before the barrier is read after it).
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& generation) {
+    __syncthreads();
+    ++generation;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const uint32_t target = gridDim.x * generation;
+        while (ld_acquire_u32(counter) < target) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// The whole PLOC loop down to kTailN clusters as ONE persistent kernel (cooperative launch, one CTA per resident
+// slot): per iteration the CTAs draw tiles from a counter, then meet at a grid barrier -- no launch per iteration, no
+// host round trip to size a grid or to learn the iteration count (the reference's `while (_Iteration > 1)`,
+// bvh.cpp:62, runs on the device).  ctl[0] = barrier counter, ctl[1] = status (see BuildStatus).
+template <bool FULL>
+__global__ void __launch_bounds__(kPT, RTR_PLOC_MINB)
+ploc_loop_kernel(uint32_t n_leaves, int radius, uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
+                 float4* __restrict__ node, uint32_t* __restrict__ isize,
+                 PlocState* __restrict__ state, uint64_t* __restrict__ tile_status,
+                 uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
+                 uint32_t* __restrict__ iter_first_id, uint32_t* __restrict__ barrier_counter) {
+    __shared__ IterSmem s;
+    const int tid = (int)threadIdx.x;
+    uint32_t generation = 0u, parity = 0u, prev_n = 0xFFFFFFFFu;
+    while (true) {
+        PlocState* cur = &state[parity];
+        PlocState* nxt = &state[parity ^ 1u];
+        const uint32_t n = ld_relaxed_u32(&cur->n_active), total = ld_relaxed_u32(&cur->total), iter = ld_relaxed_u32(&cur->iter);
+        // done, handed to the tail kernel, or stuck (non-finite areas never merge, Q4: the reference would spin forever)
+        if (n <= kTailN || n >= prev_n || iter >= kMaxPlocIterations) break;
+        prev_n = n;
+        const uint32_t tiles = (n + kTileT - 1) / kTileT;
+        const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
+        uint32_t* __restrict__ cout = (iter & 1u) ? buf0 : buf1;
+        while (true) {
+            // tiles are handed out in start order, so the look-back only ever waits on tiles of running CTAs
+            if (tid == 0) s.tile = atomicAdd(&cur->tile_counter, 1u);
+            __syncthreads();
+            const uint32_t tile = s.tile;
+            if (tile >= tiles) break;
+            ploc_process_tile<FULL>(s, tile, tiles, n, total, iter, n_leaves, radius, cin, cout, node, isize, nxt, tile_status,
+                                    trace_active, trace_merges, iter_first_id);
+            __syncthreads();  // the staging area is reused by the next tile
+        }
+        grid_barrier(barrier_counter, generation);
+        parity ^= 1u;
+    }
+    if (blockIdx.x == 0 && tid == 0) {  // what the tail kernel and the flatten start from
+        const PlocState* cur = &state[parity];
+        state[2].n_active = ld_relaxed_u32(&cur->n_active); state[2].total = ld_relaxed_u32(&cur->total);
+        state[2].iter = ld_relaxed_u32(&cur->iter); state[2].tile_counter = 0u;
     }
 }
 
@@ -507,7 +555,7 @@ struct TailSmem {
 };
 
 __global__ void __launch_bounds__(kTailN)
-ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
+ploc_tail_kernel(uint32_t n_leaves, int radius,
                  const uint32_t* __restrict__ buf0, const uint32_t* __restrict__ buf1,
                  float4* __restrict__ node, uint32_t* __restrict__ isize,
                  PlocState* __restrict__ state, uint32_t* __restrict__ trace_active,
@@ -515,13 +563,9 @@ ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
     extern __shared__ __align__(16) unsigned char tail_raw[];
     TailSmem& s = *reinterpret_cast<TailSmem*>(tail_raw);
     const uint32_t tid = threadIdx.x;
-    PlocState* cur = &state[launch_idx & 1u];
-    PlocState* nxt = &state[(launch_idx + 1u) & 1u];
-    uint32_t n = cur->n_active, total = cur->total, iter = cur->iter;
-    if (n > kTailN) {  // not ours yet: carry the state
-        if (tid == 0) { nxt->n_active = n; nxt->total = total; nxt->iter = iter; nxt->tile_counter = 0; }
-        return;
-    }
+    PlocState* fin = &state[2];
+    uint32_t n = fin->n_active, total = fin->total, iter = fin->iter;
+    if (n > kTailN) return;  // the loop kernel gave up (nothing merges any more, Q4): rtr_bvh_finish reports it
     const uint32_t* __restrict__ cin = (iter & 1u) ? buf1 : buf0;
     int cur_buf = 0;
     if (tid < n) {
@@ -576,7 +620,7 @@ ploc_tail_kernel(uint32_t launch_idx, uint32_t n_leaves, int radius,
         __syncthreads();
         if (merges == 0) break;  // non-finite areas (Q4): the reference would spin forever
     }
-    if (tid == 0) { nxt->n_active = n; nxt->total = total; nxt->iter = iter; nxt->tile_counter = 0; }
+    if (tid == 0) { fin->n_active = n; fin->total = total; fin->iter = iter; fin->tile_counter = 0; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -599,7 +643,7 @@ __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t
 __device__ __forceinline__ void place_children(uint32_t c, uint32_t n_leaves, const float4* __restrict__ node,
                                                const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
                                                uint32_t* __restrict__ order) {
-    const uint32_t p = ipos[c - n_leaves];
+    const uint32_t p = __ldcg(ipos + (c - n_leaves));  // written by another SM one level up (same kernel): L2, not L1
     const float4 hi = __ldg(node + 2 * (size_t)c + 1);
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
     const uint32_t size_l = L < n_leaves ? 1u : isize[L - n_leaves];
@@ -610,23 +654,45 @@ __device__ __forceinline__ void place_children(uint32_t c, uint32_t n_leaves, co
     if (R >= n_leaves) ipos[R - n_leaves] = pos_r;
 }
 
-__global__ void __launch_bounds__(256)
-flatten_level_kernel(uint32_t first, uint32_t count, uint32_t n_leaves, const float4* __restrict__ node,
-                     const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos, uint32_t* __restrict__ order) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) place_children(first + i, n_leaves, node, isize, ipos, order);
-}
-
-// levels [it_lo, it_hi] processed last-first by one CTA (the top of the tree: many tiny levels)
-__global__ void __launch_bounds__(1024)
-flatten_small_levels_kernel(const uint32_t* __restrict__ iter_first_id, int it_hi, int it_lo, uint32_t n_leaves,
-                            const float4* __restrict__ node, const uint32_t* __restrict__ isize,
-                            uint32_t* __restrict__ ipos, uint32_t* __restrict__ order) {
-    for (int it = it_hi; it >= it_lo; --it) {
+// All creation levels in ONE persistent kernel (cooperative launch), last iteration first: the level table
+// (iter_first_id) and the iteration count stay on the device, the host launches this without knowing either.  A run
+// of small levels (the top of the tree: the tail's iterations) is walked by CTA 0 alone with __syncthreads between
+// levels; a large level is spread over the grid and closed by a grid barrier.
+constexpr uint32_t kSmallLevel = 2048;
+constexpr int kFlattenBlock = 512;
+__global__ void __launch_bounds__(kFlattenBlock)
+flatten_positions_kernel(const PlocState* __restrict__ state, const uint32_t* __restrict__ iter_first_id, uint32_t n_leaves,
+                         const float4* __restrict__ node, const uint32_t* __restrict__ isize,
+                         uint32_t* __restrict__ ipos, uint32_t* __restrict__ order, uint32_t* __restrict__ barrier_counter) {
+    const PlocState fin = state[2];
+    if (fin.n_active != 1u || fin.total != 2u * n_leaves - 1u) return;  // the build did not converge: nothing to place
+    uint32_t generation = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // root 2n-2 -> position 0 (scene.cpp:205); its level is CTA 0's
+        order[0] = 2u * n_leaves - 2u;
+        ipos[n_leaves - 2u] = 0u;
+    }
+    __syncthreads();
+    int it = (int)fin.iter - 1;
+    while (it >= 0) {
         const uint32_t first = iter_first_id[it], count = iter_first_id[it + 1] - first;
-        for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
-            place_children(first + i, n_leaves, node, isize, ipos, order);
-        __syncthreads();
+        if (count > kSmallLevel) {
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+                place_children(first + i, n_leaves, node, isize, ipos, order);
+            --it;
+            grid_barrier(barrier_counter, generation);
+        } else {
+            int lo = it;
+            while (lo - 1 >= 0 && iter_first_id[lo] - iter_first_id[lo - 1] <= kSmallLevel) --lo;
+            if (blockIdx.x == 0) {
+                for (int l = it; l >= lo; --l) {
+                    const uint32_t f = iter_first_id[l], c = iter_first_id[l + 1] - f;
+                    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) place_children(f + i, n_leaves, node, isize, ipos, order);
+                    __syncthreads();
+                }
+            }
+            it = lo - 1;
+            if (it >= 0) grid_barrier(barrier_counter, generation);
+        }
     }
 }
 
@@ -652,10 +718,20 @@ __device__ __forceinline__ void store_inner_record(uint4* __restrict__ pairs, ui
 // (bvh.cuh: the compressed child pair of an inner node, box + world-space vertices of a leaf).  All stores of
 // a warp are contiguous; the left child's record is the next lane's own (position p + 1).
 __global__ void __launch_bounds__(256)
-flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __restrict__ order,
+flatten_emit_kernel(const PlocState* __restrict__ state, uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __restrict__ order,
                     const float4* __restrict__ node, const uint32_t* __restrict__ isize,
                     const float4* __restrict__ wtri, rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (state[2].n_active != 1u || state[2].total != nb_nodes) {
+        // The build did not converge (non-finite triangle data, Q4; rtr_bvh_finish reports it).  Leave a tree that is
+        // safe to trace: one leaf with an empty box, which no ray enters.
+        if (p == 0) {
+            const float4 lo = make_float4(INFINITY, INFINITY, INFINITY, -INFINITY), hi = make_float4(-INFINITY, -INFINITY, 0.f, 0.f);
+            store_node(flat, 0, lo, hi, 0u, 0u, 0u, 0u);
+            store_leaf_record(pairs, 0, lo, hi, wtri, 0u);
+        }
+        return;
+    }
     const bool live = p < nb_nodes;
     const uint32_t c = live ? order[p] : 0u;
     const Box me = load_box(node, c);
@@ -684,8 +760,6 @@ flatten_emit_kernel(uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __rest
                       br.lo, make_float2(br.hi.x, br.hi.y), lleaf, rleaf, pos_r, o0, o1);
     store_inner_record(pairs, p, o0, o1);
 }
-
-__global__ void flatten_root_kernel(uint32_t* order, uint32_t root) { order[0] = root; }
 
 __global__ void flatten_single_leaf_kernel(const float4* node, const float4* wtri, rtr_node* flat, uint4* pairs) {
     const Box bx_ = load_box(node, 0); const float4 lo = bx_.lo, hi = bx_.hi;
@@ -726,9 +800,10 @@ pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t
 // Second half of every inner traversal record (bvh.cuh): the four grandchild slots on the node's own grid, for the
 // traversal's wide step.  One thread per flat index, after the first halves and the flat nodes are written.
 __global__ void __launch_bounds__(256)
-pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* __restrict__ pairs) {
+pack_quads_kernel(const PlocState* __restrict__ state, const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* __restrict__ pairs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_nodes) return;
+    if (state && (state[2].n_active != 1u || state[2].total != nb_nodes)) return;  // failed build: see flatten_emit_kernel
     const uint4* me = reinterpret_cast<const uint4*>(flat + i);
     const uint4 links = __ldg(me + 2);
     if (links.y == 0u && links.z == 0u) return;
@@ -837,7 +912,7 @@ int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
     pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->wtri_view,
                                                                  b->pairs_own, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
-    pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->pairs_own);
+    pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nullptr, b->flat_view, nc, b->pairs_own);
     RTR_LAUNCH_CHECK(ctx);
     b->pairs_view = b->pairs_own;
     return RTR_OK;
@@ -878,102 +953,64 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     leaf_init_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b->tris, b->meshes, b->tri_idx, n, b->node,
                                                                b->cin, b->wtri, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
-    ploc_state_init_kernel<<<1, 1, 0, ctx->stream>>>(b->state, n, b->iter_first_id);
+    ploc_state_init_kernel<<<1, 1, 0, ctx->stream>>>(b->state, n, b->iter_first_id, b->ctl);
     RTR_LAUNCH_CHECK(ctx);
     RTR_CHECK(record(b, 3));
 
-    // 4. PLOC loop
-    PlocState* h_state = static_cast<PlocState*>(ctx->pinned);
-    uint32_t launch_idx = 0;
-    uint32_t bound_n = n;  // upper bound of n_active, refreshed from the device every kChunk launches
-    static bool tail_configured = false;
-    if (!tail_configured) {
-
-        RTR_CUDA(ctx, cudaFuncSetAttribute(ploc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(TailSmem)));
-        tail_configured = true;
-    }
-    uint32_t last_iter = 0;
-    while (bound_n > kTailN) {
-        const uint32_t tiles = (bound_n + kTileT - 1) / kTileT;
-        for (int k = 0; k < kChunk; ++k) {
-            RTR_PROF(ctx, "ploc_iteration_kernel");
-            auto kern = (radius == kR) ? ploc_iteration_kernel<true> : ploc_iteration_kernel<false>;
-            kern<<<tiles, kPT, 0, ctx->stream>>>(
-                launch_idx, n, radius, b->cin, b->cout, b->node, b->isize, b->state, b->tile_status,
-                b->trace_active, b->trace_merges, b->iter_first_id);
-            RTR_LAUNCH_CHECK(ctx);
-            ++launch_idx;
+    // 4. PLOC loop: one persistent kernel down to kTailN clusters, one CTA for the rest.  Nothing here waits for
+    //    the device: iteration count, level table and the verdict stay there (rtr_bvh_finish reads them on demand).
+    RTR_CUDA(ctx, cudaFuncSetAttribute(ploc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+    if (n > kTailN) {
+        const bool full = radius == kR;
+        const void* kern = full ? (const void*)ploc_loop_kernel<true> : (const void*)ploc_loop_kernel<false>;
+        int& per_sm = full ? ctx->ploc_ctas_per_sm[0] : ctx->ploc_ctas_per_sm[1];
+        if (per_sm == 0) {
+            int c = 0;
+            RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, kPT, 0));
+            per_sm = c < 1 ? 1 : c;
         }
-        RTR_CUDA(ctx, cudaMemcpyAsync(h_state, &b->state[launch_idx & 1u], sizeof(PlocState), cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h_state->n_active > kTailN && h_state->iter == last_iter)
-            return rtr_set_error(ctx, RTR_E_INVALID, "PLOC made no progress (non-finite triangle data?)");
-        if (h_state->n_active >= bound_n && h_state->n_active > kTailN)
-            return rtr_set_error(ctx, RTR_E_INVALID, "PLOC iteration merged nothing (non-finite triangle data?)");
-        if (h_state->iter >= kMaxPlocIterations)
-            return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "more than %u PLOC iterations (degenerate input)", kMaxPlocIterations);
-        last_iter = h_state->iter;
-        bound_n = h_state->n_active;
+        const uint32_t tiles = (n + kTileT - 1) / kTileT;
+        uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
+        if (grid > tiles) grid = tiles;
+        uint32_t n_arg = n; int radius_arg = radius;
+        uint32_t* ctl0 = b->ctl;
+        void* args[] = {&n_arg, &radius_arg, &b->cin, &b->cout, &b->node, &b->isize, &b->state, &b->tile_status,
+                        &b->trace_active, &b->trace_merges, &b->iter_first_id, &ctl0};
+        RTR_PROF(ctx, "ploc_loop_kernel");
+        RTR_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kPT), args, 0, ctx->stream));
+        RTR_LAUNCH_CHECK(ctx);
     }
     RTR_PROF(ctx, "ploc_tail_kernel");
-    ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(launch_idx, n, radius, b->cin, b->cout, b->node,
-                                                                   b->isize, b->state, b->trace_active,
-                                                                   b->trace_merges, b->iter_first_id);
+    ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(n, radius, b->cin, b->cout, b->node, b->isize, b->state,
+                                                                   b->trace_active, b->trace_merges, b->iter_first_id);
     RTR_LAUNCH_CHECK(ctx);
-    ++launch_idx;
-    RTR_CUDA(ctx, cudaMemcpyAsync(h_state, &b->state[launch_idx & 1u], sizeof(PlocState), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (h_state->n_active != 1 || h_state->total != 2 * n - 1)
-        return rtr_set_error(ctx, RTR_E_INVALID, "PLOC did not converge: %u clusters left, %u created (non-finite input?)",
-                             h_state->n_active, h_state->total);
-    if (h_state->iter > kMaxPlocIterations)
-        return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "more than %u PLOC iterations (degenerate input)", kMaxPlocIterations);
-    b->iterations = h_state->iter;
-    b->h_first_id.resize(b->iterations + 1);
-    if (b->iterations)
-        RTR_CUDA(ctx, cudaMemcpyAsync(b->h_first_id.data(), b->iter_first_id, sizeof(uint32_t) * (b->iterations + 1),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
     RTR_CHECK(record(b, 4));
-    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 
     // 5. flatten, last creation level first
     if (n == 1) {
         flatten_single_leaf_kernel<<<1, 1, 0, ctx->stream>>>(b->node, b->wtri, b->flat, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     } else {
-        uint32_t* order = b->order;
-        RTR_CUDA(ctx, cudaMemsetAsync(b->ipos + (n - 2), 0, sizeof(uint32_t), ctx->stream));  // root 2n-2 -> position 0
-        flatten_root_kernel<<<1, 1, 0, ctx->stream>>>(order, 2 * n - 2);
-        RTR_LAUNCH_CHECK(ctx);
-        const uint32_t kSmall = 4096;
-        int it = (int)b->iterations - 1;
-        while (it >= 0) {
-            const uint32_t count = b->h_first_id[it + 1] - b->h_first_id[it];
-            if (count > kSmall) {
-                RTR_PROF(ctx, "flatten_level_kernel");
-                flatten_level_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(b->h_first_id[it], count, n, b->node,
-                                                                                   b->isize, b->ipos, order);
-                RTR_LAUNCH_CHECK(ctx);
-                --it;
-            } else {
-                int lo = it;
-                while (lo - 1 >= 0 && b->h_first_id[lo] - b->h_first_id[lo - 1] <= kSmall) --lo;
-                RTR_PROF(ctx, "flatten_small_levels_kernel");
-                flatten_small_levels_kernel<<<1, 1024, 0, ctx->stream>>>(b->iter_first_id, it, lo, n, b->node,
-                                                                         b->isize, b->ipos, order);
-                RTR_LAUNCH_CHECK(ctx);
-                it = lo - 1;
-            }
+        if (ctx->flatten_ctas_per_sm == 0) {
+            int c = 0;
+            RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, flatten_positions_kernel, kFlattenBlock, 0));
+            ctx->flatten_ctas_per_sm = c < 1 ? 1 : c;
         }
+        uint32_t grid = (uint32_t)(ctx->sm_count * ctx->flatten_ctas_per_sm);
+        const uint32_t need = (n + kFlattenBlock - 1) / kFlattenBlock;
+        if (grid > need) grid = need;
+        uint32_t n_arg = n;
+        uint32_t* ctl1 = b->ctl + 1;
+        void* args[] = {&b->state, &b->iter_first_id, &n_arg, &b->node, &b->isize, &b->ipos, &b->order, &ctl1};
+        RTR_PROF(ctx, "flatten_positions_kernel");
+        RTR_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)flatten_positions_kernel, dim3(grid), dim3(kFlattenBlock), args, 0, ctx->stream));
+        RTR_LAUNCH_CHECK(ctx);
         const uint32_t nc = 2 * n - 1;
         RTR_PROF(ctx, "flatten_emit_kernel");
-        flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, n, order, b->node, b->isize, b->wtri, b->flat, b->pairs);
+        flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->state, nc, n, b->order, b->node, b->isize, b->wtri, b->flat, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
         RTR_PROF(ctx, "pack_quads_kernel");
-        pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat, nc, b->pairs);
+        pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->state, b->flat, nc, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     }
     b->pairs_view = b->pairs;  // written by the flatten kernels
@@ -981,7 +1018,28 @@ int rtr_bvh_run_build(rtr_bvh* b) {
     b->flat_view = b->flat;
     b->wtri_view = b->wtri;
     b->wtri_by_rank = true;
-    b->built = true;
+    b->built = true;            // optimistic: the verdict is still on the device
+    b->finish_pending = true;
+    return RTR_OK;
+}
+
+// The part of a build the host has to wait for: did PLOC converge, and in how many iterations.  Called by everything
+// that hands results to the host (accessors, host-pointer trace calls, the synchronous rtr_bvh_build).
+int rtr_bvh_finish(rtr_bvh* b) {
+    if (!b->finish_pending) return RTR_OK;
+    rtr_ctx* ctx = b->ctx;
+    b->finish_pending = false;
+    PlocState* h = static_cast<PlocState*>(ctx->pinned);
+    RTR_CUDA(ctx, cudaMemcpyAsync(h, &b->state[2], sizeof(PlocState), cudaMemcpyDeviceToHost, ctx->stream));
+    RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    b->iterations = h->iter;
+    if (h->n_active != 1 || h->total != 2 * b->n - 1) {
+        b->built = false;
+        if (h->iter >= kMaxPlocIterations)
+            return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "more than %u PLOC iterations (degenerate input)", kMaxPlocIterations);
+        return rtr_set_error(ctx, RTR_E_INVALID, "PLOC did not converge: %u clusters left, %u created after %u iterations (non-finite triangle data?)",
+                             h->n_active, h->total, h->iter);
+    }
     return RTR_OK;
 }
 

@@ -484,11 +484,8 @@ int launch_pass(rtr_ctx* ctx, const KeyT* kin, KeyT* kout, const uint32_t* vin, 
     using Cfg = SortCfg<KeyT>;
     auto kern = onesweep_kernel<KeyT, PAIRS, Cfg::BLOCK, Cfg::IPT, TMA>;
     const size_t smem = sizeof(OnesweepSmem<KeyT, PAIRS, Cfg::BLOCK, Cfg::IPT>);
-    static bool configured = false;  // per template instantiation
-    if (!configured) {
-        RTR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // the opt-in is per device and a process may hold contexts on several: set it every time (a cheap host-side call)
+    RTR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RTR_PROF(ctx, sizeof(KeyT) == 4 ? (PAIRS ? "onesweep_kernel<u32,pairs>" : "onesweep_kernel<u32,keys>")
                                     : (PAIRS ? "onesweep_kernel<u64,pairs>" : "onesweep_kernel<u64,keys>"));
     kern<<<tiles, Cfg::BLOCK, smem, ctx->stream>>>(kin, kout, vin, vout, n, tiles, shift, mask, gbase, status, counter);
@@ -533,7 +530,8 @@ int sort_impl(rtr_ctx* ctx, KeyT* keys, uint32_t* vals, uint32_t n, int begin_bi
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
         const uint32_t mask = (1u << bits) - 1u;
-        const bool tma = (reinterpret_cast<uintptr_t>(kin) & 15u) == 0;
+        // cp.async.bulk needs 16-byte aligned global addresses -- for the payload as well as for the keys
+        const bool tma = (reinterpret_cast<uintptr_t>(kin) & 15u) == 0 && (!pairs || (reinterpret_cast<uintptr_t>(vin) & 15u) == 0);
         uint32_t* status = ws.status + (size_t)p * tiles * kRadix;
         int r;
         if (pairs) r = tma ? launch_pass<KeyT, true, true>(ctx, kin, kout, vin, vout, n, tiles, shift, mask, ws.gbase + p * kRadix, status, ws.counters + p)

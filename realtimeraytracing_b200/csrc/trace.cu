@@ -249,7 +249,7 @@ __device__ __forceinline__ Hit closest_hit_reference(const Ray& r, const Accel& 
     }
     return best;
 }
-__device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, const Accel& A) {
+__device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, const Accel& A, uint32_t* overflow) {
     uint32_t stack[kStack];
     int sp = 0;
     stack[sp++] = 0u;
@@ -264,6 +264,8 @@ __device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, con
         } else if (sp + 2 <= kStack) {
             stack[sp++] = n.links.y;
             stack[sp++] = n.links.z;
+        } else {
+            *overflow = 1u;  // a subtree is dropped: "no occluder" would not be trustworthy
         }
     }
     return false;
@@ -335,12 +337,9 @@ __device__ __forceinline__ Hit closest_hit(const Ray& r, const Accel& A, const P
     return closest_hit_reference(r, A, overflow);
 }
 template <bool PRUNE>
-__device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const Accel& A, const PruneBound& pb) {
-    if (PRUNE) {
-        uint32_t ovf = 0u;
-        return trace_ordered<true>(r, t_max, A, pb, &ovf).did_hit != 0u;
-    }
-    return any_hit_reference(r, t_max, A);
+__device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const Accel& A, const PruneBound& pb, uint32_t* overflow) {
+    if (PRUNE) return trace_ordered<true>(r, t_max, A, pb, overflow).did_hit != 0u;
+    return any_hit_reference(r, t_max, A, overflow);
 }
 
 __device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, const Hit& h) {
@@ -429,14 +428,14 @@ trace_rays_kernel(const Accel A, TraceParams* __restrict__ tp,
     const Ray r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
     const PruneBound pb = make_prune_bound(tp, PRUNE);
     Hit h = no_hit();
+    uint32_t ovf = 0;
     if (want_any) {
         const float tm = t_max ? t_max[i] : INFINITY;
-        h.did_hit = any_hit<PRUNE>(r, tm, A, pb) ? 1u : 0u;
+        h.did_hit = any_hit<PRUNE>(r, tm, A, pb, &ovf) ? 1u : 0u;
     } else {
-        uint32_t ovf = 0;
         h = closest_hit<PRUNE>(r, A, pb, &ovf);
-        if (ovf) atomicAdd(&tp->stack_overflows, 1u);
     }
+    if (ovf) atomicAdd(&tp->stack_overflows, 1u);
     store_hit(hits, i, h);
 }
 
@@ -468,7 +467,7 @@ render_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
                     const float sx = __fsub_rn(lx, ox), sy = __fsub_rn(ly, oy), sz = __fsub_rn(lz, oz);
                     const float len = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
                     const Ray sr = make_ray(ox, oy, oz, __fdiv_rn(sx, len), __fdiv_rn(sy, len), __fdiv_rn(sz, len));
-                    const bool occ = any_hit<PRUNE>(sr, len, A, pb);
+                    const bool occ = any_hit<PRUNE>(sr, len, A, pb, &ovf);
                     ++traced;
                     const float ndl = dot3(nx, ny, nz, sr.dx, sr.dy, sr.dz);
                     c = occ ? 0.f : fmaxf(0.f, ndl);
@@ -959,6 +958,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             }
             if (jd.kind != 0u) {
                 store_hit(jd.hits, job, best);
+                if (st & 0x20000u) atomicAdd(&tp->stack_overflows, 1u);  // never silent: the host forms refuse the batch
                 job = RTR_NONE;
             } else {
                 uint32_t x, y, out_row;
@@ -1110,11 +1110,12 @@ inline Accel accel_of(const rtr_bvh* b) {
 
 // one CTA per resident slot of the device
 int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_t* rays) {
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, trace_persistent_kernel, kTraceBlock, 0));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctx->trace_ctas_per_sm == 0) {  // per context = per device (one rtr_ctx per (host thread, GPU))
+        int c = 0;
+        RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, trace_persistent_kernel, kTraceBlock, 0));
+        ctx->trace_ctas_per_sm = c < 1 ? 1 : c;
     }
+    const int ctas_per_sm = ctx->trace_ctas_per_sm;
     const uint32_t need = (jd.total + kTraceBlock - 1) / kTraceBlock;
     const uint32_t full = (uint32_t)(ctx->sm_count * ctas_per_sm);
     uint32_t grid = full, reserve = 0u;
@@ -1203,6 +1204,8 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
     if (width == 0 || row0 >= row1 || row1 > height || denom_w == 0 || denom_h == 0)
         return rtr_set_error(ctx, RTR_E_INVALID, "render: bad image geometry %ux%u rows [%u,%u) denom %ux%u", width,
                              height, row0, row1, denom_w, denom_h);
+    if (bounces > 0xFFFFu)  // the lane state keeps the bounce index in 16 bits
+        return rtr_set_error(ctx, RTR_E_INVALID, "render: %u bounces (at most 65535)", bounces);
     RowMap rm;
     memset(&rm, 0, sizeof(rm));
     rm.row0 = row0; rm.rows = row1 - row0; rm.height = height; rm.rpb = 1; rm.count = 1; rm.span = 1; rm.off[0] = 0;

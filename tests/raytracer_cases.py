@@ -110,7 +110,35 @@ def hit_points(tris, meshes, hits):
             + hits["b2"].astype(np.float64)[:, None] * P[0])
 
 
+def incidence_cos(tris, meshes, hits, rays):
+    """|cos| of the angle between the ray and the normal of the triangle each hit names (float64).  The distance
+    of a hit is ill-conditioned at grazing incidence: a relative change eps of the direction moves t by about
+    eps * t / |cos|, and the shader accepts |cos| down to ~1e-4 / (2 * area) (its |a| >= 1e-4 test)."""
+    t = tris[hits["tri"]]
+    n = t.size
+    M = meshes["m"][t["model_id"]].reshape(n, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    P = [np.einsum("nij,nj->ni", M, t[k].astype(np.float64))[:, :3] for k in ("p0", "p1", "p2")]
+    nrm = _unit(np.cross(P[1] - P[0], P[2] - P[0]))
+    d = _unit(rays["d"][:, :3].astype(np.float64))
+    return np.abs((nrm * d).sum(axis=1))
+
+
 def has_zero_component(rays):
     """Q11: a direction component of exactly 0 makes the slab test divide by zero; where the origin also lies on
     a slab plane the result is NaN and GLSL min/max leave the outcome to the implementation."""
     return (rays["d"][:, :3] == 0).any(axis=1)
+
+
+def armadillo():
+    """(triangles, meshes): resources/models/armadillo.obj as the reference's Mesh::load returns it (99 976 triangles),
+    from tests/golden/armadillo_mesh.npz (make_armadillo_fixture.py); identity model matrix, ModelId 0."""
+    import os
+    from realtimeraytracing_b200.layouts import TRIANGLE
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "armadillo_mesh.npz"))
+    v = z["vertex_words"].view(np.float32)
+    f = z["faces"]
+    tris = np.zeros(f.shape[0], dtype=TRIANGLE)
+    for k, name in enumerate(("p0", "p1", "p2")):
+        tris[name][:, :3] = v[f[:, k]]
+        tris[name][:, 3] = 1.0
+    return tris, synth.identity_meshes(1)

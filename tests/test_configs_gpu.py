@@ -1,0 +1,189 @@
+"""Parity ON the BASELINE.json configurations themselves (configs 2, 3 and 4 at their full sizes), through the C ABI:
+
+ * config 2: ~100 k triangles (the synthetic soup AND the reference's armadillo.obj), Morton + sort + PLOC build,
+   primary rays at 1920x1080 with the reference's own dispatch geometry (Q5: 1920 x 1072 pixels are traced)
+ * config 3: 1 M-triangle soup, topology bit-exact against the reference's bvh.cpp, primary + shadow rays at 1080p
+ * config 4: 10 M-triangle soup, the tree bench.py times compared with the reference's bvh.cpp (capacity-patched
+   oracle/_ref/libref_bvh_16777216.so), and a band of the 3840x2160 primary + 2-bounce frame against the oracle
+
+Three checkers, in decreasing order of authority:
+   the reference's own code   oracle/_ref/libref_bvh_<cap>.so (bvh.cpp), libref_raytracer_div.so (raytracer.glsl)
+   the pinned restatement     oracle/rtr_oracle.c (equal to both of the above, tests/test_*_cpu.py)
+   size-independent property  default traversal order == the shader's order, record for record
+The build and the hit records are compared bit for bit; the glm::normalize variant of the shader within 1e-5.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+import raytracer_cases as rc
+import scenes
+from oracle import Reference, ReferenceRaytracer, raytracer_available, reference_available
+from realtimeraytracing_b200 import capi, synth
+from realtimeraytracing_b200.layouts import node_words
+
+pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1   # conftest pins OMP_NUM_THREADS=1 for the reference's bvh.cpp (Q3); rays are independent
+
+
+def words(a):
+    return np.ascontiguousarray(a).view(np.uint32).reshape(a.size, -1)
+
+
+def check_build_against_reference(oracle, bvh, tris, meshes, cap):
+    """Sort permutation, cluster arrays and the flattened array against the reference's own bvh.cpp."""
+    if not reference_available(cap):
+        pytest.skip("oracle/_ref/libref_bvh_%d.so not built" % cap)
+    rb = Reference(cap).bvh_build(tris, meshes, want_morton=True)
+    assert np.array_equal(bvh.triangle_indices(), rb.triangle_indices), "sort permutation"
+    assert np.array_equal(bvh.morton_codes(), rb.morton_unsorted[rb.triangle_indices]), "Morton codes (sorted)"
+    nodes, parent, left, right, is_leaf = bvh.clusters()
+    assert np.array_equal(left, rb.left) and np.array_equal(right, rb.right) and np.array_equal(parent, rb.parent), "PLOC topology"
+    assert np.array_equal(node_words(nodes), node_words(rb.clusters)), "cluster boxes"
+    rflat = oracle.flatten(rb.clusters, rb.left, rb.right)     # scene.cpp:189-208 (needs GL to compile; restated, pinned by App. C hashes)
+    flat = bvh.flat_nodes()
+    assert np.array_equal(node_words(flat), node_words(rflat)), "flattened array"
+    assert oracle.hash_flat_nodes(flat) == oracle.hash_flat_nodes(rflat)
+    return rflat
+
+
+def check_primary_frame(ctx, oracle, bvh, tris, meshes, cam, W, H, flat):
+    dw, dh = synth.reference_denominators(W, H)
+    got = bvh.trace_primary(cam, W, H)                          # denominators default to the reference formula (Q5)
+    exp = oracle.render(flat, tris, meshes, cam, W, H, dw, dh, threads=THREADS)[1]
+    assert exp["did_hit"].mean() > 0.05
+    assert np.array_equal(words(got), words(exp)), "hit records vs oracle"
+    by_letter = bvh.trace_primary(cam, W, H, flags=capi.TRACE_REFERENCE_ORDER)
+    assert np.array_equal(words(got), words(by_letter)), "default order vs shader order"
+    if raytracer_available("div"):                              # the reference's own shader, compiled
+        r = ReferenceRaytracer("div")
+        r.set_scene(tris, meshes, flat)
+        r.set_camera(cam)
+        sh, rays = r.trace_primary(W, H, dw, dh, want_rays=True)
+        q11 = rc.has_zero_component(rays)                       # incl. the pixels without an invocation (zero rays)
+        assert np.array_equal(words(got)[~q11], words(sh)[~q11]), "hit records vs raytracer.glsl"
+        assert (~q11).sum() >= dw * dh - dw - dh
+    if raytracer_available("glm"):
+        r = ReferenceRaytracer("glm")
+        r.set_scene(tris, meshes, flat)
+        r.set_camera(cam)
+        sh, rays = r.trace_primary(W, H, dw, dh, want_rays=True)
+        ok = ~rc.has_zero_component(rays)
+        a, b, rr = got[ok], sh[ok], rays[ok]
+        both = (a["did_hit"] == 1) & (b["did_hit"] == 1)
+        assert (a["did_hit"] != b["did_hit"]).mean() < 1e-4      # silhouettes under a 1-ulp different ray
+        x, y, rr = a[both], b[both], rr[both]
+        same_id = x["tri"] == y["tri"]
+        assert (~same_id).mean() < 1e-3                           # ties on shared edges
+        # these are hits of DIFFERENT rays (directions 1 ulp apart): t is within 1e-5 relative (north_star) wherever
+        # the problem is well conditioned, and within 1e-5 / |cos(incidence)| down to the shader's grazing limit
+        x, y, rr = x[same_id], y[same_id], rr[same_id]
+        rel = np.abs(x["t"].astype(np.float64) - y["t"]) / np.abs(y["t"])
+        cosi = rc.incidence_cos(tris, meshes, y, rr)
+        assert np.all(rel[cosi > 0.05] <= 1e-5), "t within 1e-5 relative"
+        assert np.all(rel <= 1e-5 / np.maximum(cosi, 1e-6)) and (rel <= 1e-5).mean() > 0.999
+        px, py = rc.hit_points(tris, meshes, x), rc.hit_points(tris, meshes, y)
+        assert np.all(np.linalg.norm(px - py, axis=1) <= 1e-5 / np.maximum(cosi, 1e-6) * np.abs(y["t"].astype(np.float64)))
+    return got
+
+
+def test_config2_soup_100k_1080p(ctx, oracle):
+    tris, meshes, L = scenes.soup(100_000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        flat = check_build_against_reference(oracle, bvh, tris, meshes, 1048576)
+        W, H = 1920, 1080
+        got = check_primary_frame(ctx, oracle, bvh, tris, meshes, synth.soup_camera(L, W, H), W, H, flat)
+        g = got.reshape(H, W)
+        assert not g["did_hit"][1072:].any()                    # Q5: rows 1072..1079 have no invocation
+    finally:
+        bvh.close()
+
+
+def test_config2_armadillo_1080p(ctx, oracle):
+    """The ~100 k-triangle real mesh of the reference's resources (99 976 triangles, connected: exact ties)."""
+    tris, meshes = rc.armadillo()
+    assert tris.size == 99_976
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        flat = check_build_against_reference(oracle, bvh, tris, meshes, 1048576)
+        W, H = 1920, 1080
+        cam = synth.reference_camera(eye=(0.0, 20.0, -230.0), aspect=W / H, far=1000.0)
+        check_primary_frame(ctx, oracle, bvh, tris, meshes, cam, W, H, flat)
+    finally:
+        bvh.close()
+
+
+def test_config3_soup_1m_primary_and_shadow_1080p(ctx, oracle):
+    tris, meshes, L = scenes.soup(1_000_000)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        flat = check_build_against_reference(oracle, bvh, tris, meshes, 1048576)
+        W, H = 1920, 1080
+        dw, dh = synth.reference_denominators(W, H)
+        cam = synth.soup_camera(L, W, H)
+        light = (0.3 * L, 0.8 * L, -1.2 * L)
+        rgba, hits, nrays = bvh.render(cam, W, H, bounces=0, shadow=True, light=light)
+        ergba, ehits, enrays = oracle.render(flat, tris, meshes, cam, W, H, dw, dh, bounces=0, shadow=True, light=light,
+                                             threads=THREADS)
+        assert nrays == enrays and nrays > dw * dh * 1.3          # primary + one shadow ray per hit
+        assert np.array_equal(words(hits), words(ehits)), "primary hits"
+        assert np.array_equal(rgba.view(np.uint32), ergba.view(np.uint32)), "shadowed image"
+        lit = rgba.reshape(-1, 4)[hits["did_hit"] == 1, 0]
+        assert 0.05 < (lit == 0).mean() < 0.95                    # some hits are in shadow, some are lit
+        if raytracer_available("div"):
+            r = ReferenceRaytracer("div")
+            r.set_scene(tris, meshes, flat)
+            r.set_camera(cam)
+            sh, rays = r.trace_primary(W, H, dw, dh, want_rays=True)
+            q11 = rc.has_zero_component(rays)
+            assert np.array_equal(words(hits)[~q11], words(sh)[~q11]), "primary hits vs raytracer.glsl"
+    finally:
+        bvh.close()
+
+
+def test_config4_soup_10m_build_and_4k_two_bounce_band(ctx, oracle):
+    """The scene bench.py times.  The reference build takes ~1 min and ~6 GB of host memory at this size."""
+    cap = 16777216
+    if not reference_available(cap):
+        pytest.skip("oracle/_ref/libref_bvh_%d.so not built" % cap)
+    n = 10_000_000
+    tris, meshes, L = scenes.soup(n)
+    bvh = capi.Bvh(ctx).build(tris, meshes)
+    try:
+        t0 = time.time()
+        rb = Reference(cap).bvh_build(tris, meshes, want_morton=False)
+        print("reference bvh.cpp, 10 M triangles: %.1f s" % (time.time() - t0))
+        got_idx = bvh.triangle_indices()
+        assert np.array_equal(got_idx, rb.triangle_indices), "sort permutation"
+        assert "%016x" % oracle.hash_words(got_idx) == "%016x" % oracle.hash_words(rb.triangle_indices)
+        rflat = oracle.flatten(rb.clusters, rb.left, rb.right)
+        del rb
+        flat = bvh.flat_nodes()
+        assert flat.size == 2 * n - 1
+        assert oracle.hash_flat_nodes(flat) == oracle.hash_flat_nodes(rflat), "flat-node hash (SURVEY App. C)"
+        assert np.array_equal(node_words(flat), node_words(rflat)), "flattened array"
+        del rflat
+        # a band of 96 rows through the middle of the 4K frame (368 640 pixels), primary + 2 bounces
+        W, H, r0, r1 = 3840, 2160, 1032, 1128
+        cam = synth.soup_camera(L, W, H)
+        rgba, hits, nrays = bvh.render(cam, W, H, row0=r0, row1=r1, bounces=2)
+        ergba, ehits, enrays = oracle.render(flat, tris, meshes, cam, W, H, W, H, row0=r0, row1=r1, bounces=2, threads=THREADS)
+        assert nrays == enrays and nrays > 1.5 * W * (r1 - r0)
+        assert np.array_equal(words(hits), words(ehits)), "primary hits"
+        assert np.array_equal(rgba.view(np.uint32), ergba.view(np.uint32)), "2-bounce image band"
+        full, fhits, _ = bvh.render(cam, W, H, bounces=2)         # and the band is what the whole frame holds there
+        assert np.array_equal(full.reshape(H, W, 4)[r0:r1].view(np.uint32), rgba.reshape(r1 - r0, W, 4).view(np.uint32))
+        if raytracer_available("div"):                            # primary hits of a 256 x 256 crop vs the compiled shader
+            r = ReferenceRaytracer("div")
+            r.set_scene(tris, meshes, flat)
+            r.set_camera(cam)
+            rays = oracle.get_rays(cam, W, H, W, H).reshape(H, W)[952:1208, 1792:2048].reshape(-1)
+            sh = r.closest_hit_bvh(rays)
+            crop = fhits.reshape(H, W)[952:1208, 1792:2048].reshape(-1)
+            q11 = rc.has_zero_component(rays)
+            assert np.array_equal(words(crop)[~q11], words(sh)[~q11]), "256x256 crop vs raytracer.glsl"
+    finally:
+        bvh.close()

@@ -340,3 +340,65 @@ def test_long_directions_are_refused_in_the_default_order(ctx):
         assert bvh.trace_rays(rays).size == 64
     finally:
         bvh.close()
+
+
+def _chain_scene(n):
+    """n small triangles facing -z, strung along +z, under a RIGHT-deep chain in DFS pre-order: inner node i sits at
+    2i, its left child (the leaf of triangle i, at 2i + 1) is the FARTHEST remaining triangle and its right child
+    (2i + 2) holds all the nearer ones -- so both visiting orders stack one entry per level."""
+    from realtimeraytracing_b200.layouts import NODE, TRIANGLE
+    tris = np.zeros(n, dtype=TRIANGLE)
+    z = (n - 1 - np.arange(n)).astype(np.float32)                 # triangle i at z = n - 1 - i
+    tris["p0"][:, :3] = np.stack([np.full(n, -1.0), np.full(n, -1.0), z], 1)
+    tris["p1"][:, :3] = np.stack([np.full(n, 0.0), np.full(n, 1.0), z], 1)   # host P1, P2 counter-clockwise seen from -z (Q8)
+    tris["p2"][:, :3] = np.stack([np.full(n, 1.0), np.full(n, -1.0), z], 1)
+    for k in ("p0", "p1", "p2"):
+        tris[k][:, 3] = 1.0
+    flat = np.zeros(2 * n - 1, dtype=NODE)
+    for i in range(n - 1):
+        flat[2 * i]["bmin"] = (-1.0, -1.0, 0.0)
+        flat[2 * i]["bmax"] = (1.0, 1.0, z[i])                    # triangles i .. n-1 lie at z <= z[i]
+        flat[2 * i]["left"], flat[2 * i]["right"] = 2 * i + 1, 2 * i + 2
+    for i in range(n):
+        p = 2 * i + 1 if i < n - 1 else 2 * n - 2
+        flat[p]["bmin"] = (-1.0, -1.0, z[i])
+        flat[p]["bmax"] = (1.0, 1.0, z[i])
+        flat[p]["tri"] = i
+    return tris, synth.identity_meshes(1), flat
+
+
+def test_stack_overflow_is_never_silent(ctx, oracle):
+    """A chain deeper than the 128-entry lane stack (the shader's own stack holds 1024, raytracer.glsl:251): every
+    entry point either returns the oracle's record or refuses -- explicit ray batches and any-hit rays included."""
+    deep, shallow = _chain_scene(300), _chain_scene(100)
+    rays = np.zeros(64, dtype=RAY)
+    rays["o"][:, :3] = (0.05, -0.1, -10.0); rays["o"][:, 3] = 1.0
+    rays["d"][:, :3] = (0.001, 0.002, 1.0)
+    rays["d"][:, :3] /= np.linalg.norm(rays["d"][0, :3])
+    for (tris, meshes, flat), fits in ((shallow, True), (deep, False)):
+        d_nodes, d_tris, d_meshes = ctx.dev_alloc(flat.nbytes), ctx.dev_alloc(tris.nbytes), ctx.dev_alloc(meshes.nbytes)
+        ctx.upload(d_nodes, flat); ctx.upload(d_tris, tris); ctx.upload(d_meshes, meshes)
+        bvh = capi.Bvh(ctx).adopt_dev(d_nodes, tris.size, d_tris, d_meshes, meshes.size)
+        try:
+            exp = oracle.trace_rays(flat, tris, meshes, rays)
+            assert exp["did_hit"].all() and (exp["tri"] == tris.size - 1).all()        # the nearest triangle, z = 0
+            for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER):
+                for any_hit in (False, True):
+                    tmax = np.full(rays.size, 1e-3, np.float32) if any_hit else None   # nothing that close: the whole chain is walked
+                    if fits:
+                        got = bvh.trace_rays(rays, any_hit=any_hit, t_max=tmax, flags=flags)
+                        if any_hit: assert not got["did_hit"].any()
+                        else: assert_hits_equal(got, exp, "chain of 100")
+                    else:
+                        with pytest.raises(capi.RtrError) as e:
+                            bvh.trace_rays(rays, any_hit=any_hit, t_max=tmax, flags=flags)
+                        assert e.value.code == -5, (flags, any_hit, str(e.value))      # RTR_E_UNSUPPORTED
+            if not fits:
+                d_rays, d_hits = ctx.dev_alloc(rays.nbytes), ctx.dev_alloc(rays.size * 24)
+                ctx.upload(d_rays, rays)
+                bvh.trace_rays_dev(d_rays, rays.size, d_hits)
+                assert bvh.stack_overflows() == rays.size
+                ctx.dev_free(d_rays); ctx.dev_free(d_hits)
+        finally:
+            bvh.close()
+            ctx.dev_free(d_nodes); ctx.dev_free(d_tris); ctx.dev_free(d_meshes)
