@@ -29,7 +29,22 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s"
-WORKLOAD = "10M-triangle soup, full BVH rebuild per frame + 3840x2160 primary + 2-bounce rays"
+WORKLOAD = "10M-triangle soup, full BVH rebuild per frame + 3840x2160 primary + 2-bounce rays"            # BASELINE config 4
+WORKLOAD5 = "10M-triangle soup, full BVH rebuild per frame + 3840x2160 4-bounce paths, BVH broadcast, tiles sharded"  # config 5
+
+
+def workload_name(tris, w, h, bounces):
+    if (tris, w, h, bounces) == (10_000_000, 3840, 2160, 2):
+        return WORKLOAD
+    if (tris, w, h, bounces) == (10_000_000, 3840, 2160, 4):
+        return WORKLOAD5
+    return "%d-triangle soup, full BVH rebuild per frame + %dx%d primary + %d-bounce rays" % (tris, w, h, bounces)
+
+
+def image_hash(rgba: np.ndarray) -> str:
+    """64-bit digest of a frame's rgba32f bytes: equal across GPU counts iff the frames are bit-identical."""
+    import hashlib
+    return hashlib.blake2b(np.ascontiguousarray(rgba).view(np.uint8).tobytes(), digest_size=8).hexdigest()
 
 
 def parse_args():
@@ -41,7 +56,8 @@ def parse_args():
     p.add_argument("--tris", type=int, default=10_000_000)
     p.add_argument("--width", type=int, default=3840)
     p.add_argument("--height", type=int, default=2160)
-    p.add_argument("--bounces", type=int, default=2)
+    p.add_argument("--bounces", type=int, default=None,
+                   help="default: 2 on one GPU (BASELINE config 4), 4 on several (config 5: 4-bounce paths, tiles sharded)")
     p.add_argument("--rows-per-block", type=int, default=16)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-kernel side measurements")
@@ -49,6 +65,7 @@ def parse_args():
     p.add_argument("--reserve-sms", type=int, default=0,
                    help="N>1: SMs the traversal leaves free for the NCCL kernels of the broadcast in flight")
     p.add_argument("--no-pipeline", action="store_true", help="N>1: rebuild, broadcast, render and gather strictly in sequence")
+    p.add_argument("--record-hash", action="store_true", help="N=1: store this frame's digest in profiles/image_hashes.json")
     return p.parse_args()
 
 
@@ -182,10 +199,7 @@ def run_reference_arm(args):
         "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD if (args.tris, args.width, args.height, args.bounces) == (10_000_000, 3840, 2160, 2) else
-                   "%d-triangle soup, full BVH rebuild per frame + %dx%d primary + %d-bounce rays" % (
-                       args.tris, args.width, args.height, args.bounces),
-                   "sample": arm.describe()},
+        "config": {"workload": workload_name(args.tris, args.width, args.height, args.bounces), "sample": arm.describe()},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -207,6 +221,8 @@ ALGO_BYTES = {  # algorithmic HBM bytes per launch as a function of (n triangles
 
 def main():
     args = parse_args()
+    if args.bounces is None:
+        args.bounces = 2 if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) == 1 else 4
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -248,13 +264,21 @@ def main():
     cam = synth.soup_camera(L, W, H)
 
     # ---- inputs: generated on the host once, resident in HBM for `value`, pinned for `e2e` ----
-    tris_pinned = meshes_np = None
+    tris_pinned = meshes_np = slice_pinned = None
     d_tris = d_meshes = None
+    slice_lo, slice_hi = parallel.slice_range(n, rank, world)
+    if world > 1 and rank != 0:
+        # e2e with sharded host traffic: this rank uploads triangles [slice_lo, slice_hi) over its own PCIe link
+        tris_np, _, _ = synth.triangle_soup(n)
+        slice_pinned = torch.empty((slice_hi - slice_lo) * TRIANGLE.itemsize, dtype=torch.uint8, pin_memory=True)
+        slice_pinned.numpy().view(TRIANGLE)[:] = tris_np[slice_lo:slice_hi]
+        del tris_np
     if rank == 0:
         tris_np, meshes_np, _ = synth.triangle_soup(n)
         tris_pinned = torch.empty(n * TRIANGLE.itemsize, dtype=torch.uint8, pin_memory=True)
         tris_pinned.numpy().view(TRIANGLE)[:] = tris_np
         del tris_np
+        slice_pinned = tris_pinned[slice_lo * TRIANGLE.itemsize: slice_hi * TRIANGLE.itemsize]
         with torch.cuda.stream(stream):
             d_tris = torch.empty(n * TRIANGLE.itemsize, dtype=torch.uint8, device=dev)
             d_tris.copy_(tris_pinned, non_blocking=True)
@@ -345,14 +369,27 @@ def main():
         last_built = [None]
         ctx.reserve_sms(args.reserve_sms)
 
-        # e2e arm: double-buffered host traffic (as on one GPU, see below)
+        # e2e arm, host traffic SHARDED over the ranks' own PCIe links: every rank uploads its slice of the frame's
+        # triangles (rtr_dev_upload_async), the slices are assembled on rank 0 over NVLink (rtr_gather_slices), and every
+        # rank downloads the rows it traced straight into one pinned host image all ranks share
+        # (rtr_download_stripes_async) -- the frame is never gathered on a device.  All double-buffered.
         x_in, x_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        slice_bytes = (slice_hi - slice_lo) * TRIANGLE.itemsize
         with torch.cuda.stream(stream):
             x_rgba = [d_rgba, torch.empty_like(d_rgba)]
-            x_tris = [d_tris, torch.empty_like(d_tris)] if rank == 0 else None
-        x_rgba_pinned = [rgba_pinned, torch.empty_like(rgba_pinned).pin_memory()] if rank == 0 else None
+            x_tris = [d_tris, torch.empty_like(d_tris)] if rank == 0 else [None, None]
+            x_slice = [torch.empty(max(slice_bytes, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
+        shm_names = ["/dev/shm/rtr_bench_%s_img%d" % (os.environ.get("MASTER_PORT", "0"), j) for j in range(2)]
+        if rank == 0:
+            for nm in shm_names:
+                np.memmap(nm, dtype=np.float32, mode="w+", shape=(H, W, 4)).flush()
+        dist.barrier()
+        x_host_img = [np.memmap(nm, dtype=np.float32, mode="r+", shape=(H, W, 4)) for nm in shm_names]
+        for img in x_host_img:
+            capi.host_register(img)
         x_meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory() if rank == 0 else None
-        x_up_done, x_tris_free, x_frame_done, x_img_free, x_img_done = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(5))
+        x_up_done, x_slice_free, x_tris_ready, x_tris_free, x_frame_done, x_img_free, x_img_done = (
+            [torch.cuda.Event(), torch.cuda.Event()] for _ in range(7))
         # one stream for the rays of all frames: two persistent launches in flight at once would feed the later one's
         # CTAs, as slots free up, into the SMs the earlier one vacated for NCCL -- where they leave at once
         streams_r = [stream_r, stream_r]
@@ -365,8 +402,29 @@ def main():
                 e.record(st)
                 marks.append((what, f, e))
 
+        def submit_upload(f):
+            """e2e, every rank: its slice of frame f's host triangles goes up its own PCIe link, then the slices are
+            assembled on rank 0 over NVLink (an NCCL point: issued by all ranks at the same place of the schedule)."""
+            j = f % 2
+            ctx.switch_stream(x_in.cuda_stream)
+            x_in.wait_event(x_slice_free[j])
+            if slice_bytes:
+                ctx.upload_async(x_slice[j].data_ptr(), slice_pinned.numpy())
+            if rank == 0:
+                ctx.upload_async(d_meshes.data_ptr(), x_meshes_pinned.numpy())
+            x_up_done[j].record(x_in)
+            ctx.switch_stream(stream_b.cuda_stream)
+            stream_b.wait_event(x_up_done[j])
+            if rank == 0:
+                stream_b.wait_event(x_tris_free[j])
+            ctx.gather_slices(x_slice[j].data_ptr(), x_tris[j].data_ptr() if rank == 0 else None, n, TRIANGLE.itemsize, 0)
+            x_slice_free[j].record(stream_b)
+            if rank == 0:
+                x_tris_ready[j].record(stream_b)
+            mark("tris", f, stream_b)
+
         def submit_build(f, e2e):
-            """stage A, rank 0 only: rebuild BVH f % NB."""
+            """stage A, rank 0 only: rebuild BVH f % NB (asynchronous: the host does not wait for the device)."""
             if rank != 0:
                 return
             k = f % NB
@@ -374,16 +432,8 @@ def main():
             stream_a.wait_event(released[k])   # own rays of the frame that used this BVH
             stream_a.wait_event(sent[k])       # and its broadcast
             if e2e:
-                # host triangles of this frame: uploaded on their own stream (beside the work of earlier frames),
-                # then rebuilt from the device copy
                 j = f % 2
-                ctx.switch_stream(x_in.cuda_stream)
-                x_in.wait_event(x_tris_free[j])
-                ctx.upload_async(x_tris[j].data_ptr(), tris_pinned.numpy())
-                ctx.upload_async(d_meshes.data_ptr(), x_meshes_pinned.numpy())
-                x_up_done[j].record(x_in)
-                ctx.switch_stream(stream_a.cuda_stream)
-                stream_a.wait_event(x_up_done[j])
+                stream_a.wait_event(x_tris_ready[j])
                 bvhs[k].build_dev(x_tris[j].data_ptr(), n, n, d_meshes.data_ptr(), 1)
                 x_tris_free[j].record(stream_a)
             else:
@@ -420,35 +470,47 @@ def main():
                 sr.wait_event(last_built[0])
             mark("rays0", f, sr)
             img = x_rgba[j]
-            if e2e and rank == 0:
+            if e2e:
                 sr.wait_event(x_img_free[j])   # the download of the frame that used this image buffer is through
             bvhs[k].render_stripes_dev(cam, W, H, img.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
                                        bounces=bounces, flags=flags)
             released[k].record(sr)
             mark("rays1", f, sr)
-            ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
-            x_img_done[j].record(sr)
-            mark("gather", f, sr)
-            if e2e and rank == 0:
+            if e2e:
+                # every rank sends the rows it traced to the shared host image over its own PCIe link
                 x_frame_done[j].record(sr)
+                x_img_done[j].record(sr)
                 ctx.switch_stream(x_out.cuda_stream)
                 x_out.wait_event(x_frame_done[j])
-                ctx.download_async(x_rgba_pinned[j].numpy(), img.data_ptr())   # D2H of the frame, beside the next one
+                ctx.download_stripes_async(x_host_img[j].ctypes.data, img.data_ptr(), W, H, 16, rpb, layout)
                 x_img_free[j].record(x_out)
                 ctx.switch_stream(sr.cuda_stream)
+            else:
+                ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
+                x_img_done[j].record(sr)
+                mark("gather", f, sr)
 
         def run_pipelined(steps, e2e):
-            # every rank issues its NCCL calls in the same order: exchange(f+1), gather(f), exchange(f+2), ...
+            # every rank issues its NCCL calls in the same order:
+            #   value: exchange(f+1), gather(f), exchange(f+2), ...     e2e: slices(f+2), exchange(f+1), slices(f+3), ...
+            # (the slices of f+2 go BEFORE the exchange of f+1 on the communicator's stream: they only wait for host
+            #  uploads, whereas the exchange waits for the rebuild of f+1 -- so rank 0 can rebuild f+2 beside it)
             last_built[0] = None
+            if e2e:
+                submit_upload(0)
+                if steps > 1:
+                    submit_upload(1)
             submit_build(0, e2e)
             submit_exchange(0)
             if steps > 1:
                 submit_build(1, e2e)
             for f in range(steps):
+                if e2e and f + 2 < steps:
+                    submit_upload(f + 2)
                 if f + 1 < steps:
                     submit_exchange(f + 1)
                 if f + 2 < steps:
-                    submit_build(f + 2, e2e)     # host-blocking on rank 0: everything it must not delay is enqueued
+                    submit_build(f + 2, e2e)
                 submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
@@ -516,13 +578,21 @@ def main():
         ms, rays, launches = timed(frame_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = rays / (ms * 1e-3) / 1e6
+    # the frame the timed region produced last (device-gathered on rank 0 when N > 1)
+    hashes = {}
+    if rank == 0:
+        last_img = x_rgba[(args.steps - 1) % 2] if pipelined else d_rgba
+        ctx.download(rgba_pinned.numpy(), last_img.data_ptr())
+        hashes["value_frame"] = image_hash(rgba_pinned.numpy())
 
     # ---- end to end through the host-pointer ABI ----
     e2e_steps = args.steps
     e2e_how = "rtr_bvh_build (host triangles, synchronous upload) + frame + rtr_dev_download of the image, per step"
     if pipelined:
-        e2e_how = ("pipelined frames; on rank 0 rtr_dev_upload_async of frame f+1's triangles and rtr_dev_download_async of "
-                   "frame f's gathered image run on their own streams beside the rebuild and the rays")
+        e2e_how = ("pipelined frames, host traffic sharded: every rank uploads 1/%d of frame f+2's triangles over its own PCIe "
+                   "link (rtr_dev_upload_async), rtr_gather_slices assembles them on rank 0 over NVLink, and every rank downloads "
+                   "the rows it traced into one pinned host image shared by all ranks (rtr_download_stripes_async); the byte "
+                   "counts are the totals over all ranks" % world)
         run_pipelined(2, True)
         e2e_ms, e2e_rays, _ = timed_pipelined(e2e_steps, True)
     elif world == 1 and not args.no_pipeline:
@@ -594,6 +664,37 @@ def main():
             frame_e2e()
         e2e_ms, e2e_rays, _ = timed(frame_e2e, e2e_steps)
     e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+    # ---- correctness gate: the frame that came out of the (pipelined, sharded) loop is the frame one GPU renders ----
+    image_check = None
+    if rank == 0:
+        if pipelined:
+            hashes["e2e_frame"] = image_hash(np.asarray(x_host_img[(e2e_steps - 1) % 2]))
+            ctx.switch_stream(stream.cuda_stream)
+            bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            bvh.render_sharded_dev(cam, W, H, d_rgba.data_ptr(), rpb, 0, 1, bounces=bounces, flags=flags)
+            ctx.download(rgba_pinned.numpy(), d_rgba.data_ptr())
+            hashes["one_gpu_frame"] = image_hash(rgba_pinned.numpy())
+        elif world == 1 and not args.no_pipeline:
+            hashes["e2e_frame"] = image_hash(rgba_pinned2[(e2e_steps - 1) % 2].numpy())
+        else:
+            hashes["e2e_frame"] = image_hash(rgba_pinned.numpy())
+        key = "%d_%dx%d_b%d" % (n, W, H, bounces)
+        hash_file = os.path.join(ROOT, "profiles", "image_hashes.json")
+        try:
+            known = json.load(open(hash_file))
+        except Exception:
+            known = {}
+        if args.record_hash and world == 1:
+            known[key] = hashes["value_frame"]
+            json.dump(known, open(hash_file, "w"), indent=1, sort_keys=True)
+        distinct = sorted(set(hashes.values()) | ({known[key]} if key in known else set()))
+        image_check = {"hash": hashes["value_frame"], "frames_compared": sorted(hashes), "expected_n1": known.get(key),
+                       "ok": len(distinct) == 1,
+                       "how": "blake2b-64 of the rgba32f frame: the timed loop's last frame (device-gathered), the e2e loop's last "
+                              "frame (host image)" + (", rank 0 rendering the frame alone" if pipelined else "") +
+                              " and the digest recorded at N=1 (profiles/image_hashes.json) must all be equal"}
+        if not image_check["ok"]:
+            raise RuntimeError("frames differ: %s (expected %s)" % (hashes, known.get(key)))
     # a ray that ran out of traversal stack would have dropped subtrees: such a run is not a measurement
     for k, used in enumerate(bvhs if pipelined else [bvh]):
         try:
@@ -689,8 +790,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (n, W, H, bounces) == (10_000_000, 3840, 2160, 2) else
-                       "%d-triangle soup, full BVH rebuild per frame + %dx%d primary + %d-bounce rays" % (n, W, H, bounces),
+            "config": {"workload": workload_name(n, W, H, bounces),
                        "triangles": n, "image": [W, H], "traced_pixels": [dw, dh], "bounces": bounces,
                        "rays_per_step": rays // args.steps, "search_radius": 16,
                        "trace_order": "reference" if args.reference_order else "pruned (identical records)",
@@ -702,6 +802,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "how": e2e_how},
             "gpu_launches": launches,
+            "image_check": image_check,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
@@ -711,6 +812,16 @@ def main():
         print(json.dumps(line, default=float))
 
     if pipelined:
+        for img in x_host_img:
+            capi.host_unregister(img)
+        del x_host_img
+        dist.barrier()
+        if rank == 0:
+            for nm in shm_names:
+                try:
+                    os.unlink(nm)
+                except OSError:
+                    pass
         for other in bvhs[1:]:
             other.close()
     bvh.close()

@@ -130,6 +130,10 @@ int rtr_ctx_profile_read(rtr_ctx* ctx, char* names, size_t names_bytes, float* t
 /* pinned host buffers for the host-pointer entry points (plain malloc'd memory also works) */
 int rtr_host_alloc(size_t bytes, void** out);
 int rtr_host_free(void* p);
+/* page-lock / release host memory the caller owns (a mapping shared by the processes of a multi-GPU job, for
+ * rtr_download_stripes_async) */
+int rtr_host_register(void* p, size_t bytes);
+int rtr_host_unregister(void* p);
 /* device buffers for C/C++ hosts (replace glCreateBuffers/glNamedBufferStorage,
  * tests/testsSortGPU/testHistogramCreation.cpp:75-85, and glGetNamedBufferSubData :131) */
 int rtr_dev_alloc(rtr_ctx* ctx, size_t bytes, void** out);
@@ -203,6 +207,9 @@ uint32_t rtr_bvh_nb_triangles(const rtr_bvh* bvh);
 uint32_t rtr_bvh_nb_nodes(const rtr_bvh* bvh); /* 2n-1 */
 /* PLOC iterations of the last build and its trace (n_i active clusters, m_i merges) */
 int rtr_bvh_iteration_trace(rtr_bvh* bvh, uint32_t* active, uint32_t* merges, uint32_t capacity, uint32_t* count);
+/* diagnostics: device clock (%globaltimer, ns) at the start of every PLOC iteration of the last build; count + 1
+ * values, the last one is the end of the loop.  The loop runs on the device without the host (see rtr_bvh_build_dev). */
+int rtr_bvh_iteration_times(rtr_bvh* bvh, uint64_t* start_ns, uint32_t capacity, uint32_t* count);
 /* per-stage device times of the last build in ms: [0] scene box + Morton, [1] sort, [2] leaf init,
  * [3] PLOC loop, [4] flatten, [5] total.  Only measured when enabled. */
 int rtr_bvh_enable_stage_timing(rtr_bvh* bvh, int enable);
@@ -375,6 +382,17 @@ int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_
 /* only `root` ends up with the whole image: every block travels once, from its owner to the root (ncclSend/ncclRecv) */
 int rtr_gather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t height, uint32_t bytes_per_pixel,
                        uint32_t rows_per_block, const uint32_t* stripes_of_rank, int root);
+
+/* Sharded host traffic of a multi-GPU frame loop (no reference counterpart: the reference is single-GPU).
+ * rtr_gather_slices: an array of n_elems elements (the frame's TriangleGPU records) is cut into nranks contiguous
+ * slices, rank r holding [n_elems*r/nranks, n_elems*(r+1)/nranks) in slice_dev -- uploaded over ITS OWN PCIe link --
+ * and the slices are assembled in full_dev on the root over NVLink (every slice travels once; full_dev may be NULL on
+ * the other ranks).  rtr_download_stripes_async: this rank's row blocks of a striped frame (rtr_render_stripes_dev)
+ * are copied from image_dev to the same rows of image_host, a full-size host image (e.g. one pinned buffer shared by
+ * all ranks); asynchronous on the context's stream, no collective. */
+int rtr_gather_slices(rtr_ctx* ctx, const void* slice_dev, void* full_dev, uint64_t n_elems, uint32_t elem_bytes, int root);
+int rtr_download_stripes_async(rtr_ctx* ctx, void* image_host, const void* image_dev, uint32_t width, uint32_t height,
+                               uint32_t bytes_per_pixel, uint32_t rows_per_block, const uint32_t* stripes_of_rank);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ NCCL_UNIQUE_ID_BYTES = 128
 SYMBOLS = [
     "rtr_version", "rtr_ctx_create", "rtr_ctx_destroy", "rtr_last_error", "rtr_ctx_sync", "rtr_ctx_stream",
     "rtr_ctx_set_stream", "rtr_ctx_device", "rtr_ctx_sm_count", "rtr_ctx_launch_count",
-    "rtr_host_alloc", "rtr_host_free", "rtr_dev_alloc", "rtr_dev_free", "rtr_dev_upload", "rtr_dev_download",
+    "rtr_host_alloc", "rtr_host_free", "rtr_host_register", "rtr_host_unregister", "rtr_dev_alloc", "rtr_dev_free", "rtr_dev_upload", "rtr_dev_download",
     "rtr_dev_zero",
     "rtr_bit_histogram32", "rtr_bit_histogram32_dev", "rtr_digitplace_exclusive_scan",
     "rtr_digitplace_exclusive_scan_dev",
@@ -29,7 +29,7 @@ SYMBOLS = [
     "rtr_sort_pairs_u32_dev", "rtr_sort_pairs_u64_dev",
     "rtr_morton_codes", "rtr_morton_codes_dev", "rtr_morton_codes64", "rtr_scene_bounds",
     "rtr_bvh_build", "rtr_bvh_build_dev", "rtr_bvh_destroy", "rtr_bvh_nb_triangles", "rtr_bvh_nb_nodes",
-    "rtr_bvh_iteration_trace", "rtr_bvh_enable_stage_timing", "rtr_bvh_stage_ms", "rtr_bvh_morton_codes",
+    "rtr_bvh_iteration_trace", "rtr_bvh_iteration_times", "rtr_bvh_enable_stage_timing", "rtr_bvh_stage_ms", "rtr_bvh_morton_codes",
     "rtr_bvh_triangle_indices", "rtr_bvh_clusters", "rtr_bvh_flat_nodes", "rtr_bvh_device_nodes",
     "rtr_bvh_device_triangles", "rtr_bvh_device_meshes", "rtr_bvh_adopt_dev",
     "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
@@ -37,6 +37,7 @@ SYMBOLS = [
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
     "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
     "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
+    "rtr_gather_slices", "rtr_download_stripes_async",
     "rtr_bvh_build64", "rtr_bvh_build64_dev", "rtr_bvh_morton_codes64",
     "rtr_bvh_depth_overlay", "rtr_bvh_depth_overlay_dev",
     "rtr_obj_load", "rtr_obj_parse", "rtr_obj_free", "rtr_mesh_primitive", "rtr_mesh_init", "rtr_mesh_set_model",
@@ -84,6 +85,8 @@ def load_library():
     L.rtr_ctx_launch_count.argtypes = [vp]
     L.rtr_ctx_launch_count.restype = u64
     L.rtr_host_alloc.argtypes = [sz, pp]
+    L.rtr_host_register.argtypes = [vp, sz]
+    L.rtr_host_unregister.argtypes = [vp]
     L.rtr_host_free.argtypes = [vp]
     L.rtr_dev_alloc.argtypes = [vp, sz, pp]
     L.rtr_dev_free.argtypes = [vp, vp]
@@ -117,6 +120,7 @@ def load_library():
     L.rtr_bvh_nb_nodes.argtypes = [vp]
     L.rtr_bvh_nb_nodes.restype = u32
     L.rtr_bvh_iteration_trace.argtypes = [vp, vp, vp, u32, vp]
+    L.rtr_bvh_iteration_times.argtypes = [vp, vp, u32, vp]
     L.rtr_bvh_enable_stage_timing.argtypes = [vp, i32]
     L.rtr_bvh_stage_ms.argtypes = [vp, vp]
     L.rtr_bvh_morton_codes.argtypes = [vp, vp]
@@ -145,6 +149,8 @@ def load_library():
     L.rtr_render_stripes_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, u32, vp, u32, u32, u32, i32, vp, u32, vp, vp, vp]
     L.rtr_allgather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp]
     L.rtr_gather_stripes.argtypes = [vp, vp, u32, u32, u32, u32, vp, i32]
+    L.rtr_gather_slices.argtypes = [vp, vp, vp, C.c_uint64, u32, i32]
+    L.rtr_download_stripes_async.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp]
     L.rtr_shade.argtypes = [vp, vp, C.c_uint64, vp, u32, vp, u32, vp, u32, u32, vp, vp]
     L.rtr_shade_dev.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, u32, vp, vp]
     L.rtr_bvh_depth_overlay.argtypes = [vp, vp, vp, u32, u32, u32, u32, i32, vp]
@@ -193,6 +199,15 @@ def _check_host(rc):
     if rc != 0:
         msg = load_library().rtr_last_error(None)
         raise RtrError(rc, msg.decode() if msg else "")
+
+
+def host_register(array: np.ndarray):
+    """Page-locks the memory of `array` (e.g. an np.memmap shared by all ranks) for asynchronous copies."""
+    _check_host(load_library().rtr_host_register(C.c_void_p(array.ctypes.data), array.nbytes))
+
+
+def host_unregister(array: np.ndarray):
+    load_library().rtr_host_unregister(C.c_void_p(array.ctypes.data))
 
 
 def _take_triangles(out, n) -> np.ndarray:
@@ -464,6 +479,18 @@ class Context:
         self.check(self.lib.rtr_gather_stripes(self.handle, C.c_void_p(image_dev), width, height, bytes_per_pixel,
                                                rows_per_block, _ptr(st), root))
 
+    def gather_slices(self, slice_dev: int, full_dev, n_elems: int, elem_bytes: int, root: int = 0):
+        """Assemble on `root` an array whose contiguous slices (parallel.slice_range) the ranks uploaded themselves."""
+        self.check(self.lib.rtr_gather_slices(self.handle, C.c_void_p(slice_dev), C.c_void_p(full_dev) if full_dev else None,
+                                              n_elems, elem_bytes, root))
+
+    def download_stripes_async(self, image_host_ptr: int, image_dev: int, width: int, height: int, bytes_per_pixel: int,
+                               rows_per_block: int, stripes_of_rank):
+        """This rank's row blocks of a striped frame, device -> the same rows of a full-size host image."""
+        st = np.ascontiguousarray(stripes_of_rank, dtype=np.uint32)
+        self.check(self.lib.rtr_download_stripes_async(self.handle, C.c_void_p(image_host_ptr), C.c_void_p(image_dev), width,
+                                                       height, bytes_per_pixel, rows_per_block, _ptr(st)))
+
     def switch_stream(self, cuda_stream: int):
         """Enqueue later calls on `cuda_stream` without waiting for the work already enqueued (pipelined frames)."""
         self.check(self.lib.rtr_ctx_switch_stream(self.handle, C.c_void_p(cuda_stream)))
@@ -557,6 +584,14 @@ class Bvh:
         self.ctx.check(self.lib.rtr_bvh_iteration_trace(self.handle, _ptr(active), _ptr(merges), cap, C.byref(count)))
         k = min(cap, count.value)
         return active[:k].copy(), merges[:k].copy()
+
+    def iteration_times(self) -> np.ndarray:
+        """Device clock (ns) at the start of every PLOC iteration of the last build (+ the end of the loop)."""
+        cap = (1 << 16) + 2
+        t = np.zeros(cap, dtype=np.uint64)
+        count = C.c_uint32(0)
+        self.ctx.check(self.lib.rtr_bvh_iteration_times(self.handle, _ptr(t), cap, C.byref(count)))
+        return t[:min(cap, count.value + 1)].copy()
 
     def morton_codes(self) -> np.ndarray:
         out = np.zeros(self.nb_triangles, dtype=np.uint32)

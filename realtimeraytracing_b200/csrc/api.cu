@@ -65,15 +65,15 @@ int dev_alloc(rtr_ctx* ctx, T** p, size_t count) {
 
 void bvh_free_arrays(rtr_bvh* b) {
     void* ptrs[] = {b->codes, b->tri_idx, b->node, b->isize, b->ipos, b->order, b->codes64, b->cin, b->cout, b->tile_status,
-                    b->state, b->ctl, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
+                    b->state, b->ctl, b->iter_ns, b->trace_active, b->trace_merges, b->iter_first_id, b->bounds12, b->ordered6, b->flat,
                     b->tparams, b->tris_own, b->meshes_own, b->flat_recv, b->wtri, b->wtri_own, b->pairs, b->pairs_own};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    b->codes = b->tri_idx = b->isize = b->ipos = b->order = b->cin = b->cout = nullptr;
+    b->codes = b->tri_idx = b->ipos = b->order = b->cin = b->cout = nullptr; b->isize = nullptr;
     b->codes64 = nullptr; b->codes64_cap = 0;
     b->node = nullptr;
     b->tile_status = nullptr; b->state = nullptr; b->ctl = nullptr;
-    b->trace_active = b->trace_merges = b->iter_first_id = nullptr;
+    b->trace_active = b->trace_merges = b->iter_first_id = nullptr; b->iter_ns = nullptr;
     b->bounds12 = nullptr; b->ordered6 = nullptr; b->flat = nullptr; b->tparams = nullptr;
     b->tris_own = nullptr; b->meshes_own = nullptr; b->tris_own_cap = b->meshes_own_cap = 0;
     b->flat_recv = nullptr; b->recv_cap = 0;
@@ -108,6 +108,7 @@ int bvh_reserve(rtr_bvh* b, uint32_t n) {
     RTR_CHECK(dev_alloc(ctx, &b->trace_active, kMaxPlocIterations));
     RTR_CHECK(dev_alloc(ctx, &b->trace_merges, kMaxPlocIterations));
     RTR_CHECK(dev_alloc(ctx, &b->iter_first_id, kMaxPlocIterations + 1));
+    RTR_CHECK(dev_alloc(ctx, &b->iter_ns, kMaxPlocIterations + 2));
     RTR_CHECK(dev_alloc(ctx, &b->bounds12, 12));
     RTR_CHECK(dev_alloc(ctx, &b->ordered6, 8));
     RTR_CHECK(dev_alloc(ctx, &b->flat, nc));
@@ -386,6 +387,18 @@ int rtr_host_alloc(size_t bytes, void** out) {
 }
 int rtr_host_free(void* p) {
     if (p) cudaFreeHost(p);
+    return RTR_OK;
+}
+// page-locks memory the caller owns (e.g. a file mapping shared by the processes of a multi-GPU job), so that the
+// asynchronous copies can target it
+int rtr_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return RTR_E_INVALID;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) return rtr_set_error(nullptr, RTR_E_NOMEM, "cudaHostRegister(%zu): %s", bytes, cudaGetErrorString(e));
+    return RTR_OK;
+}
+int rtr_host_unregister(void* p) {
+    if (p) cudaHostUnregister(p);
     return RTR_OK;
 }
 int rtr_dev_alloc(rtr_ctx* ctx, size_t bytes, void** out) {
@@ -671,6 +684,18 @@ int rtr_bvh_iteration_trace(rtr_bvh* b, uint32_t* active, uint32_t* merges, uint
         const uint32_t m = b->iterations < capacity ? b->iterations : capacity;
         if (m && active) RTR_CUDA(ctx, cudaMemcpyAsync(active, b->trace_active, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (m && merges) RTR_CUDA(ctx, cudaMemcpyAsync(merges, b->trace_merges, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RTR_OK;
+    });
+}
+
+// diagnostics: %globaltimer (ns) at the start of every PLOC iteration of the last build, count + 1 values
+int rtr_bvh_iteration_times(rtr_bvh* b, uint64_t* start_ns, uint32_t capacity, uint32_t* count) {
+    return with_bvh(b, true, [&]() -> int {
+        rtr_ctx* ctx = b->ctx;
+        if (count) *count = b->iterations;
+        const uint32_t m = (b->iterations + 1) < capacity ? (b->iterations + 1) : capacity;
+        if (m && start_ns) RTR_CUDA(ctx, cudaMemcpyAsync(start_ns, b->iter_ns, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return RTR_OK;
     });

@@ -50,7 +50,7 @@ struct rtr_bvh {
     uint32_t* codes = nullptr;     // [cap]  sorted Morton codes
     uint32_t* tri_idx = nullptr;   // [cap]  BVH_Params::_TriangleIndices
     float4* node = nullptr;        // [2*(2cap-1)] by cluster id, 32 B records: (min.xyz, max.x)(max.y, max.z, bits(left | triangle id), bits(right | NONE))
-    uint32_t* isize = nullptr;     // [cap] nodes in the subtree of internal cluster (id - n)
+    uint2* isize = nullptr;        // [cap] internal cluster (id - n): (nodes in its subtree, nodes in its left subtree)
     uint32_t* ipos = nullptr;      // [cap] DFS pre-order position of internal cluster (id - n)
     uint32_t* order = nullptr;     // [2cap-1] cluster id at every DFS pre-order position (flatten pass 1)
     uint32_t* cin = nullptr;       // [cap] active list, ping
@@ -61,6 +61,7 @@ struct rtr_bvh {
     uint32_t* trace_active = nullptr;   // [kMaxPlocIterations]
     uint32_t* trace_merges = nullptr;   // [kMaxPlocIterations]
     uint32_t* iter_first_id = nullptr;  // [kMaxPlocIterations + 1] first cluster id created by iteration i
+    unsigned long long* iter_ns = nullptr;  // [kMaxPlocIterations + 2] %globaltimer at the start of iteration i (diagnostics)
     float* bounds12 = nullptr;     // scene box + cube
     uint32_t* ordered6 = nullptr;
     rtr_node* flat = nullptr;      // [2cap-1] DFS pre-order, the reference's SSBO 5

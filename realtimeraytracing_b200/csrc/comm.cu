@@ -69,6 +69,27 @@ int load_nccl(rtr_ctx* ctx) {
                                  g_nccl.GetErrorString ? g_nccl.GetErrorString(_e) : "nccl error"); \
     } while (0)
 
+// Inside ncclGroupStart/End an error must not return before the group is closed (the thread would stay in group
+// mode): RTR_NCCL_G remembers the first failure and carries on, rtr_group_end closes the group and reports it.
+struct GroupGuard {
+    int first_error = 0;
+    const char* what = nullptr;
+};
+#define RTR_NCCL_G(g, call)                                            \
+    do {                                                               \
+        if ((g).first_error == 0) {                                    \
+            int _e = (call);                                           \
+            if (_e != 0) { (g).first_error = _e; (g).what = #call; }   \
+        }                                                              \
+    } while (0)
+int rtr_group_end(rtr_ctx* ctx, const GroupGuard& g) {
+    const int e = g_nccl.GroupEnd();
+    if (g.first_error != 0)
+        return rtr_set_error(ctx, RTR_E_COMM, "%s -> %s", g.what, g_nccl.GetErrorString ? g_nccl.GetErrorString(g.first_error) : "nccl error");
+    if (e != 0) return rtr_set_error(ctx, RTR_E_COMM, "ncclGroupEnd -> %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "nccl error");
+    return RTR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -181,12 +202,13 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
     // 3. one grouped broadcast: flat nodes (48 B*(2n-1)) + triangles (64 B*n) + meshes + world-space
     //    triangle cache (48 B*n) + trace constants
     RTR_NCCL(ctx, g_nccl.GroupStart());
-    RTR_NCCL(ctx, g_nccl.Broadcast(nodes, nodes, nc * sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(tris, tris, (size_t)n * sizeof(rtr_triangle), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(meshes, meshes, (size_t)nb_meshes * sizeof(rtr_mesh), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(wtri, wtri, (size_t)n * 3 * sizeof(float4), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    GroupGuard grp;
+    RTR_NCCL_G(grp, g_nccl.Broadcast(nodes, nodes, nc * sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(tris, tris, (size_t)n * sizeof(rtr_triangle), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(meshes, meshes, (size_t)nb_meshes * sizeof(rtr_mesh), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(wtri, wtri, (size_t)n * 3 * sizeof(float4), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
+    RTR_CHECK(rtr_group_end(ctx, grp));
 
     if (!is_root) {
         b->n = n; b->array_len = n; b->nb_meshes = nb_meshes;
@@ -256,10 +278,11 @@ int rtr_bvh_broadcast_traversal(rtr_ctx* ctx, rtr_bvh** bvh, int root, uint32_t 
 
     // 3. one grouped broadcast: 64 B*(2n-1) + 48 B + trace constants
     RTR_NCCL(ctx, g_nccl.GroupStart());
-    RTR_NCCL(ctx, g_nccl.Broadcast(pairs, pairs, nc * 4 * sizeof(uint4), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(node0, node0, sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
-    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    GroupGuard grp;
+    RTR_NCCL_G(grp, g_nccl.Broadcast(pairs, pairs, nc * 4 * sizeof(uint4), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(node0, node0, sizeof(rtr_node), kNcclUint8, root, comm, ctx->stream));
+    RTR_NCCL_G(grp, g_nccl.Broadcast(b->tparams, b->tparams, sizeof(TraceParams), kNcclUint8, root, comm, ctx->stream));
+    RTR_CHECK(rtr_group_end(ctx, grp));
 
     if (!is_root) {
         b->n = n; b->array_len = n; b->nb_meshes = 0;
@@ -281,14 +304,15 @@ int rtr_allgather_rows(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t h
     const size_t row_bytes = (size_t)width * bytes_per_pixel;
     const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
     RTR_NCCL(ctx, g_nccl.GroupStart());
+    GroupGuard grp;
     for (uint32_t blk = 0; blk < blocks; ++blk) {
         const uint32_t r0 = blk * rows_per_block;
         const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
         char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
-        RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, (int)(blk % (uint32_t)ctx->nranks),
+        RTR_NCCL_G(grp, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, (int)(blk % (uint32_t)ctx->nranks),
                                        ctx->nccl_comm, ctx->stream));
     }
-    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    RTR_CHECK(rtr_group_end(ctx, grp));
     return RTR_OK;
 }
 
@@ -304,14 +328,15 @@ int rtr_allgather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_
     const size_t row_bytes = (size_t)width * bytes_per_pixel;
     const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
     RTR_NCCL(ctx, g_nccl.GroupStart());
+    GroupGuard grp;
     for (uint32_t blk = 0; blk < blocks; ++blk) {
         const uint32_t r0 = blk * rows_per_block;
         const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
         char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
-        RTR_NCCL(ctx, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, owner[blk % owner.size()],
+        RTR_NCCL_G(grp, g_nccl.Broadcast(p, p, (size_t)(r1 - r0) * row_bytes, kNcclUint8, owner[blk % owner.size()],
                                        ctx->nccl_comm, ctx->stream));
     }
-    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    RTR_CHECK(rtr_group_end(ctx, grp));
     return RTR_OK;
 }
 
@@ -329,6 +354,7 @@ int rtr_gather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t h
     const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
     // point to point: every block travels once, from its owner to the root (an all-gather moves nranks - 1 copies)
     RTR_NCCL(ctx, g_nccl.GroupStart());
+    GroupGuard grp;
     for (uint32_t blk = 0; blk < blocks; ++blk) {
         const int own = owner[blk % owner.size()];
         if (own == root || (ctx->rank != root && ctx->rank != own)) continue;
@@ -336,10 +362,67 @@ int rtr_gather_stripes(rtr_ctx* ctx, void* image_dev, uint32_t width, uint32_t h
         const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
         char* p = static_cast<char*>(image_dev) + (size_t)r0 * row_bytes;
         const size_t bytes = (size_t)(r1 - r0) * row_bytes;
-        if (ctx->rank == root) RTR_NCCL(ctx, g_nccl.Recv(p, bytes, kNcclUint8, own, ctx->nccl_comm, ctx->stream));
-        else RTR_NCCL(ctx, g_nccl.Send(p, bytes, kNcclUint8, root, ctx->nccl_comm, ctx->stream));
+        if (ctx->rank == root) RTR_NCCL_G(grp, g_nccl.Recv(p, bytes, kNcclUint8, own, ctx->nccl_comm, ctx->stream));
+        else RTR_NCCL_G(grp, g_nccl.Send(p, bytes, kNcclUint8, root, ctx->nccl_comm, ctx->stream));
     }
-    RTR_NCCL(ctx, g_nccl.GroupEnd());
+    RTR_CHECK(rtr_group_end(ctx, grp));
+    return RTR_OK;
+}
+
+// Sharded host input: an array of n_elems elements is cut into nranks contiguous slices, rank r holding elements
+// [n_elems * r / nranks, n_elems * (r + 1) / nranks) in slice_dev (each rank uploaded its slice over its own PCIe
+// link); the slices are assembled in full_dev on `root` over NVLink.  Every slice travels once.
+int rtr_gather_slices(rtr_ctx* ctx, const void* slice_dev, void* full_dev, uint64_t n_elems, uint32_t elem_bytes, int root) {
+    if (!ctx) return RTR_E_INVALID;
+    if (elem_bytes == 0 || (n_elems && !slice_dev)) return rtr_set_error(ctx, RTR_E_INVALID, "gather_slices: bad argument");
+    if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "gather_slices: bad root %d", root);
+    const bool is_root = ctx->rank == root;
+    if (is_root && !full_dev && n_elems) return rtr_set_error(ctx, RTR_E_INVALID, "gather_slices: the root needs full_dev");
+    auto lo_of = [&](int r) { return n_elems * (uint64_t)r / (uint64_t)ctx->nranks; };
+    const uint64_t my_lo = lo_of(ctx->rank), my_hi = lo_of(ctx->rank + 1);
+    if (is_root && my_hi > my_lo) {
+        char* dst = static_cast<char*>(full_dev) + my_lo * elem_bytes;
+        if (dst != slice_dev)
+            RTR_CUDA(ctx, cudaMemcpyAsync(dst, slice_dev, (my_hi - my_lo) * elem_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (ctx->nranks == 1) return RTR_OK;
+    if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "gather_slices: rtr_comm_init has not been called");
+    RTR_NCCL(ctx, g_nccl.GroupStart());
+    GroupGuard grp;
+    if (is_root) {
+        for (int r = 0; r < ctx->nranks; ++r) {
+            if (r == root) continue;
+            const uint64_t lo = lo_of(r), hi = lo_of(r + 1);
+            if (hi > lo)
+                RTR_NCCL_G(grp, g_nccl.Recv(static_cast<char*>(full_dev) + lo * elem_bytes, (hi - lo) * elem_bytes, kNcclUint8, r,
+                                            ctx->nccl_comm, ctx->stream));
+        }
+    } else if (my_hi > my_lo) {
+        RTR_NCCL_G(grp, g_nccl.Send(slice_dev, (my_hi - my_lo) * elem_bytes, kNcclUint8, root, ctx->nccl_comm, ctx->stream));
+    }
+    return rtr_group_end(ctx, grp);
+}
+
+// Sharded host output: this rank's row blocks of a striped frame go from image_dev straight to the same rows of
+// image_host (a full-size host image, e.g. one pinned buffer shared by all ranks), over this rank's own PCIe link; one
+// asynchronous copy per block on the context's stream.  No collective.
+int rtr_download_stripes_async(rtr_ctx* ctx, void* image_host, const void* image_dev, uint32_t width, uint32_t height,
+                               uint32_t bytes_per_pixel, uint32_t rows_per_block, const uint32_t* stripes_of_rank) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!image_host || !image_dev || width == 0 || height == 0 || bytes_per_pixel == 0 || rows_per_block == 0 || !stripes_of_rank)
+        return rtr_set_error(ctx, RTR_E_INVALID, "download_stripes: bad argument");
+    const std::vector<int> owner = rtr_stripe_owners(stripes_of_rank, ctx->nranks);  // stripe -> rank
+    if (owner.empty()) return rtr_set_error(ctx, RTR_E_INVALID, "download_stripes: no stripes");
+    const size_t row_bytes = (size_t)width * bytes_per_pixel;
+    const uint32_t blocks = (height + rows_per_block - 1) / rows_per_block;
+    for (uint32_t blk = 0; blk < blocks; ++blk) {
+        if (owner[blk % owner.size()] != ctx->rank) continue;
+        const uint32_t r0 = blk * rows_per_block;
+        const uint32_t r1 = (r0 + rows_per_block < height) ? r0 + rows_per_block : height;
+        const size_t off = (size_t)r0 * row_bytes;
+        RTR_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(image_host) + off, static_cast<const char*>(image_dev) + off,
+                                      (size_t)(r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     return RTR_OK;
 }
 

@@ -288,7 +288,7 @@ __device__ __forceinline__ void ploc_process_tile(IterSmem& s, const uint32_t ti
                                                   const uint32_t n, const uint32_t total, const uint32_t iter,
                                                   const uint32_t n_leaves, const int radius,
                                                   const uint32_t* __restrict__ cin, uint32_t* __restrict__ cout,
-                                                  float4* __restrict__ node, uint32_t* __restrict__ isize,
+                                                  float4* __restrict__ node, uint2* __restrict__ isize,
                                                   PlocState* __restrict__ nxt, uint64_t* __restrict__ tile_status,
                                                   uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
                                                   uint32_t* __restrict__ iter_first_id) {
@@ -470,9 +470,9 @@ __device__ __forceinline__ void ploc_process_tile(IterSmem& s, const uint32_t ti
                 store_box(node, new_id,
                           make_float4(fminf(lo[i].x, plo.x), fminf(lo[i].y, plo.y), fminf(lo[i].z, plo.z), fmaxf(lo[i].w, plo.w)),
                           make_float4(fmaxf(hi[i].x, phi.x), fmaxf(hi[i].y, phi.y), __uint_as_float(cl), __uint_as_float(cr)));
-                const uint32_t sl = cl < n_leaves ? 1u : __ldcg(isize + (cl - n_leaves));  // written by other SMs in earlier iterations
-                const uint32_t sr = cr < n_leaves ? 1u : __ldcg(isize + (cr - n_leaves));
-                isize[new_id - n_leaves] = sl + sr + 1u;
+                const uint32_t sl = cl < n_leaves ? 1u : __ldcg(isize + (cl - n_leaves)).x;  // written by other SMs in earlier iterations
+                const uint32_t sr = cr < n_leaves ? 1u : __ldcg(isize + (cr - n_leaves)).x;
+                isize[new_id - n_leaves] = make_uint2(sl + sr + 1u, sl);  // nodes in the subtree, and in its left part
                 out_id = new_id;
                 ++ex_lo_local;
             }
@@ -506,18 +506,27 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& genera
 template <bool FULL>
 __global__ void __launch_bounds__(kPT, RTR_PLOC_MINB)
 ploc_loop_kernel(uint32_t n_leaves, int radius, uint32_t* __restrict__ buf0, uint32_t* __restrict__ buf1,
-                 float4* __restrict__ node, uint32_t* __restrict__ isize,
+                 float4* __restrict__ node, uint2* __restrict__ isize,
                  PlocState* __restrict__ state, uint64_t* __restrict__ tile_status,
                  uint32_t* __restrict__ trace_active, uint32_t* __restrict__ trace_merges,
-                 uint32_t* __restrict__ iter_first_id, uint32_t* __restrict__ barrier_counter) {
+                 uint32_t* __restrict__ iter_first_id, uint32_t* __restrict__ barrier_counter,
+                 unsigned long long* __restrict__ iter_ns) {
     __shared__ IterSmem s;
     const int tid = (int)threadIdx.x;
     uint32_t generation = 0u, parity = 0u, prev_n = 0xFFFFFFFFu;
+    auto stamp = [&](uint32_t slot) {  // %globaltimer at the start of iteration `slot` (rtr_bvh_iteration_times)
+        if (blockIdx.x == 0 && tid == 0 && slot <= kMaxPlocIterations) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            iter_ns[slot] = t;
+        }
+    };
     while (true) {
         PlocState* cur = &state[parity];
         PlocState* nxt = &state[parity ^ 1u];
         const uint32_t n = ld_relaxed_u32(&cur->n_active), total = ld_relaxed_u32(&cur->total), iter = ld_relaxed_u32(&cur->iter);
         // done, handed to the tail kernel, or stuck (non-finite areas never merge, Q4: the reference would spin forever)
+        stamp(iter);
         if (n <= kTailN || n >= prev_n || iter >= kMaxPlocIterations) break;
         prev_n = n;
         const uint32_t tiles = (n + kTileT - 1) / kTileT;
@@ -557,9 +566,10 @@ struct TailSmem {
 __global__ void __launch_bounds__(kTailN)
 ploc_tail_kernel(uint32_t n_leaves, int radius,
                  const uint32_t* __restrict__ buf0, const uint32_t* __restrict__ buf1,
-                 float4* __restrict__ node, uint32_t* __restrict__ isize,
+                 float4* __restrict__ node, uint2* __restrict__ isize,
                  PlocState* __restrict__ state, uint32_t* __restrict__ trace_active,
-                 uint32_t* __restrict__ trace_merges, uint32_t* __restrict__ iter_first_id) {
+                 uint32_t* __restrict__ trace_merges, uint32_t* __restrict__ iter_first_id,
+                 unsigned long long* __restrict__ iter_ns) {
     extern __shared__ __align__(16) unsigned char tail_raw[];
     TailSmem& s = *reinterpret_cast<TailSmem*>(tail_raw);
     const uint32_t tid = threadIdx.x;
@@ -572,7 +582,7 @@ ploc_tail_kernel(uint32_t n_leaves, int radius,
         const uint32_t id = cin[tid];
         const Box bx_ = load_box(node, id); const float4 lo = bx_.lo, hi = bx_.hi;
         s.id[0][tid] = id;
-        s.size[0][tid] = id < n_leaves ? 1u : isize[id - n_leaves];
+        s.size[0][tid] = id < n_leaves ? 1u : isize[id - n_leaves].x;
         s.box[0][0][tid] = lo.x; s.box[0][1][tid] = lo.y; s.box[0][2][tid] = lo.z;
         s.box[0][3][tid] = lo.w; s.box[0][4][tid] = hi.x; s.box[0][5][tid] = hi.y;
     }
@@ -603,7 +613,7 @@ ploc_tail_kernel(uint32_t n_leaves, int radius,
                 const uint32_t sz = s.size[cur_buf][q] + s.size[cur_buf][nn] + 1u;
                 store_box(node, new_id, make_float4(mnx, mny, mnz, mxx),
                           make_float4(mxy, mxz, __uint_as_float(cl), __uint_as_float(cr)));
-                isize[new_id - n_leaves] = sz;
+                isize[new_id - n_leaves] = make_uint2(sz, s.size[cur_buf][q]);
                 s.id[nb][dst] = new_id; s.size[nb][dst] = sz;
                 s.box[nb][0][dst] = mnx; s.box[nb][1][dst] = mny; s.box[nb][2][dst] = mnz;
                 s.box[nb][3][dst] = mxx; s.box[nb][4][dst] = mxy; s.box[nb][5][dst] = mxz;
@@ -615,6 +625,9 @@ ploc_tail_kernel(uint32_t n_leaves, int radius,
         }
         if (tid == 0 && iter < kMaxPlocIterations) {
             trace_active[iter] = n; trace_merges[iter] = merges; iter_first_id[iter + 1] = total + merges;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            iter_ns[iter + 1] = t;  // end of iteration `iter` (its start: the previous stamp)
         }
         n -= removed; total += merges; iter += 1; cur_buf = nb;
         __syncthreads();
@@ -641,12 +654,12 @@ __device__ __forceinline__ void store_node(rtr_node* __restrict__ flat, uint32_t
 // (scene.cpp:189-199) -- and records which cluster sits at each position.  Only 4-byte arrays are touched
 // (order 8 B/triangle, ipos and isize 4 B/triangle), which the 126 MB L2 absorbs.
 __device__ __forceinline__ void place_children(uint32_t c, uint32_t n_leaves, const float4* __restrict__ node,
-                                               const uint32_t* __restrict__ isize, uint32_t* __restrict__ ipos,
+                                               const uint2* __restrict__ isize, uint32_t* __restrict__ ipos,
                                                uint32_t* __restrict__ order) {
     const uint32_t p = __ldcg(ipos + (c - n_leaves));  // written by another SM one level up (same kernel): L2, not L1
     const float4 hi = __ldg(node + 2 * (size_t)c + 1);
     const uint32_t L = __float_as_uint(hi.z), R = __float_as_uint(hi.w);
-    const uint32_t size_l = L < n_leaves ? 1u : isize[L - n_leaves];
+    const uint32_t size_l = isize[c - n_leaves].y;  // own record (coalesced over a level), not the child's
     const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
     order[pos_l] = L;
     order[pos_r] = R;
@@ -662,7 +675,7 @@ constexpr uint32_t kSmallLevel = 2048;
 constexpr int kFlattenBlock = 512;
 __global__ void __launch_bounds__(kFlattenBlock)
 flatten_positions_kernel(const PlocState* __restrict__ state, const uint32_t* __restrict__ iter_first_id, uint32_t n_leaves,
-                         const float4* __restrict__ node, const uint32_t* __restrict__ isize,
+                         const float4* __restrict__ node, const uint2* __restrict__ isize,
                          uint32_t* __restrict__ ipos, uint32_t* __restrict__ order, uint32_t* __restrict__ barrier_counter) {
     const PlocState fin = state[2];
     if (fin.n_active != 1u || fin.total != 2u * n_leaves - 1u) return;  // the build did not converge: nothing to place
@@ -719,7 +732,7 @@ __device__ __forceinline__ void store_inner_record(uint4* __restrict__ pairs, ui
 // a warp are contiguous; the left child's record is the next lane's own (position p + 1).
 __global__ void __launch_bounds__(256)
 flatten_emit_kernel(const PlocState* __restrict__ state, uint32_t nb_nodes, uint32_t n_leaves, const uint32_t* __restrict__ order,
-                    const float4* __restrict__ node, const uint32_t* __restrict__ isize,
+                    const float4* __restrict__ node, const uint2* __restrict__ isize,
                     const float4* __restrict__ wtri, rtr_node* __restrict__ flat, uint4* __restrict__ pairs) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (state[2].n_active != 1u || state[2].total != nb_nodes) {
@@ -735,12 +748,19 @@ flatten_emit_kernel(const PlocState* __restrict__ state, uint32_t nb_nodes, uint
     const bool live = p < nb_nodes;
     const uint32_t c = live ? order[p] : 0u;
     const Box me = load_box(node, c);
-    // the next position's record (the left child of an inner node), through the warp
-    Box nx;
+    const uint32_t my_size_l = (live && c >= n_leaves) ? isize[c - n_leaves].y : 1u;  // nodes in the left subtree
+    // the records of the next two positions -- the left child of an inner node and that child's own left child --
+    // come through the warp instead of two more gathers
+    Box nx, nx2;
     nx.lo.x = __shfl_down_sync(0xffffffffu, me.lo.x, 1); nx.lo.y = __shfl_down_sync(0xffffffffu, me.lo.y, 1);
     nx.lo.z = __shfl_down_sync(0xffffffffu, me.lo.z, 1); nx.lo.w = __shfl_down_sync(0xffffffffu, me.lo.w, 1);
     nx.hi.x = __shfl_down_sync(0xffffffffu, me.hi.x, 1); nx.hi.y = __shfl_down_sync(0xffffffffu, me.hi.y, 1);
     nx.hi.z = __shfl_down_sync(0xffffffffu, me.hi.z, 1); nx.hi.w = __shfl_down_sync(0xffffffffu, me.hi.w, 1);
+    nx2.lo.x = __shfl_down_sync(0xffffffffu, me.lo.x, 2); nx2.lo.y = __shfl_down_sync(0xffffffffu, me.lo.y, 2);
+    nx2.lo.z = __shfl_down_sync(0xffffffffu, me.lo.z, 2); nx2.lo.w = __shfl_down_sync(0xffffffffu, me.lo.w, 2);
+    nx2.hi.x = __shfl_down_sync(0xffffffffu, me.hi.x, 2); nx2.hi.y = __shfl_down_sync(0xffffffffu, me.hi.y, 2);
+    nx2.hi.z = __shfl_down_sync(0xffffffffu, me.hi.z, 2); nx2.hi.w = __shfl_down_sync(0xffffffffu, me.hi.w, 2);
+    const uint32_t nx_size_l = __shfl_down_sync(0xffffffffu, my_size_l, 1);
     if (!live) return;
     const bool leaf = c < n_leaves;
     const uint32_t L = __float_as_uint(me.hi.z), R = __float_as_uint(me.hi.w);
@@ -749,16 +769,51 @@ flatten_emit_kernel(const PlocState* __restrict__ state, uint32_t nb_nodes, uint
         store_leaf_record(pairs, p, me.lo, me.hi, wtri + 3 * (size_t)c, L);
         return;
     }
+    const uint32_t lane = lane_id();
     const bool lleaf = L < n_leaves, rleaf = R < n_leaves;
-    const uint32_t size_l = lleaf ? 1u : isize[L - n_leaves];
-    const uint32_t pos_l = p + 1u, pos_r = p + 1u + size_l;
+    const uint32_t pos_l = p + 1u, pos_r = p + 1u + my_size_l;
     const Box br = load_box(node, R);
-    const Box bl = (lane_id() < 31u) ? nx : load_box(node, L);
+    const Box bl = (lane < 31u) ? nx : load_box(node, L);
     store_node(flat, p, me.lo, me.hi, 0u, pos_l, pos_r);  // internal _TriangleId stays 0 (bvh.cpp:415-420)
     uint4 o0, o1;
     trav_encode_inner(me.lo, make_float2(me.hi.x, me.hi.y), bl.lo, make_float2(bl.hi.x, bl.hi.y),
                       br.lo, make_float2(br.hi.x, br.hi.y), lleaf, rleaf, pos_r, o0, o1);
+    // ---- second half (bvh.cuh): the four grandchild slots on the node's own grid.  Slot 0 / 1 = the children of L
+    //      (L itself, twice, when it is a leaf), slot 2 / 3 = those of R; slot 0 sits at p + 2, slot 2 at pos_r + 1. ----
+    float4 glo[4]; float2 ghi[4];
+    uint32_t idx1, idx3, leaf_bits = 0u;
+    if (lleaf) {
+        glo[0] = glo[1] = bl.lo; ghi[0] = ghi[1] = make_float2(bl.hi.x, bl.hi.y);
+        idx1 = pos_l; leaf_bits |= 3u;
+    } else {
+        const uint32_t LL = __float_as_uint(bl.hi.z), LR = __float_as_uint(bl.hi.w);
+        const Box b0 = (lane < 30u) ? nx2 : load_box(node, LL);
+        const Box b1 = load_box(node, LR);
+        const uint32_t size_ll = (lane < 31u) ? nx_size_l : isize[L - n_leaves].y;
+        glo[0] = b0.lo; ghi[0] = make_float2(b0.hi.x, b0.hi.y);
+        glo[1] = b1.lo; ghi[1] = make_float2(b1.hi.x, b1.hi.y);
+        idx1 = p + 2u + size_ll;
+        leaf_bits |= (LL < n_leaves ? 1u : 0u) | (LR < n_leaves ? 2u : 0u);
+    }
+    if (rleaf) {
+        glo[2] = glo[3] = br.lo; ghi[2] = ghi[3] = make_float2(br.hi.x, br.hi.y);
+        idx3 = pos_r; leaf_bits |= 0xCu;
+    } else {
+        const uint32_t RL = __float_as_uint(br.hi.z), RR = __float_as_uint(br.hi.w);
+        const Box b2 = load_box(node, RL), b3 = load_box(node, RR);
+        glo[2] = b2.lo; ghi[2] = make_float2(b2.hi.x, b2.hi.y);
+        glo[3] = b3.lo; ghi[3] = make_float2(b3.hi.x, b3.hi.y);
+        idx3 = pos_r + 1u + isize[R - n_leaves].y;
+        leaf_bits |= (RL < n_leaves ? 4u : 0u) | (RR < n_leaves ? 8u : 0u);
+    }
+    bool ok = true;
+    uint4 o2, o3;
+    trav_encode_quads(me.lo, make_float2(me.hi.x, me.hi.y), glo, ghi, idx1 | ((leaf_bits & 2u) ? 0x80000000u : 0u),
+                      idx3 | ((leaf_bits & 8u) ? 0x80000000u : 0u), o2, o3, ok);
+    if (ok && !((o0.w >> 24) & 4u)) o0.w |= (0x80u | (leaf_bits << 3)) << 24;  // second half usable + which slots are leaves
     store_inner_record(pairs, p, o0, o1);
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(pairs + (size_t)p * 4 + 2), "r"(o2.x), "r"(o2.y), "r"(o2.z), "r"(o2.w), "r"(o3.x), "r"(o3.y), "r"(o3.z), "r"(o3.w) : "memory");
 }
 
 __global__ void flatten_single_leaf_kernel(const float4* node, const float4* wtri, rtr_node* flat, uint4* pairs) {
@@ -797,13 +852,12 @@ pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t
     store_inner_record(pairs, i, o0, o1);
 }
 
-// Second half of every inner traversal record (bvh.cuh): the four grandchild slots on the node's own grid, for the
-// traversal's wide step.  One thread per flat index, after the first halves and the flat nodes are written.
+// Second half of every inner traversal record (bvh.cuh) of an ADOPTED / received flat array (a BVH built here gets both
+// halves from flatten_emit_kernel): the four grandchild slots on the node's own grid, for the traversal's wide step.
 __global__ void __launch_bounds__(256)
-pack_quads_kernel(const PlocState* __restrict__ state, const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* __restrict__ pairs) {
+pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* __restrict__ pairs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_nodes) return;
-    if (state && (state[2].n_active != 1u || state[2].total != nb_nodes)) return;  // failed build: see flatten_emit_kernel
     const uint4* me = reinterpret_cast<const uint4*>(flat + i);
     const uint4 links = __ldg(me + 2);
     if (links.y == 0u && links.z == 0u) return;
@@ -912,7 +966,7 @@ int rtr_bvh_pack_pairs_own(rtr_bvh* b) {
     pack_pairs_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->wtri_by_rank ? 1u : 0u, b->wtri_view,
                                                                  b->pairs_own, b->tparams);
     RTR_LAUNCH_CHECK(ctx);
-    pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nullptr, b->flat_view, nc, b->pairs_own);
+    pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->flat_view, nc, b->pairs_own);
     RTR_LAUNCH_CHECK(ctx);
     b->pairs_view = b->pairs_own;
     return RTR_OK;
@@ -975,14 +1029,14 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         uint32_t n_arg = n; int radius_arg = radius;
         uint32_t* ctl0 = b->ctl;
         void* args[] = {&n_arg, &radius_arg, &b->cin, &b->cout, &b->node, &b->isize, &b->state, &b->tile_status,
-                        &b->trace_active, &b->trace_merges, &b->iter_first_id, &ctl0};
+                        &b->trace_active, &b->trace_merges, &b->iter_first_id, &ctl0, &b->iter_ns};
         RTR_PROF(ctx, "ploc_loop_kernel");
         RTR_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kPT), args, 0, ctx->stream));
         RTR_LAUNCH_CHECK(ctx);
     }
     RTR_PROF(ctx, "ploc_tail_kernel");
     ploc_tail_kernel<<<1, kTailN, sizeof(TailSmem), ctx->stream>>>(n, radius, b->cin, b->cout, b->node, b->isize, b->state,
-                                                                   b->trace_active, b->trace_merges, b->iter_first_id);
+                                                                   b->trace_active, b->trace_merges, b->iter_first_id, b->iter_ns);
     RTR_LAUNCH_CHECK(ctx);
     RTR_CHECK(record(b, 4));
 
@@ -1008,9 +1062,6 @@ int rtr_bvh_run_build(rtr_bvh* b) {
         const uint32_t nc = 2 * n - 1;
         RTR_PROF(ctx, "flatten_emit_kernel");
         flatten_emit_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->state, nc, n, b->order, b->node, b->isize, b->wtri, b->flat, b->pairs);
-        RTR_LAUNCH_CHECK(ctx);
-        RTR_PROF(ctx, "pack_quads_kernel");
-        pack_quads_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(b->state, b->flat, nc, b->pairs);
         RTR_LAUNCH_CHECK(ctx);
     }
     b->pairs_view = b->pairs;  // written by the flatten kernels

@@ -46,6 +46,42 @@ def pixels_of_rank(width: int, height: int, rank: int, world: int, rows_per_bloc
     return int(rows_of_rank(height, rank, world, rows_per_block).size) * width
 
 
+def slice_range(n_elems: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of the contiguous slice of an n_elems array that `rank` uploads itself (rtr_gather_slices)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    return n_elems * rank // world, n_elems * (rank + 1) // world
+
+
+def gather_slices(my_slice, full, n_elems: int, root: int = 0, group=None):
+    """Host-side mirror of rtr_gather_slices: `full` (root only) receives every rank's slice at its place.
+    Works on CPU tensors with gloo and CUDA tensors with NCCL; every slice travels once."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = slice_range(n_elems, rank, world)
+    if rank == root:
+        full[lo:hi] = my_slice
+        works = []
+        for r in range(world):
+            a, b = slice_range(n_elems, r, world)
+            if r != root and b > a:
+                works.append(dist.irecv(full[a:b], src=r, group=group))
+        for w in works:
+            w.wait()
+    elif hi > lo:
+        dist.send(my_slice, dst=root, group=group)
+    return full
+
+
+def write_stripes(shared_image, local_image, height: int, layout: List[int], rank: int,
+                  rows_per_block: int = DEFAULT_ROWS_PER_BLOCK):
+    """Host-side mirror of rtr_download_stripes_async: this rank's row blocks go to the same rows of an image all
+    ranks share (no collective)."""
+    for r0, r1 in blocks_of_rank_striped(height, rank, layout, rows_per_block):
+        shared_image[r0:r1] = local_image[r0:r1]
+    return shared_image
+
+
 # ---- weighted dealing: the rank that rebuilds the BVH renders fewer rows ------------------------------------
 def stripe_layout(world: int, builder_share: float = 1.0, stripes_per_rank: int = 8) -> List[int]:
     """Stripes owned by each rank.  Block b of the image belongs to stripe b % sum(layout); rank r owns

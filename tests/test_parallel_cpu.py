@@ -178,3 +178,61 @@ def test_striped_gather_over_gloo(tmp_path, world, height):
     port = _free_port()
     mp.spawn(_striped_worker, args=(world, port, height, 8, 16, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+# ---- sharded host traffic: every rank uploads a slice of the triangles and downloads its own rows ------------
+def test_slices_partition_the_array():
+    for n in (0, 1, 7, 1000, 10_000_001):
+        for world in (1, 2, 3, 8):
+            cuts = [parallel.slice_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    with pytest.raises(ValueError):
+        parallel.slice_range(10, 2, 2)
+
+
+def _sharded_worker(rank, world, port, n, height, width, rpb, layout, out_dir):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from realtimeraytracing_b200 import parallel as par
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # input: rank r holds only its slice of the frame's triangles; the build rank assembles them
+        lo, hi = par.slice_range(n, rank, world)
+        mine = torch.arange(lo, hi, dtype=torch.int64) * 7
+        full = torch.full((n,), -1, dtype=torch.int64) if rank == 0 else None
+        par.gather_slices(mine, full, n, root=0)
+        if rank == 0:
+            assert torch.equal(full, torch.arange(n, dtype=torch.int64) * 7)
+        # output: every rank writes its own row blocks into one image all ranks share (a file mapping here, a pinned
+        # host buffer in bench.py); nobody gathers
+        shared = np.memmap(os.path.join(out_dir, "image"), dtype=np.float32, mode="r+", shape=(height, width))
+        local = np.full((height, width), -1.0, np.float32)
+        for r0, r1 in par.blocks_of_rank_striped(height, rank, layout, rpb):
+            local[r0:r1] = np.arange(r0, r1, dtype=np.float32)[:, None] * 100 + rank
+        par.write_stripes(shared, local, height, layout, rank, rpb)
+        shared.flush()
+        dist.barrier()
+        if rank == 0:
+            owner = np.array([par.owner_of_block_striped(r // rpb, layout) for r in range(height)], np.float32)
+            exp = (np.arange(height, dtype=np.float32) * 100 + owner)[:, None] * np.ones((1, width), np.float32)
+            assert np.array_equal(np.asarray(shared), exp)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,layout", [(2, [3, 8]), (3, [0, 4, 4])])
+def test_sharded_upload_and_download_over_gloo(tmp_path, world, layout):
+    import numpy as np
+    import torch.multiprocessing as mp
+    height, width = 100, 12
+    np.memmap(str(tmp_path / "image"), dtype=np.float32, mode="w+", shape=(height, width)).flush()
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(world, port, 1001, height, width, 8, layout, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))

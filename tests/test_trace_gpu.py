@@ -375,6 +375,12 @@ def test_stack_overflow_is_never_silent(ctx, oracle):
     rays["o"][:, :3] = (0.05, -0.1, -10.0); rays["o"][:, 3] = 1.0
     rays["d"][:, :3] = (0.001, 0.002, 1.0)
     rays["d"][:, :3] /= np.linalg.norm(rays["d"][0, :3])
+    # through a corner of every box but outside every triangle: an any-hit ray finds no occluder and has to walk the
+    # whole chain (with a distance limit the default order would prune the chain away instead)
+    miss = rays.copy()
+    miss["o"][:, :3] = (0.9, 0.9, -10.0)
+    miss["d"][:, :3] = (0.0001, 0.0001, 1.0)
+    miss["d"][:, :3] /= np.linalg.norm(miss["d"][0, :3])
     for (tris, meshes, flat), fits in ((shallow, True), (deep, False)):
         d_nodes, d_tris, d_meshes = ctx.dev_alloc(flat.nbytes), ctx.dev_alloc(tris.nbytes), ctx.dev_alloc(meshes.nbytes)
         ctx.upload(d_nodes, flat); ctx.upload(d_tris, tris); ctx.upload(d_meshes, meshes)
@@ -382,16 +388,17 @@ def test_stack_overflow_is_never_silent(ctx, oracle):
         try:
             exp = oracle.trace_rays(flat, tris, meshes, rays)
             assert exp["did_hit"].all() and (exp["tri"] == tris.size - 1).all()        # the nearest triangle, z = 0
+            assert not oracle.trace_rays(flat, tris, meshes, miss)["did_hit"].any()
             for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER):
                 for any_hit in (False, True):
-                    tmax = np.full(rays.size, 1e-3, np.float32) if any_hit else None   # nothing that close: the whole chain is walked
+                    batch = miss if any_hit else rays
                     if fits:
-                        got = bvh.trace_rays(rays, any_hit=any_hit, t_max=tmax, flags=flags)
+                        got = bvh.trace_rays(batch, any_hit=any_hit, flags=flags)
                         if any_hit: assert not got["did_hit"].any()
                         else: assert_hits_equal(got, exp, "chain of 100")
                     else:
                         with pytest.raises(capi.RtrError) as e:
-                            bvh.trace_rays(rays, any_hit=any_hit, t_max=tmax, flags=flags)
+                            bvh.trace_rays(batch, any_hit=any_hit, flags=flags)
                         assert e.value.code == -5, (flags, any_hit, str(e.value))      # RTR_E_UNSUPPORTED
             if not fits:
                 d_rays, d_hits = ctx.dev_alloc(rays.nbytes), ctx.dev_alloc(rays.size * 24)
