@@ -181,6 +181,54 @@ class CpuArm:
             self.n, build, self.w, self.h, self.bounces, self.cores)
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_stage_baselines(args):
+    """every stage of the path on the host cores of THIS box, next to the GPU numbers --
+    the reference's own code where it compiles (bvh.cpp, its std::sort of pairs), a host radix sort of the same design
+    as the Onesweep kernel, the oracle's traversal.  Thread counts are stated per entry.  (oracle/, CPU arm only.)"""
+    from oracle import Oracle, Reference, reference_available
+    from realtimeraytracing_b200 import synth
+    o = Oracle()
+    cores = os.cpu_count() or 1
+    out = {"cores_available": cores, "cpu": cpu_model()}
+    ref = Reference(65536) if reference_available(65536) else None
+    for label, n in (("10M", 10_000_000), ("1M_config1", 1_000_000)):
+        keys = synth.random_keys_u32(n, seed=1)
+        idx = np.arange(n, dtype=np.uint32)
+        if ref is not None:
+            _, _, ms = ref.sort_pairs_ms(keys)
+            out["sort_pairs_%s_std_sort" % label] = {"ms": ms, "gkeys_s": n / ms / 1e6, "cores": 1,
+                                                     "what": "std::sort of pair<code,index>, the reference's sort (bvh.cpp:223-231)"}
+        for th in sorted({1, cores}):
+            k2, v2 = keys.copy(), idx.copy()   # sorted in place
+            t0 = time.perf_counter()
+            o.lib.orc_radix_sort_pairs_mt(k2.ctypes.data, v2.ctypes.data, n, th)
+            ms = (time.perf_counter() - t0) * 1e3
+            assert k2[0] <= k2[n // 2] <= k2[-1]
+            out["sort_pairs_%s_host_lsd_%dt" % (label, th)] = {"ms": ms, "gkeys_s": n / ms / 1e6, "cores": th,
+                                                              "what": "stable LSD radix-256 sort of (key, index) pairs, OpenMP"}
+    # the reference's bvh.cpp (capacity-patched): 1 thread at 1 M triangles, and 1 vs all threads at 262 144
+    if reference_available(1048576):
+        big = Reference(1048576)
+        for n, threads in ((1_000_000, 1), (262_144, 1), (262_144, cores)):
+            tris, meshes, _ = synth.triangle_soup(n)
+            big.set_threads(threads)
+            ms = big.bvh_build(tris, meshes, want_morton=False, timing_only=True).build_ms
+            out["bvh_cpp_build_%d_tris_%dt" % (n, threads)] = {"ms": ms, "mtris_s": n / ms / 1e3, "cores": threads,
+                                                            "what": "cr::BVH constructor of the reference (bvh.cpp:11-24), OpenMP threads as stated"}
+        big.set_threads(1)
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -215,7 +263,7 @@ ALGO_BYTES = {  # algorithmic HBM bytes per launch as a function of (n triangles
     "radix_histogram_kernel": lambda n: 4.0 * n,
     "scene_aabb_kernel": lambda n: 64.0 * n,
     "morton_kernel": lambda n: 72.0 * n,                 # 64 read + code 4 + index 4
-    "leaf_init_kernel": lambda n: 104.0 * n,             # index 4 + triangle 64 + node 32 + active id 4
+    "leaf_init_kernel": lambda n: 116.0 * n,             # index 4 + triangle 64 + node 48 (32-byte record + active id + the traversal copy is extra)
 }
 
 
@@ -777,13 +825,18 @@ def main():
             extras["trace_only"] = {"ms_per_frame": tr_ms / 3, "mrays_s": tr_rays / (tr_ms * 1e-3) / 1e6,
                                     "rays_per_frame": tr_rays // 3}
 
-    cpu_baseline = None
+    cpu_baseline = cpu_stages = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cn, cw, ch = cpu_sample_sizes(args, 12.0)
         arm = CpuArm(args, cn, cw, ch)
-        crays, csecs = arm.step()
+        crays, csecs, cbuild = arm.step(split=True)
         cpu_baseline = {"value": crays / csecs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": arm.kind,
-                        "sample": arm.describe(), "seconds": csecs}
+                        "sample": arm.describe(), "seconds": csecs,
+                        "rebuild_seconds": cbuild, "traversal_mrays_s": crays / max(1e-9, csecs - cbuild) / 1e6,
+                        "note": "a bounded sample (%.1f %% of the triangles, %.1f %% of the pixels of the GPU workload): unpruned CPU "
+                                "Mrays/s falls as the scene grows, so value / this understates the like-for-like ratio"
+                                % (100.0 * cn / n, 100.0 * cw * ch / (W * H))}
+        cpu_stages = cpu_stage_baselines(args)
 
     if rank == 0:
         line = {
@@ -805,6 +858,7 @@ def main():
             "image_check": image_check,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "cpu_stage_baselines": cpu_stages,
         }
         if pipelined:
             line["multi_gpu"] = phases

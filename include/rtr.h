@@ -241,6 +241,10 @@ int rtr_bvh_adopt_dev(rtr_ctx* ctx, const rtr_node* nodes_dev, uint32_t nb_trian
  * first.  The default order prunes by the closest hit found so far with a conservative margin
  * and returns identical results. */
 #define RTR_TRACE_REFERENCE_ORDER 1u
+/* the shader's loop with the shader's own stack: `const uint STACK_SIZE = 1024` (raytracer.glsl:251) where the other
+ * kernels keep 128 entries per lane.  Same records, slower (the stack lives in local memory).  The host-pointer calls
+ * fall back to it by themselves when a ray runs out of the 128 entries; see rtr_bvh_stack_overflows. */
+#define RTR_TRACE_DEEP_STACK 2u
 
 int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* camera,
                       uint32_t width, uint32_t height, uint32_t denom_w, uint32_t denom_h,
@@ -251,8 +255,9 @@ int rtr_trace_primary_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* ca
 /* explicit ray batches (getClosestHitBVH semantics); any_hit != 0: did_hit = 1 iff a hit with
  * t < t_max[i] exists (t_max NULL = +inf), other fields zero.
  * Directions: the shader's rays are unit vectors and the default order's pruning margin is derived for them; it holds
- * with room up to |direction| = 8.  rtr_trace_rays refuses longer directions in the default order (RTR_E_UNSUPPORTED;
- * RTR_TRACE_REFERENCE_ORDER takes any length); the caller of rtr_trace_rays_dev is responsible for the same. */
+ * with room up to |direction| = 8.  A batch of rtr_trace_rays that holds a longer direction is traced in the shader's
+ * own order instead (RTR_TRACE_REFERENCE_ORDER, which takes any length -- same records, no pruning); the caller of
+ * rtr_trace_rays_dev is responsible for the same choice. */
 int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays, uint64_t n_rays, int any_hit,
                    const float* t_max, uint32_t flags, rtr_hit* hits_out);
 int rtr_trace_rays_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_ray* rays_dev, uint64_t n_rays, int any_hit,
@@ -276,10 +281,12 @@ int rtr_render_sharded_dev(rtr_ctx* ctx, const rtr_bvh* bvh, const rtr_camera* c
                            uint32_t bounces, int shadow, const float light_pos[3], uint32_t flags,
                            float* rgba_dev, rtr_hit* primary_hits_dev, uint64_t* rays_traced_dev);
 
-/* The shader's private stack is 1024 entries deep (raytracer.glsl:251), the kernels' 128.  A ray that runs out of it
- * drops subtrees; the kernels count such rays.  rtr_trace_primary / rtr_trace_rays / rtr_render (host pointers) fail
- * with RTR_E_UNSUPPORTED instead of returning an incomplete frame; after the asynchronous _dev forms, this call waits
- * for the ctx stream and returns the count since the last call (and clears it).  0 on every scene measured so far. */
+/* The shader's private stack is 1024 entries deep (raytracer.glsl:251), the fast kernels' 128.  A ray that runs out of
+ * it drops subtrees; the kernels count such rays.  rtr_trace_primary / rtr_trace_rays / rtr_render (host pointers)
+ * then trace the call again with RTR_TRACE_DEEP_STACK -- the shader's loop with the shader's stack -- and fail with
+ * RTR_E_UNSUPPORTED only if a ray exhausts those 1024 entries too (where the shader itself writes out of bounds);
+ * after the asynchronous _dev forms, this call waits for the ctx stream and returns the count since the last call
+ * (and clears it), and the caller may repeat the launch with RTR_TRACE_DEEP_STACK.  0 on every scene measured so far. */
 int rtr_bvh_stack_overflows(const rtr_bvh* bvh, uint32_t* count_out);
 
 /* ---- shading: getColor + main of raytracer.glsl (:159-179, :299-331), the reference's rgba32f frame from the hit

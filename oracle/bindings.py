@@ -80,6 +80,7 @@ class Oracle:
         L.orc_morton_codes64.argtypes = [vp, u32, u32, vp, vp]
         L.orc_sort_pairs.argtypes = [vp, vp, u32]
         L.orc_radix_sort_pairs.argtypes = [vp, vp, u32]
+        L.orc_radix_sort_pairs_mt.argtypes = [vp, vp, u32, i32]
         L.orc_radix_sort_keys_u32.argtypes = [vp, u32]
         L.orc_radix_sort_keys_u64.argtypes = [vp, u32]
         L.orc_radix_sort_pairs_u64.argtypes = [vp, vp, u32]
@@ -169,6 +170,12 @@ class Oracle:
         keys = np.array(keys, dtype=np.uint32)
         vals = np.array(vals, dtype=np.uint32)
         self.lib.orc_radix_sort_pairs(_p(keys), _p(vals), keys.size)
+        return keys, vals
+
+    def radix_sort_pairs_mt(self, keys, vals, threads=0):
+        keys = np.array(keys, dtype=np.uint32)
+        vals = np.array(vals, dtype=np.uint32)
+        self.lib.orc_radix_sort_pairs_mt(_p(keys), _p(vals), keys.size, threads)
         return keys, vals
 
     def radix_sort_keys_u32(self, keys):
@@ -350,8 +357,24 @@ class Reference:
         L.ref_bvh_triangle_indices.argtypes = [vp, vp]
         L.ref_bvh_clusters.argtypes = [vp, vp, vp, vp, vp, vp]
         L.ref_bvh_clusters.restype = u32
+        L.ref_set_threads.argtypes = [C.c_int]
+        L.ref_max_threads.restype = C.c_int
+        L.ref_sort_pairs_ms.argtypes = [vp, u32, vp, vp]
+        L.ref_sort_pairs_ms.restype = C.c_double
         self.cap = int(L.ref_max_triangles())
         assert self.cap == cap
+
+    def set_threads(self, n: int):
+        """OpenMP threads of the next builds (cluster ids are only reproducible with 1, Q3)."""
+        self.lib.ref_set_threads(int(n))
+
+    def sort_pairs_ms(self, codes):
+        """The reference's std::sort of (code, index) pairs (bvh.cpp:223-231): (sorted codes, indices, milliseconds)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        k = np.zeros(codes.size, np.uint32)
+        v = np.zeros(codes.size, np.uint32)
+        ms = float(self.lib.ref_sort_pairs_ms(_p(codes), codes.size, _p(k), _p(v)))
+        return k, v, ms
 
     def bvh_build(self, tris, meshes, n=None, want_morton=True, timing_only=False) -> ReferenceBvh:
         n = tris.size if n is None else n

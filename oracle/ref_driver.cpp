@@ -11,10 +11,14 @@
 #include "bvh.hpp"
 #undef private
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <utility>
 #include <vector>
+
+#include <omp.h>
 
 namespace {
 struct RefNode {  // same 48-byte layout as cr::BVH_NodeGPU, padding zeroed
@@ -99,6 +103,24 @@ uint32_t ref_bvh_clusters(const void* h, void* nodes_out, uint32_t* parent, uint
         is_leaf[i] = p._IsLeaf[i].has_value() ? 1 : 0;  // Q9: has_value() is what scene.cpp:193 tests
     }
     return present;
+}
+
+// OpenMP threads of the NEXT ref_bvh_build calls (bvh.cpp:67-147 has the reference's 8 parallel regions).  Cluster ids
+// are only reproducible with 1 thread (Q3); the tree itself is the same for any count.
+void ref_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+int ref_max_threads() { return omp_get_max_threads(); }
+
+// The reference's pair sort, BVH::sortMortonCodesAndTriangleIndices (bvh.cpp:214-232), as a stage of its own for the
+// per-stage CPU baseline: the method is private and only reachable through the constructor (which runs the whole
+// build), so its five lines are restated -- pairs of (code, iota index), std::sort, unzip.  Returns milliseconds.
+double ref_sort_pairs_ms(const uint32_t* codes, uint32_t n, uint32_t* codes_out, uint32_t* indices_out) {
+    std::vector<std::pair<uint32_t, uint32_t>> v(n);
+    for (uint32_t i = 0; i < n; ++i) v[i] = {codes[i], i};
+    auto t0 = std::chrono::steady_clock::now();
+    std::sort(v.begin(), v.end());
+    auto t1 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n; ++i) { codes_out[i] = v[i].first; indices_out[i] = v[i].second; }
+    return std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
 
 }  // extern "C"

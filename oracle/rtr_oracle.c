@@ -268,6 +268,56 @@ void orc_radix_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t n) {
     /* P even: result is back in keys/vals */
     free(hist); free(k2); free(v2);
 }
+/* The same stable LSD radix-256 sort on `threads` host cores (OpenMP): every thread histograms and scatters a
+ * contiguous chunk, chunk offsets per digit come from a (digit-major, thread-minor) exclusive scan, which keeps the
+ * sort stable.  The host-side counterpart of the Onesweep kernel for the per-stage CPU baseline. */
+void orc_radix_sort_pairs_mt(uint32_t* keys, uint32_t* vals, uint32_t n, int threads) {
+    if (n < 2) return;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+    uint32_t* k2 = (uint32_t*)malloc((size_t)n * 4);
+    uint32_t* v2 = (uint32_t*)malloc((size_t)n * 4);
+    uint32_t* hist = (uint32_t*)malloc((size_t)threads * 256 * 4);
+    uint32_t *kin = keys, *vin = vals, *kout = k2, *vout = v2;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#endif
+        {
+#ifdef _OPENMP
+            const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+            const int t = 0, nt = 1;
+#endif
+            const uint64_t lo = (uint64_t)n * t / nt, hi = (uint64_t)n * (t + 1) / nt;
+            uint32_t* h = hist + (size_t)t * 256;
+            memset(h, 0, 256 * 4);
+            for (uint64_t i = lo; i < hi; ++i) h[(kin[i] >> shift) & 255u]++;
+#ifdef _OPENMP
+#pragma omp barrier
+#pragma omp single
+#endif
+            {
+                uint32_t run = 0;
+                for (int d = 0; d < 256; ++d)
+                    for (int q = 0; q < nt; ++q) { uint32_t c = hist[(size_t)q * 256 + d]; hist[(size_t)q * 256 + d] = run; run += c; }
+            }
+            for (uint64_t i = lo; i < hi; ++i) {
+                const uint32_t dst = h[(kin[i] >> shift) & 255u]++;
+                kout[dst] = kin[i]; vout[dst] = vin[i];
+            }
+        }
+        uint32_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    /* 4 passes: the result is back in keys / vals */
+    free(k2); free(v2); free(hist);
+}
+
 void orc_radix_sort_keys_u32(uint32_t* keys, uint32_t n) { orc_radix_sort_pairs(keys, NULL, n); }
 
 void orc_radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint32_t n) {

@@ -99,6 +99,7 @@ void orc_morton_codes(const orc_triangle* tris, uint32_t n, uint32_t array_len,
 /* ---- sort (bvh.cpp:214-232): std::sort on pair<code,index> ---- */
 void orc_sort_pairs(uint32_t* codes, uint32_t* indices, uint32_t n); /* comparison sort */
 void orc_radix_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t n); /* stable LSD radix-256 */
+void orc_radix_sort_pairs_mt(uint32_t* keys, uint32_t* vals, uint32_t n, int threads); /* the same on `threads` cores (<= 0: all) */
 void orc_radix_sort_keys_u32(uint32_t* keys, uint32_t n);
 void orc_radix_sort_keys_u64(uint64_t* keys, uint32_t n);
 void orc_radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint32_t n);

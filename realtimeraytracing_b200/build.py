@@ -56,9 +56,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     objs = []
     tuning = os.environ.get("RTR_NVCC_EXTRA", "").split()  # e.g. "-DRTR_LEAF_BATCH=8" for parameter sweeps
+    only = os.environ.get("RTR_BUILD_ONLY", "").split()    # parameter sweeps: recompile just these sources (objects of the others are reused)
     for src in SOURCES:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
+        if only and src not in only and os.path.exists(obj):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + tuning + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
     failed = False

@@ -15,6 +15,7 @@ TRACE_DEFAULT = 0
 SHADE_WIREFRAME = 1  # RTR_SHADE_WIREFRAME
 SHADE_BVH = 2        # RTR_SHADE_BVH
 TRACE_REFERENCE_ORDER = 1
+TRACE_DEEP_STACK = 2   # the shader's loop with the shader's own 1024-entry stack (raytracer.glsl:251)
 NCCL_UNIQUE_ID_BYTES = 128
 
 # every symbol include/rtr.h declares (tests/test_abi.py checks the header against this list and the .so)

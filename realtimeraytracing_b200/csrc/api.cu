@@ -770,8 +770,8 @@ static int trace_args_ok(rtr_ctx* ctx, const rtr_bvh* b, const void* cam_or_rays
 }
 // the by-the-letter order walks the 48-byte nodes, which a traversal-only replica does not have
 static int order_ok(rtr_ctx* ctx, const rtr_bvh* b, uint32_t flags) {
-    if ((flags & RTR_TRACE_REFERENCE_ORDER) && b->trav_only)
-        return rtr_set_error(ctx, RTR_E_STATE, "trace: RTR_TRACE_REFERENCE_ORDER needs the flat nodes; this BVH holds traversal records only");
+    if ((flags & (RTR_TRACE_REFERENCE_ORDER | RTR_TRACE_DEEP_STACK)) && b->trav_only)
+        return rtr_set_error(ctx, RTR_E_STATE, "trace: RTR_TRACE_REFERENCE_ORDER / RTR_TRACE_DEEP_STACK need the flat nodes; this BVH holds traversal records only");
     return RTR_OK;
 }
 
@@ -782,11 +782,30 @@ static int fetch_overflows(rtr_ctx* ctx, const rtr_bvh* b, uint32_t* host_count)
     RTR_CUDA(ctx, cudaMemcpyAsync(host_count, &b->tparams->stack_overflows, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     return RTR_OK;
 }
-static int refuse_overflows(rtr_ctx* ctx, const rtr_bvh* b, uint32_t count, const char* what) {
+static int refuse_overflows(rtr_ctx* ctx, const rtr_bvh* b, uint32_t count, const char* what, uint32_t flags) {
     if (count == 0u) return RTR_OK;
     cudaMemsetAsync(&b->tparams->stack_overflows, 0, sizeof(uint32_t), ctx->stream);
-    return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "%s: %u ray(s) ran out of traversal stack (128 entries); the frame is incomplete", what, count);
+    return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "%s: %u ray(s) ran out of traversal stack (%d entries%s); the frame is incomplete", what,
+                         count, (flags & RTR_TRACE_DEEP_STACK) ? 1024 : 128,
+                         (flags & RTR_TRACE_DEEP_STACK) ? ", the depth of the shader's own stack, raytracer.glsl:251" : "");
 }
+// The host-pointer calls run `attempt(flags, &overflows)` (launch + copies + stream sync).  If rays ran out of the 128
+// lane-stack entries, the call is traced once more with the shader's own 1024-entry stack (same records by
+// construction); a traversal-only replica has no flat nodes to do that with and fails right away.
+extern "C++" {
+template <typename F>
+static int trace_with_fallback(rtr_ctx* ctx, const rtr_bvh* b, uint32_t flags, const char* what, F&& attempt) {
+    uint32_t overflows = 0;
+    RTR_CHECK(attempt(flags, &overflows));
+    if (overflows != 0u && !(flags & RTR_TRACE_DEEP_STACK) && !b->trav_only) {
+        RTR_CUDA(ctx, cudaMemsetAsync(&b->tparams->stack_overflows, 0, sizeof(uint32_t), ctx->stream));
+        flags |= RTR_TRACE_DEEP_STACK;
+        overflows = 0;
+        RTR_CHECK(attempt(flags, &overflows));
+    }
+    return refuse_overflows(ctx, b, overflows, what, flags);
+}
+}  // extern "C++"
 
 int rtr_bvh_stack_overflows(const rtr_bvh* b, uint32_t* count_out) {
     if (!b) return RTR_E_INVALID;
@@ -818,15 +837,14 @@ int rtr_trace_primary(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uin
     Staging st;
     RTR_CHECK(staging_begin(ctx, bytes + 512, 0, &st));
     rtr_hit* d_hits = static_cast<rtr_hit*>(staging_take(&st, bytes));
-    auto body = [&]() -> int {
-        RTR_CHECK(rtr_trace_primary_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, flags, d_hits));
+    auto attempt = [&](uint32_t f, uint32_t* overflows) -> int {
+        RTR_CHECK(rtr_trace_primary_launch(ctx, b, *cam, width, height, denom_w, denom_h, 0, height, f, d_hits));
         RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        uint32_t overflows = 0;
-        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
+        RTR_CHECK(fetch_overflows(ctx, b, overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return refuse_overflows(ctx, b, overflows, "trace_primary");
+        return RTR_OK;
     };
-    const int r = body();
+    const int r = trace_with_fallback(ctx, b, flags, "trace_primary", attempt);
     staging_end(&st);
     return r;
 }
@@ -853,10 +871,14 @@ int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t
         for (uint64_t i = 0; i < n_rays; ++i) {
             const float* d = rays[i].direction;
             const float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-            if (d2 > 64.f && d2 < INFINITY)
-                return rtr_set_error(ctx, RTR_E_UNSUPPORTED,
-                                     "trace_rays: ray %llu has |direction| = %g; the default order needs |direction| <= 8 "
-                                     "(normalise it, or trace with RTR_TRACE_REFERENCE_ORDER)", (unsigned long long)i, sqrtf(d2));
+            if (d2 > 64.f && d2 < INFINITY) {  // the batch goes through the shader's own order: any length, same records
+                if (b->trav_only)
+                    return rtr_set_error(ctx, RTR_E_UNSUPPORTED,
+                                         "trace_rays: ray %llu has |direction| = %g; a traversal-only replica traces in the default order, "
+                                         "which needs |direction| <= 8 (normalise it)", (unsigned long long)i, sqrtf(d2));
+                flags |= RTR_TRACE_REFERENCE_ORDER;
+                break;
+            }
         }
     }
     const size_t rb = n_rays * sizeof(rtr_ray), hb = n_rays * sizeof(rtr_hit), tb = t_max ? n_rays * 4 : 0;
@@ -865,17 +887,16 @@ int rtr_trace_rays(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, uint64_t
     rtr_ray* d_rays = static_cast<rtr_ray*>(staging_take(&st, rb));
     rtr_hit* d_hits = static_cast<rtr_hit*>(staging_take(&st, hb));
     float* d_tmax = t_max ? static_cast<float*>(staging_take(&st, tb)) : nullptr;
-    auto body = [&]() -> int {
+    auto attempt = [&](uint32_t f, uint32_t* overflows) -> int {
         RTR_CUDA(ctx, cudaMemcpyAsync(d_rays, rays, rb, cudaMemcpyHostToDevice, ctx->stream));
         if (t_max) RTR_CUDA(ctx, cudaMemcpyAsync(d_tmax, t_max, tb, cudaMemcpyHostToDevice, ctx->stream));
-        RTR_CHECK(rtr_trace_rays_launch(ctx, b, d_rays, n_rays, any_hit, d_tmax, flags, d_hits));
+        RTR_CHECK(rtr_trace_rays_launch(ctx, b, d_rays, n_rays, any_hit, d_tmax, f, d_hits));
         RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, hb, cudaMemcpyDeviceToHost, ctx->stream));
-        uint32_t overflows = 0;
-        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
+        RTR_CHECK(fetch_overflows(ctx, b, overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return refuse_overflows(ctx, b, overflows, "trace_rays");
+        return RTR_OK;
     };
-    const int r = body();
+    const int r = trace_with_fallback(ctx, b, flags, "trace_rays", attempt);
     staging_end(&st);
     return r;
 }
@@ -1026,19 +1047,18 @@ int rtr_render(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera* cam, uint32_t w
     float* d_rgba = static_cast<float*>(staging_take(&st, cb));
     rtr_hit* d_hits = static_cast<rtr_hit*>(staging_take(&st, hb));
     uint64_t* d_rays = static_cast<uint64_t*>(staging_take(&st, 8));
-    auto body = [&]() -> int {
+    auto attempt = [&](uint32_t f, uint32_t* overflows) -> int {
         RTR_CUDA(ctx, cudaMemsetAsync(d_rays, 0, 8, ctx->stream));
         RTR_CHECK(rtr_render_launch(ctx, b, *cam, width, height, denom_w, denom_h, row0, row1, bounces, shadow, light_pos,
-                                    flags, d_rgba, hits_out ? d_hits : nullptr, d_rays));
+                                    f, d_rgba, hits_out ? d_hits : nullptr, d_rays));
         if (rgba_out) RTR_CUDA(ctx, cudaMemcpyAsync(rgba_out, d_rgba, cb, cudaMemcpyDeviceToHost, ctx->stream));
         if (hits_out) RTR_CUDA(ctx, cudaMemcpyAsync(hits_out, d_hits, hb, cudaMemcpyDeviceToHost, ctx->stream));
         if (rays_traced) RTR_CUDA(ctx, cudaMemcpyAsync(rays_traced, d_rays, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        uint32_t overflows = 0;
-        RTR_CHECK(fetch_overflows(ctx, b, &overflows));
+        RTR_CHECK(fetch_overflows(ctx, b, overflows));
         RTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return refuse_overflows(ctx, b, overflows, "render");
+        return RTR_OK;
     };
-    const int r = body();
+    const int r = trace_with_fallback(ctx, b, flags, "render", attempt);
     staging_end(&st);
     return r;
 }

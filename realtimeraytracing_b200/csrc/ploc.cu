@@ -1024,7 +1024,11 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             per_sm = c < 1 ? 1 : c;
         }
         const uint32_t tiles = (n + kTileT - 1) / kTileT;
-        uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
+        // Every CTA of a cooperative grid must be resident at once.  SMs the caller keeps for the kernels of a concurrent
+        // collective (rtr_ctx_reserve_sms) are left out of the count: sized for the whole device, the grid could not
+        // become resident before the collective's kernel has left, and the rebuild would queue up behind the broadcast.
+        const int sms = ctx->sm_count - ctx->reserved_sms > 8 ? ctx->sm_count - ctx->reserved_sms : 8;
+        uint32_t grid = (uint32_t)(sms * per_sm);
         if (grid > tiles) grid = tiles;
         uint32_t n_arg = n; int radius_arg = radius;
         uint32_t* ctl0 = b->ctl;
@@ -1050,7 +1054,8 @@ int rtr_bvh_run_build(rtr_bvh* b) {
             RTR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, flatten_positions_kernel, kFlattenBlock, 0));
             ctx->flatten_ctas_per_sm = c < 1 ? 1 : c;
         }
-        uint32_t grid = (uint32_t)(ctx->sm_count * ctx->flatten_ctas_per_sm);
+        const int sms = ctx->sm_count - ctx->reserved_sms > 8 ? ctx->sm_count - ctx->reserved_sms : 8;  // see the PLOC loop
+        uint32_t grid = (uint32_t)(sms * ctx->flatten_ctas_per_sm);
         const uint32_t need = (n + kFlattenBlock - 1) / kFlattenBlock;
         if (grid > need) grid = need;
         uint32_t n_arg = n;

@@ -32,6 +32,12 @@ constexpr uint32_t kValueMask = (1u << 30) - 1;
 #ifndef RTR_SORT_LOOKBATCH
 #define RTR_SORT_LOOKBATCH 4
 #endif
+#ifndef RTR_SORT_RANK_ATOMIC
+#define RTR_SORT_RANK_ATOMIC 1   // 1: one shared atomic per digit group and item (items pipelined); 0: read / last peer stores back
+#endif
+#ifndef RTR_SORT_RANK_GROUP
+#define RTR_SORT_RANK_GROUP 4    // items whose atomics are in flight together
+#endif
 #ifndef RTR_SORT_PREFETCH
 #define RTR_SORT_PREFETCH 296   // tiles ahead whose keys are pulled into L2 (two CTAs on each of the 148 SMs)
 #endif
@@ -301,6 +307,37 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     uint32_t rank[IPT];
     uint32_t* wh = s.whist[warp];
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+#if RTR_SORT_RANK_ATOMIC
+    // The lowest peer lane adds the group's size to the warp's running count of the digit with ONE shared-memory
+    // atomic and hands the old value to its peers by shuffle.  Unlike "read the count, let the last peer store it
+    // back" the items do not wait for each other: the atomics of a group of items are all in flight before the first
+    // result is consumed (same-address atomics of one warp are applied in issue order, __syncwarp orders the items).
+    constexpr int G = RTR_SORT_RANK_GROUP;
+    static_assert(IPT % G == 0, "ranking group");
+#pragma unroll
+    for (int k0 = 0; k0 < IPT; k0 += G) {
+        const bool lb_step = !lb_done;
+        if (lb_step) lb_issue();
+        uint32_t base[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t d = digit_of<KeyT>(key[k0 + j], shift, mask);
+            const uint32_t peers = digit_peers8(d);  // bits above a last partial digit are 0 in every lane: their ballots narrow nothing
+            const uint32_t below = __popc(peers & lt);
+            base[j] = 0u;
+            if (below == 0u) base[j] = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+            __syncwarp();
+            rank[k0 + j] = (d << 16) | (below << 8) | (uint32_t)(__ffs(peers) - 1);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t r = rank[k0 + j];
+            const uint32_t b = __shfl_sync(0xffffffffu, base[j], r & 31u);
+            rank[k0 + j] = (r & 0xFFFF0000u) | (b + ((r >> 8) & 0xFFu));
+        }
+        if (lb_step) lb_consume();
+    }
+#else
 #pragma unroll
     for (int k0 = 0; k0 < IPT; k0 += 4) {
         const bool lb_step = !lb_done;
@@ -321,6 +358,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         }
         if (lb_step) lb_consume();
     }
+#endif
     while (!lb_done) { lb_issue(); lb_consume(); }
     __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
 

@@ -28,7 +28,8 @@
 
 namespace {
 
-constexpr int kStack = 128;  // the shader's private stack is 1024 deep (raytracer.glsl:251)
+constexpr int kStack = 128;       // lane stack of the fast kernels
+constexpr int kStackDeep = 1024;  // the shader's own: `const uint STACK_SIZE = 1024` (raytracer.glsl:251), RTR_TRACE_DEEP_STACK
 constexpr int kTraceBlock = 128;
 
 struct Ray {
@@ -225,9 +226,10 @@ __device__ __forceinline__ float prune_limit(const PruneBound& pb, float t_best)
 }
 
 // ---- the shader's own loop (raytracer.glsl:246-295): RTR_TRACE_REFERENCE_ORDER ----
+template <int STACK = kStack>
 __device__ __forceinline__ Hit closest_hit_reference(const Ray& r, const Accel& A, uint32_t* overflow) {
     Hit best = no_hit();
-    uint32_t stack[kStack];
+    uint32_t stack[STACK];
     int sp = 0;
     stack[sp++] = 0u;
     while (sp > 0) {
@@ -240,7 +242,7 @@ __device__ __forceinline__ Hit closest_hit_reference(const Ray& r, const Accel& 
             if (ray_triangle(r, A.wtri, slot_of(A, n.links), n.links.x, h)) {
                 if (best.did_hit == 0u || h.t < best.t) best = h;
             }
-        } else if (sp + 2 <= kStack) {
+        } else if (sp + 2 <= STACK) {
             stack[sp++] = n.links.y;
             stack[sp++] = n.links.z;
         } else {
@@ -249,8 +251,9 @@ __device__ __forceinline__ Hit closest_hit_reference(const Ray& r, const Accel& 
     }
     return best;
 }
+template <int STACK = kStack>
 __device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, const Accel& A, uint32_t* overflow) {
-    uint32_t stack[kStack];
+    uint32_t stack[STACK];
     int sp = 0;
     stack[sp++] = 0u;
     while (sp > 0) {
@@ -261,7 +264,7 @@ __device__ __forceinline__ bool any_hit_reference(const Ray& r, float t_max, con
         if (is_leaf(n.links)) {
             Hit h;
             if (ray_triangle(r, A.wtri, slot_of(A, n.links), n.links.x, h) && h.t < t_max) return true;
-        } else if (sp + 2 <= kStack) {
+        } else if (sp + 2 <= STACK) {
             stack[sp++] = n.links.y;
             stack[sp++] = n.links.z;
         } else {
@@ -331,15 +334,19 @@ __device__ __forceinline__ Hit trace_ordered(const Ray& r, float t_max, const Ac
     return best;
 }
 
-template <bool PRUNE>
+// MODE 0: the shader's loop with the 128-entry stack; 1: front-to-back with pruning (one thread per ray; the default
+// order itself runs in trace_persistent_kernel); 2: the shader's loop with the shader's own 1024-entry stack
+template <int MODE>
 __device__ __forceinline__ Hit closest_hit(const Ray& r, const Accel& A, const PruneBound& pb, uint32_t* overflow) {
-    if (PRUNE) return trace_ordered<false>(r, INFINITY, A, pb, overflow);
-    return closest_hit_reference(r, A, overflow);
+    if (MODE == 1) return trace_ordered<false>(r, INFINITY, A, pb, overflow);
+    if (MODE == 2) return closest_hit_reference<kStackDeep>(r, A, overflow);
+    return closest_hit_reference<kStack>(r, A, overflow);
 }
-template <bool PRUNE>
+template <int MODE>
 __device__ __forceinline__ bool any_hit(const Ray& r, float t_max, const Accel& A, const PruneBound& pb, uint32_t* overflow) {
-    if (PRUNE) return trace_ordered<true>(r, t_max, A, pb, overflow).did_hit != 0u;
-    return any_hit_reference(r, t_max, A, overflow);
+    if (MODE == 1) return trace_ordered<true>(r, t_max, A, pb, overflow).did_hit != 0u;
+    if (MODE == 2) return any_hit_reference<kStackDeep>(r, t_max, A, overflow);
+    return any_hit_reference<kStack>(r, t_max, A, overflow);
 }
 
 __device__ __forceinline__ void store_hit(rtr_hit* __restrict__ out, size_t i, const Hit& h) {
@@ -397,7 +404,7 @@ __device__ __forceinline__ bool pixel_of_thread(uint32_t width, uint32_t rows, u
     return x < width && y_local < rows;
 }
 
-template <bool PRUNE>
+template <int PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
 trace_primary_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
                      uint32_t width, uint32_t denom_w, uint32_t denom_h, uint32_t row0, uint32_t rows,
@@ -407,7 +414,7 @@ trace_primary_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_came
     const uint32_t y = row0 + yl;
     Hit h = no_hit();
     if (x < denom_w && y < denom_h) {
-        const PruneBound pb = make_prune_bound(tp, PRUNE);
+        const PruneBound pb = make_prune_bound(tp, PRUNE == 1);
         const Ray r = camera_ray(cam, x, y, denom_w, denom_h);
         uint32_t ovf = 0;
         h = closest_hit<PRUNE>(r, A, pb, &ovf);
@@ -416,7 +423,7 @@ trace_primary_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_came
     store_hit(hits, (size_t)yl * width + x, h);
 }
 
-template <bool PRUNE>
+template <int PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
 trace_rays_kernel(const Accel A, TraceParams* __restrict__ tp,
                   const rtr_ray* __restrict__ rays, uint64_t n_rays, int want_any, const float* __restrict__ t_max,
@@ -426,7 +433,7 @@ trace_rays_kernel(const Accel A, TraceParams* __restrict__ tp,
     const float4 o = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i);
     const float4 d = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
     const Ray r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
-    const PruneBound pb = make_prune_bound(tp, PRUNE);
+    const PruneBound pb = make_prune_bound(tp, PRUNE == 1);
     Hit h = no_hit();
     uint32_t ovf = 0;
     if (want_any) {
@@ -440,7 +447,7 @@ trace_rays_kernel(const Accel A, TraceParams* __restrict__ tp,
 }
 
 // Multi-bounce frame, one thread per pixel (definition: oracle/rtr_oracle.c orc_render).
-template <bool PRUNE>
+template <int PRUNE>
 __global__ void __launch_bounds__(kTraceBlock)
 render_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
               uint32_t width, uint32_t denom_w, uint32_t denom_h, const RowMap rm,
@@ -453,7 +460,7 @@ render_kernel(const Accel A, TraceParams* __restrict__ tp, const rtr_camera cam,
         float L = 0.f, wgt = 1.f;
         Hit first = no_hit();
         if (x < denom_w && y < denom_h) {
-            const PruneBound pb = make_prune_bound(tp, PRUNE);
+            const PruneBound pb = make_prune_bound(tp, PRUNE == 1);
             Ray r = camera_ray(cam, x, y, denom_w, denom_h);
             uint32_t ovf = 0;
             for (uint32_t k = 0; k <= bounces; ++k) {
@@ -575,6 +582,7 @@ struct JobDesc {
     float lx, ly, lz;
     float4* rgba;
     rtr_hit* hits;
+    uint32_t sbw, sbh;  // 8x4-pixel job tiles are dealt in super-blocks of sbw x sbh tiles (0: plain row-major order)
     // rays
     const rtr_ray* rays;
     const float* t_max;
@@ -735,8 +743,17 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     auto job_pixel = [&](uint32_t j, uint32_t& x, uint32_t& y, uint32_t& out_row) -> bool {
         const uint32_t tiles_x = (jd.width + 7u) / 8u;
         const uint32_t wg = j >> 5, ln = j & 31u;
-        x = (wg % tiles_x) * 8u + (ln & 7u);
-        const uint32_t yl = (wg / tiles_x) * 4u + (ln >> 3);
+        uint32_t tx, ty;
+        if (jd.sbw == 0u) { tx = wg % tiles_x; ty = wg / tiles_x; }
+        else {  // super-blocks: the warps in flight at one time cover a compact part of the image (L2 locality)
+            const uint32_t per = jd.sbw * jd.sbh, blocks_x = (tiles_x + jd.sbw - 1u) / jd.sbw;
+            const uint32_t blk = wg / per, in = wg % per;
+            tx = (blk % blocks_x) * jd.sbw + in % jd.sbw;
+            ty = (blk / blocks_x) * jd.sbh + in / jd.sbw;
+            if (tx >= tiles_x) return false;
+        }
+        x = tx * 8u + (ln & 7u);
+        const uint32_t yl = ty * 4u + (ln >> 3);
         return x < jd.width && yl < jd.rm.rows && map_row(jd.rm, yl, y, out_row);
     };
 
@@ -1151,7 +1168,14 @@ static JobDesc pixel_jobs(const rtr_camera& cam, uint32_t width, uint32_t denom_
     jd.bounces = bounces; jd.shadow = shadow;
     jd.lx = light ? light[0] : 0.f; jd.ly = light ? light[1] : 0.f; jd.lz = light ? light[2] : 0.f;
     jd.rgba = reinterpret_cast<float4*>(rgba); jd.hits = hits;
-    jd.total = ((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u;
+    const uint32_t tiles_x = (width + 7) / 8, tiles_y = (rm.rows + 3) / 4;
+    jd.sbw = jd.sbh = 0u;
+    jd.total = tiles_x * tiles_y * 32u;
+    static const int sb = [] { const char* e = getenv("RTR_TILE_BLOCK"); return e ? atoi(e) : 0; }();  // experiment knob
+    if (sb > 0) {
+        jd.sbw = (uint32_t)sb; jd.sbh = (uint32_t)sb * 2u;   // sb x 2sb tiles = 8sb x 8sb pixels
+        jd.total = ((tiles_x + jd.sbw - 1) / jd.sbw) * ((tiles_y + jd.sbh - 1) / jd.sbh) * jd.sbw * jd.sbh * 32u;
+    }
     return jd;
 }
 
@@ -1167,9 +1191,13 @@ int rtr_trace_primary_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& c
     if ((uint64_t)((width + 7) / 8) * ((rows + 3) / 4) * 32u >= 0xFFFFFF00ull)
         return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_primary: image too large");
     RTR_PROF(ctx, "trace_primary_kernel");
-    if (flags & RTR_TRACE_REFERENCE_ORDER) {
-        trace_primary_kernel<false><<<pixel_grid(width, rows), kTraceBlock, 0, ctx->stream>>>(
-            accel_of(b), b->tparams, cam, width, denom_w, denom_h, row0, rows, hits);
+    if (flags & (RTR_TRACE_REFERENCE_ORDER | RTR_TRACE_DEEP_STACK)) {
+        if (flags & RTR_TRACE_DEEP_STACK)
+            trace_primary_kernel<2><<<pixel_grid(width, rows), kTraceBlock, 0, ctx->stream>>>(
+                accel_of(b), b->tparams, cam, width, denom_w, denom_h, row0, rows, hits);
+        else
+            trace_primary_kernel<0><<<pixel_grid(width, rows), kTraceBlock, 0, ctx->stream>>>(
+                accel_of(b), b->tparams, cam, width, denom_w, denom_h, row0, rows, hits);
         RTR_LAUNCH_CHECK(ctx);
         return RTR_OK;
     }
@@ -1183,9 +1211,12 @@ int rtr_trace_rays_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_ray* rays, u
     if (n_rays == 0) return RTR_OK;
     if (n_rays >= 0xFFFFFF00ull) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "trace_rays: too many rays");
     RTR_PROF(ctx, "trace_rays_kernel");
-    if (flags & RTR_TRACE_REFERENCE_ORDER) {
+    if (flags & (RTR_TRACE_REFERENCE_ORDER | RTR_TRACE_DEEP_STACK)) {
         const uint32_t grid = (uint32_t)((n_rays + kTraceBlock - 1) / kTraceBlock);
-        trace_rays_kernel<false><<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, rays, n_rays, any, t_max, hits);
+        if (flags & RTR_TRACE_DEEP_STACK)
+            trace_rays_kernel<2><<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, rays, n_rays, any, t_max, hits);
+        else
+            trace_rays_kernel<0><<<grid, kTraceBlock, 0, ctx->stream>>>(accel_of(b), b->tparams, rays, n_rays, any, t_max, hits);
         RTR_LAUNCH_CHECK(ctx);
         return RTR_OK;
     }
@@ -1230,11 +1261,16 @@ int rtr_render_launch(rtr_ctx* ctx, const rtr_bvh* b, const rtr_camera& cam, uin
     if ((uint64_t)((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u >= 0xFFFFFF00ull)
         return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "render: image too large");
     RTR_PROF(ctx, "render_kernel");
-    if (flags & RTR_TRACE_REFERENCE_ORDER) {
+    if (flags & (RTR_TRACE_REFERENCE_ORDER | RTR_TRACE_DEEP_STACK)) {
         const float lx = light ? light[0] : 0.f, ly = light ? light[1] : 0.f, lz = light ? light[2] : 0.f;
-        render_kernel<false><<<pixel_grid(width, rm.rows), kTraceBlock, 0, ctx->stream>>>(
-            accel_of(b), b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
-            reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+        if (flags & RTR_TRACE_DEEP_STACK)
+            render_kernel<2><<<pixel_grid(width, rm.rows), kTraceBlock, 0, ctx->stream>>>(
+                accel_of(b), b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
+                reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
+        else
+            render_kernel<0><<<pixel_grid(width, rm.rows), kTraceBlock, 0, ctx->stream>>>(
+                accel_of(b), b->tparams, cam, width, denom_w, denom_h, rm, bounces, shadow, lx, ly, lz,
+                reinterpret_cast<float4*>(rgba), hits, reinterpret_cast<unsigned long long*>(rays));
         RTR_LAUNCH_CHECK(ctx);
         return RTR_OK;
     }

@@ -321,23 +321,27 @@ def test_tiny_trees_through_the_wide_step(ctx, oracle, n):
         bvh.close()
 
 
-def test_long_directions_are_refused_in_the_default_order(ctx):
-    """The pruning margin is derived for the shader's unit directions (tests/test_prune_bound_cpu.py): rtr_trace_rays
-    refuses |d| > 8 unless the by-the-letter order is asked for."""
+def test_long_directions_take_the_shaders_order(ctx, oracle):
+    """The pruning margin is derived for the shader's unit directions (tests/test_prune_bound_cpu.py): a batch of
+    rtr_trace_rays that holds a direction longer than 8 is traced in the by-the-letter order instead (any length, same
+    records, no pruning)."""
     tris, meshes, L = scenes.soup(2000)
     bvh = capi.Bvh(ctx).build(tris, meshes)
     try:
-        rays = np.zeros(64, dtype=RAY)
+        flat = bvh.flat_nodes()
+        rng = np.random.default_rng(11)
+        rays = np.zeros(256, dtype=RAY)
+        rays["o"][:, :3] = rng.uniform(-0.4 * L, 0.4 * L, (rays.size, 3)).astype(np.float32)
         rays["o"][:, 2] = -2.0 * L
         rays["o"][:, 3] = 1.0
-        rays["d"][:, 2] = 1.0
-        rays["d"][5, :3] = (0.0, 30.0, 40.0)
-        with pytest.raises(capi.RtrError) as e:
-            bvh.trace_rays(rays)
-        assert e.value.code == -5 and "ray 5" in str(e.value)
-        assert bvh.trace_rays(rays, flags=capi.TRACE_REFERENCE_ORDER).size == 64
-        rays["d"][5, :3] = (0.0, 3.0, 4.0)
-        assert bvh.trace_rays(rays).size == 64
+        rays["d"][:, :3] = (rng.normal(size=(rays.size, 3)) * 0.05 + (0.0, 0.0, 1.0)).astype(np.float32)
+        rays["d"][5, :3] *= 50.0                                   # |d| ~ 50
+        got = bvh.trace_rays(rays)
+        exp = oracle.trace_rays(flat, tris, meshes, rays)
+        assert exp["did_hit"].sum() > 20
+        assert_hits_equal(got, exp, "long direction in the batch")
+        rays["d"][5, :3] /= 50.0
+        assert_hits_equal(bvh.trace_rays(rays), oracle.trace_rays(flat, tris, meshes, rays), "unit-ish directions")
     finally:
         bvh.close()
 
@@ -368,9 +372,10 @@ def _chain_scene(n):
 
 
 def test_stack_overflow_is_never_silent(ctx, oracle):
-    """A chain deeper than the 128-entry lane stack (the shader's own stack holds 1024, raytracer.glsl:251): every
-    entry point either returns the oracle's record or refuses -- explicit ray batches and any-hit rays included."""
-    deep, shallow = _chain_scene(300), _chain_scene(100)
+    """Chains deeper than the 128-entry lane stack.  The shader's own stack holds 1024 entries (raytracer.glsl:251):
+    up to that depth the host-pointer calls return the oracle's records -- they fall back to RTR_TRACE_DEEP_STACK, the
+    shader's loop with the shader's stack -- and beyond it (where the shader itself writes out of bounds) they refuse;
+    explicit ray batches and any-hit rays included.  The asynchronous forms report the count."""
     rays = np.zeros(64, dtype=RAY)
     rays["o"][:, :3] = (0.05, -0.1, -10.0); rays["o"][:, 3] = 1.0
     rays["d"][:, :3] = (0.001, 0.002, 1.0)
@@ -381,31 +386,34 @@ def test_stack_overflow_is_never_silent(ctx, oracle):
     miss["o"][:, :3] = (0.9, 0.9, -10.0)
     miss["d"][:, :3] = (0.0001, 0.0001, 1.0)
     miss["d"][:, :3] /= np.linalg.norm(miss["d"][0, :3])
-    for (tris, meshes, flat), fits in ((shallow, True), (deep, False)):
+    for depth, outcome in ((100, "fits"), (300, "deep stack"), (1300, "refused")):
+        tris, meshes, flat = _chain_scene(depth)
         d_nodes, d_tris, d_meshes = ctx.dev_alloc(flat.nbytes), ctx.dev_alloc(tris.nbytes), ctx.dev_alloc(meshes.nbytes)
         ctx.upload(d_nodes, flat); ctx.upload(d_tris, tris); ctx.upload(d_meshes, meshes)
         bvh = capi.Bvh(ctx).adopt_dev(d_nodes, tris.size, d_tris, d_meshes, meshes.size)
         try:
-            exp = oracle.trace_rays(flat, tris, meshes, rays)
-            assert exp["did_hit"].all() and (exp["tri"] == tris.size - 1).all()        # the nearest triangle, z = 0
-            assert not oracle.trace_rays(flat, tris, meshes, miss)["did_hit"].any()
-            for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER):
+            if outcome != "refused":   # the oracle's stack is the shader's: 1024 entries
+                exp = oracle.trace_rays(flat, tris, meshes, rays)
+                assert exp["did_hit"].all() and (exp["tri"] == tris.size - 1).all()        # the nearest triangle, z = 0
+                assert not oracle.trace_rays(flat, tris, meshes, miss)["did_hit"].any()
+            for flags in (capi.TRACE_DEFAULT, capi.TRACE_REFERENCE_ORDER, capi.TRACE_DEEP_STACK):
                 for any_hit in (False, True):
                     batch = miss if any_hit else rays
-                    if fits:
-                        got = bvh.trace_rays(batch, any_hit=any_hit, flags=flags)
-                        if any_hit: assert not got["did_hit"].any()
-                        else: assert_hits_equal(got, exp, "chain of 100")
-                    else:
+                    if outcome == "refused":
                         with pytest.raises(capi.RtrError) as e:
                             bvh.trace_rays(batch, any_hit=any_hit, flags=flags)
-                        assert e.value.code == -5, (flags, any_hit, str(e.value))      # RTR_E_UNSUPPORTED
-            if not fits:
-                d_rays, d_hits = ctx.dev_alloc(rays.nbytes), ctx.dev_alloc(rays.size * 24)
-                ctx.upload(d_rays, rays)
-                bvh.trace_rays_dev(d_rays, rays.size, d_hits)
-                assert bvh.stack_overflows() == rays.size
-                ctx.dev_free(d_rays); ctx.dev_free(d_hits)
+                        assert e.value.code == -5 and "1024" in str(e.value), (flags, any_hit, str(e.value))   # RTR_E_UNSUPPORTED
+                    else:
+                        got = bvh.trace_rays(batch, any_hit=any_hit, flags=flags)
+                        if any_hit: assert not got["did_hit"].any()
+                        else: assert_hits_equal(got, exp, "chain of %d, flags %d" % (depth, flags))
+            d_rays, d_hits = ctx.dev_alloc(rays.nbytes), ctx.dev_alloc(rays.size * 24)
+            ctx.upload(d_rays, rays)
+            bvh.trace_rays_dev(d_rays, rays.size, d_hits)
+            assert bvh.stack_overflows() == (0 if outcome == "fits" else rays.size)
+            bvh.trace_rays_dev(d_rays, rays.size, d_hits, flags=capi.TRACE_DEEP_STACK)
+            assert bvh.stack_overflows() == (rays.size if outcome == "refused" else 0)
+            ctx.dev_free(d_rays); ctx.dev_free(d_hits)
         finally:
             bvh.close()
             ctx.dev_free(d_nodes); ctx.dev_free(d_tris); ctx.dev_free(d_meshes)
