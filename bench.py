@@ -64,6 +64,9 @@ def parse_args():
     p.add_argument("--reference-order", action="store_true", help="trace in the shader's exact visiting order (no pruning)")
     p.add_argument("--reserve-sms", type=int, default=0,
                    help="N>1: SMs the traversal leaves free for the NCCL kernels of the broadcast in flight")
+    p.add_argument("--partition", action="store_true",
+                   help="N>1, experimental: rays in a green-context SM partition, two frames in flight (slower in the full pipeline "
+                        "on this box: the exchange chain, not the rays, sets the frame time; DESIGN.md section 7)")
     p.add_argument("--no-pipeline", action="store_true", help="N>1: rebuild, broadcast, render and gather strictly in sequence")
     p.add_argument("--record-hash", action="store_true", help="N=1: store this frame's digest in profiles/image_hashes.json")
     return p.parse_args()
@@ -269,6 +272,9 @@ ALGO_BYTES = {  # algorithmic HBM bytes per launch as a function of (n triangles
 
 def main():
     args = parse_args()
+    if os.environ.get("RTR_BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack and quit after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["RTR_BENCH_WATCHDOG"]), exit=True)
     if args.bounces is None:
         args.bounces = 2 if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) == 1 else 4
     if args.impl == "reference":
@@ -291,7 +297,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if args.reserve_sms <= 0:
-        args.reserve_sms = 8 if world <= 2 else 16   # whole SMs are vacated for NCCL (rtr_ctx_reserve_sms); 16 channels move the broadcast to 7 peers in 3.3 ms
+        # SMs left to NCCL: the rays run in a green-context partition of the other SMs (a multiple of 8 on sm_100, so
+        # 136 + 12), or -- without the partition -- vacate whole SMs (rtr_ctx_reserve_sms)
+        args.reserve_sms = 12 if args.partition else (8 if world <= 2 else 16)
     if world > 1:
         if not args.no_pipeline:
             # the broadcast of the next frame's BVH runs beside the rays of the current one on --reserve-sms SMs:
@@ -415,7 +423,6 @@ def main():
         released = [torch.cuda.Event() for _ in range(NB)]    # the rays of the frame that used BVH k are done
         sent = [torch.cuda.Event() for _ in range(NB)]        # rank 0: BVH k has left (it may be rebuilt)
         last_built = [None]
-        ctx.reserve_sms(args.reserve_sms)
 
         # e2e arm, host traffic SHARDED over the ranks' own PCIe links: every rank uploads its slice of the frame's
         # triangles (rtr_dev_upload_async), the slices are assembled on rank 0 over NVLink (rtr_gather_slices), and every
@@ -438,9 +445,21 @@ def main():
         x_meshes_pinned = torch.from_numpy(meshes_np.view(np.uint8).copy()).pin_memory() if rank == 0 else None
         x_up_done, x_slice_free, x_tris_ready, x_tris_free, x_frame_done, x_img_free, x_img_done = (
             [torch.cuda.Event(), torch.cuda.Event()] for _ in range(7))
-        # one stream for the rays of all frames: two persistent launches in flight at once would feed the later one's
-        # CTAs, as slots free up, into the SMs the earlier one vacated for NCCL -- where they leave at once
-        streams_r = [stream_r, stream_r]
+        # The rays of consecutive frames go to two streams of a green-context partition of all SMs but the ones left to
+        # NCCL: frame f+1's persistent launch fills in as the last, longest paths of frame f finish (about 0.7 ms of
+        # every launch), and NCCL's kernels always find free SMs.  (Without the partition: one stream -- two launches
+        # in flight would feed the later one's CTAs into the SMs the earlier one vacated for NCCL, where they leave.)
+        rays_sms = 0
+        if not args.partition:
+            streams_r = [stream_r, stream_r]
+            ctx.reserve_sms(args.reserve_sms)
+        else:
+            handles, rays_sms = ctx.partition_sms(ctx.sm_count - args.reserve_sms, 2)
+            streams_r = [torch.cuda.ExternalStream(h, device=dev) for h in handles]
+            if os.environ.get("RTR_BENCH_ONE_RAY_STREAM"):
+                streams_r[1] = streams_r[0]
+            # (launches on the partition's streams ignore this; the cooperative rebuild kernels leave these SMs alone)
+            ctx.reserve_sms(args.reserve_sms)
         stream.synchronize()
         marks = []
 
@@ -533,6 +552,16 @@ def main():
                 ctx.download_stripes_async(x_host_img[j].ctypes.data, img.data_ptr(), W, H, 16, rpb, layout)
                 x_img_free[j].record(x_out)
                 ctx.switch_stream(sr.cuda_stream)
+            elif args.partition:
+                # NCCL kernels do not belong into the rays' partition: the frame is gathered on rank 0 by the
+                # communicator's stream, issued by every rank at the same place of the schedule (after exchange(f+1))
+                x_frame_done[j].record(sr)
+                ctx.switch_stream(stream_b.cuda_stream)
+                stream_b.wait_event(x_frame_done[j])
+                ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
+                x_img_done[j].record(stream_b)
+                mark("gather", f, stream_b)
+                ctx.switch_stream(sr.cuda_stream)
             else:
                 ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
                 x_img_done[j].record(sr)
@@ -562,7 +591,7 @@ def main():
                 submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
-            barrier(); stream_a.synchronize(); stream_b.synchronize(); streams_r[1].synchronize()
+            barrier(); stream_a.synchronize(); stream_b.synchronize(); streams_r[0].synchronize(); streams_r[1].synchronize()
             del marks[:]
             with torch.cuda.stream(stream_r):
                 d_rays.zero_()
@@ -570,14 +599,14 @@ def main():
             launches0 = ctx.launch_count
             stream_r.synchronize()
             e0.record(stream_r)
-            for st in (stream_a, stream_b, x_in, streams_r[1]):
+            for st in (stream_a, stream_b, x_in, streams_r[0], streams_r[1]):
                 st.wait_event(e0)            # nothing of the region starts before it
             run_pipelined(steps, e2e)
-            for st in (stream_a, stream_b, x_out, streams_r[1]):
+            for st in (stream_a, stream_b, x_out, streams_r[0], streams_r[1]):
                 stream_r.wait_stream(st)
             e1.record(stream_r)
             barrier()
-            for st in (stream_a, stream_b, x_in, x_out, streams_r[1]):
+            for st in (stream_a, stream_b, x_in, x_out, streams_r[0], streams_r[1]):
                 st.synchronize()
             ctx.switch_stream(stream_r.cuda_stream)
             if marks:  # RTR_BENCH_TRACE=1: when each phase of each frame ended, ms after the start of the timed region
@@ -610,14 +639,47 @@ def main():
         phases = {"rebuild_ms": serial_ms, "broadcast_ms": bcast_ms, "full_frame_rays_ms_one_gpu": render_ms,
                   "gather_ms": gather_ms, "stripes_of_rank": layout}
         barrier()
+        if args.partition:
+            # First launch inside the green context, with nothing else in flight: loading the kernel into a new context
+            # synchronises the device, which must not happen later beside an NCCL kernel that waits for a peer.
+            for sr in set(streams_r):
+                ctx.switch_stream(sr.cuda_stream)
+                bvh.render_stripes_dev(cam, W, H, d_rgba.data_ptr(), rpb, [1] * world, rank, bounces=0, flags=flags)
+                sr.synchronize()
+            ctx.switch_stream(stream.cuda_stream)
+            barrier()
+
+    def progress(what):
+        if os.environ.get("RTR_BENCH_WATCHDOG"):
+            sys.stderr.write("[rank %d] %s\n" % (rank, what)); sys.stderr.flush()
+
+    if os.environ.get("RTR_BENCH_WATCHDOG") and pipelined:
+        def report():   # which streams still hold work, which events have fired, shortly before the watchdog quits
+            time.sleep(float(os.environ["RTR_BENCH_WATCHDOG"]) - 5.0)
+            names = {"main": stream, "A(build)": stream_a, "B(comm)": stream_b, "x_in": x_in, "x_out": x_out,
+                     "rays0": streams_r[0], "rays1": streams_r[1]}
+            busy = [k for k, st in names.items() if not st.query()]
+            evs = {"built": built, "ready": ready, "released": released, "sent": sent, "frame_done": x_frame_done, "img_done": x_img_done}
+            def q(e):
+                try:
+                    return "1" if e.query() else "0"
+                except Exception:
+                    return "?"
+            sys.stderr.write("[rank %d] busy streams: %s | events %s\n" % (
+                rank, busy, {k: "".join(q(e) for e in v) for k, v in evs.items()}))
+            sys.stderr.flush()
+        threading.Thread(target=report, daemon=True).start()
 
     # ---- warm-up, then the timed region ----
+    progress("setup done")
     sampler = ClockSampler(local_rank)
     if pipelined:
         run_pipelined(max(3, args.warmup), False)
+        progress("warm-up submitted")
         if rank == 0:
             sampler.start()
         ms, rays, launches = timed_pipelined(args.steps, False)
+        progress("timed region done")
     else:
         for _ in range(max(3, args.warmup)):
             frame_device()
@@ -642,7 +704,9 @@ def main():
                    "the rows it traced into one pinned host image shared by all ranks (rtr_download_stripes_async); the byte "
                    "counts are the totals over all ranks" % world)
         run_pipelined(2, True)
+        progress("e2e warm-up submitted")
         e2e_ms, e2e_rays, _ = timed_pipelined(e2e_steps, True)
+        progress("e2e region done")
     elif world == 1 and not args.no_pipeline:
         # Single GPU, double-buffered host traffic: the triangles of frame f+1 are uploaded (rtr_dev_upload_async,
         # pinned host memory, its own stream) while frame f is rebuilt and traced, and the image of frame f is
@@ -848,8 +912,8 @@ def main():
                        "rays_per_step": rays // args.steps, "search_radius": 16,
                        "trace_order": "reference" if args.reference_order else "pruned (identical records)",
                        "parallelism": ("build on rank 0 + NCCL broadcast + %d-row blocks dealt to %d rank(s)" % (rpb, world)) +
-                                      ((", frames pipelined (rebuild of f+2 | broadcast of f+1 | rays of f, gathered on rank 0), stripes per rank %s, %d SMs left to NCCL"
-                                        % (layout, args.reserve_sms)) if pipelined else ""),
+                                      ((", frames pipelined (rebuild of f+2 | broadcast of f+1 | rays of f, gathered on rank 0), stripes per rank %s, %d SMs left to NCCL%s"
+                                        % (layout, args.reserve_sms, (", rays in a green-context partition of %d SMs, two frames in flight" % rays_sms) if rays_sms else "")) if pipelined else ""),
                        "l2": "inputs larger than L2 (640 MB of triangles + 960 MB of nodes per step), no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

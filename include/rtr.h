@@ -114,6 +114,11 @@ int rtr_ctx_set_stream(rtr_ctx* ctx, void* stream); /* adopt a caller-owned cuda
 int rtr_ctx_switch_stream(rtr_ctx* ctx, void* cuda_stream);
 /* the persistent traversal kernel leaves `sms` SMs free, e.g. for the NCCL kernels of a broadcast in flight */
 int rtr_ctx_reserve_sms(rtr_ctx* ctx, uint32_t sms);
+/* An SM partition for the rays (a CUDA green context): `sms` SMs, rounded up to the granularity the architecture
+ * partitions by (8 on sm_90+; *sms_out gets the count), with n_streams (<= 8) streams of its own in streams_out.
+ * Traversal launches on those streams (rtr_ctx_switch_stream) fill the partition only, so several frames' rays can be
+ * in flight at once and the SMs outside it stay free for a concurrent collective.  Once per ctx. */
+int rtr_ctx_partition_sms(rtr_ctx* ctx, uint32_t sms, uint32_t n_streams, void** streams_out, uint32_t* sms_out);
 int rtr_ctx_device(const rtr_ctx* ctx);
 int rtr_ctx_sm_count(const rtr_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */

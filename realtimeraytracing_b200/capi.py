@@ -36,7 +36,7 @@ SYMBOLS = [
     "rtr_trace_primary", "rtr_trace_primary_dev", "rtr_trace_rays", "rtr_trace_rays_dev", "rtr_render",
     "rtr_render_dev", "rtr_render_sharded_dev", "rtr_ctx_profile_enable", "rtr_ctx_profile_read",
     "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_bvh_broadcast", "rtr_allgather_rows",
-    "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_bvh_broadcast_traversal",
+    "rtr_render_stripes_dev", "rtr_allgather_stripes", "rtr_ctx_switch_stream", "rtr_ctx_reserve_sms", "rtr_ctx_partition_sms", "rtr_bvh_broadcast_traversal",
     "rtr_dev_upload_async", "rtr_dev_download_async", "rtr_gather_stripes", "rtr_shade", "rtr_shade_dev",
     "rtr_gather_slices", "rtr_download_stripes_async",
     "rtr_bvh_build64", "rtr_bvh_build64_dev", "rtr_bvh_morton_codes64",
@@ -158,6 +158,7 @@ def load_library():
     L.rtr_bvh_depth_overlay_dev.argtypes = [vp, vp, vp, u32, u32, u32, u32, i32, vp]
     L.rtr_ctx_switch_stream.argtypes = [vp, vp]
     L.rtr_ctx_reserve_sms.argtypes = [vp, u32]
+    L.rtr_ctx_partition_sms.argtypes = [vp, u32, u32, vp, vp]
     f32 = C.c_float
     L.rtr_bvh_stack_overflows.argtypes = [vp, C.POINTER(u32)]
     L.rtr_camera_gpu_data.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp, vp, vp, vp]
@@ -495,6 +496,13 @@ class Context:
     def switch_stream(self, cuda_stream: int):
         """Enqueue later calls on `cuda_stream` without waiting for the work already enqueued (pipelined frames)."""
         self.check(self.lib.rtr_ctx_switch_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def partition_sms(self, sms: int, n_streams: int = 2):
+        """A green-context SM partition for the rays: returns (raw CUDA stream handles, SMs in the partition)."""
+        out = (C.c_void_p * n_streams)()
+        got = C.c_uint32(0)
+        self.check(self.lib.rtr_ctx_partition_sms(self.handle, sms, n_streams, out, C.byref(got)))
+        return [int(p) for p in out], got.value
 
     def reserve_sms(self, sms: int):
         self.check(self.lib.rtr_ctx_reserve_sms(self.handle, sms))

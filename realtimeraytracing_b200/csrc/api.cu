@@ -335,6 +335,63 @@ int rtr_ctx_reserve_sms(rtr_ctx* ctx, uint32_t sms) {
     ctx->reserved_sms = (int)sms;
     return RTR_OK;
 }
+// An SM partition for the rays: a green context (CUDA >= 12.4, driver API resolved through the runtime so the library
+// does not link libcuda) holding `sms` SMs -- rounded up to the granularity the architecture partitions by, 8 SMs on
+// sm_90+ -- with `n_streams` streams of its own.  Persistent traversal launches on those streams size themselves for
+// the partition, several of them may be in flight at once (the rays of frame f+1 fill in as the long paths of frame
+// f finish), and the SMs outside the partition stay free for the kernels of a concurrent collective.
+#include <cuda.h>
+int rtr_ctx_partition_sms(rtr_ctx* ctx, uint32_t sms, uint32_t n_streams, void** streams_out, uint32_t* sms_out) {
+    if (!ctx) return RTR_E_INVALID;
+    if (!streams_out || n_streams == 0 || n_streams > 8 || sms == 0 || (int)sms > ctx->sm_count)
+        return rtr_set_error(ctx, RTR_E_INVALID, "partition_sms: %u SMs, %u streams", sms, n_streams);
+    if (ctx->green_ctx) return rtr_set_error(ctx, RTR_E_STATE, "partition_sms: this ctx already has a partition");
+    RTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    typedef CUresult (*GetDevRes)(CUdevice, CUdevResource*, CUdevResourceType);
+    typedef CUresult (*SplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+    typedef CUresult (*GenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+    typedef CUresult (*GreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*GreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*DevGet)(CUdevice*, int);
+    GetDevRes get_res = nullptr; SplitByCount split = nullptr; GenDesc gen = nullptr; GreenCreate create = nullptr;
+    GreenStream mkstream = nullptr; DevGet dev_get = nullptr;
+    struct { const char* name; void** fn; } syms[] = {
+        {"cuDeviceGetDevResource", (void**)&get_res}, {"cuDevSmResourceSplitByCount", (void**)&split},
+        {"cuDevResourceGenerateDesc", (void**)&gen}, {"cuGreenCtxCreate", (void**)&create},
+        {"cuGreenCtxStreamCreate", (void**)&mkstream}, {"cuDeviceGet", (void**)&dev_get}};
+    for (auto& sy : syms) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(sy.name, sy.fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*sy.fn)
+            return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "partition_sms: the driver has no %s (green contexts need CUDA >= 12.4)", sy.name);
+    }
+#define RTR_CU(call)                                                                                               \
+    do {                                                                                                           \
+        CUresult _r = (call);                                                                                      \
+        if (_r != CUDA_SUCCESS) return rtr_set_error(ctx, RTR_E_CUDA, "partition_sms: %s -> CUresult %d", #call, (int)_r); \
+    } while (0)
+    CUdevice dev;
+    RTR_CU(dev_get(&dev, ctx->device));
+    CUdevResource all, part, rest;
+    RTR_CU(get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    unsigned int groups = 1;
+    RTR_CU(split(&part, &groups, &all, &rest, 0, sms));
+    if (groups != 1) return rtr_set_error(ctx, RTR_E_UNSUPPORTED, "partition_sms: cannot carve %u SMs out of %u", sms, all.sm.smCount);
+    CUdevResourceDesc desc;
+    RTR_CU(gen(&desc, &part, 1));
+    CUgreenCtx g;
+    RTR_CU(create(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    ctx->green_ctx = g;
+    ctx->partition_sms = (int)part.sm.smCount;
+    for (uint32_t i = 0; i < n_streams; ++i) {
+        CUstream st;
+        RTR_CU(mkstream(&st, g, CU_STREAM_NON_BLOCKING, 0));
+        ctx->partition_streams.push_back(reinterpret_cast<cudaStream_t>(st));
+        streams_out[i] = st;
+    }
+#undef RTR_CU
+    if (sms_out) *sms_out = part.sm.smCount;
+    return RTR_OK;
+}
 int rtr_ctx_device(const rtr_ctx* ctx) { return ctx ? ctx->device : -1; }
 int rtr_ctx_sm_count(const rtr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t rtr_ctx_launch_count(const rtr_ctx* ctx) { return ctx ? ctx->launches : 0; }

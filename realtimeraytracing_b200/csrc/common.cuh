@@ -25,6 +25,10 @@ struct rtr_ctx {
     uint32_t sm_table_turn = 0;
     int ploc_ctas_per_sm[2] = {0, 0};  // persistent PLOC loop kernel (full radius / masked radius), resident CTAs per SM
     int flatten_ctas_per_sm = 0;
+    // SM partition for the rays (rtr_ctx_partition_sms): a green context and its streams
+    void* green_ctx = nullptr;
+    int partition_sms = 0;
+    std::vector<cudaStream_t> partition_streams;
     int trace_ctas_per_sm = 0;     // resident CTAs per SM of the persistent traversal kernel on this device (0: not asked yet)
     cudaStream_t stream = nullptr;
     bool owns_stream = true;

@@ -1134,10 +1134,15 @@ int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_
     }
     const int ctas_per_sm = ctx->trace_ctas_per_sm;
     const uint32_t need = (jd.total + kTraceBlock - 1) / kTraceBlock;
-    const uint32_t full = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    // a launch on a stream of the ctx's SM partition (rtr_ctx_partition_sms) fills the partition and nothing else
+    bool in_partition = false;
+    for (cudaStream_t st : ctx->partition_streams) in_partition = in_partition || st == ctx->stream;
+    const int sms = in_partition ? ctx->partition_sms : ctx->sm_count;
+    const int keep_free = in_partition ? 0 : ctx->reserved_sms;
+    const uint32_t full = (uint32_t)(sms * ctas_per_sm);
     uint32_t grid = full, reserve = 0u;
-    if (need <= (uint32_t)((ctx->sm_count - ctx->reserved_sms) * ctas_per_sm)) grid = need;  // small job: room is left anyway
-    else reserve = (uint32_t)ctx->reserved_sms;
+    if (need <= (uint32_t)((sms - keep_free) * ctas_per_sm)) grid = need;  // small job: room is left anyway
+    else reserve = (uint32_t)keep_free;
     if (grid == 0) return RTR_OK;
     uint32_t* table = nullptr;
     if (reserve != 0u) {  // two tables in turn: consecutive launches may run on different streams and overlap
