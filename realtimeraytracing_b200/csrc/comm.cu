@@ -22,6 +22,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId*);
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int);
     int (*CommDestroy)(NcclComm);
+    int (*CommAbort)(NcclComm);
     int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
     int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t);
     int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t);
@@ -50,6 +51,7 @@ int load_nccl(rtr_ctx* ctx) {
     RTR_SYM(GetUniqueId, "ncclGetUniqueId");
     RTR_SYM(CommInitRank, "ncclCommInitRank");
     RTR_SYM(CommDestroy, "ncclCommDestroy");
+    RTR_SYM(CommAbort, "ncclCommAbort");
     RTR_SYM(Broadcast, "ncclBroadcast");
     RTR_SYM(Send, "ncclSend");
     RTR_SYM(Recv, "ncclRecv");
@@ -68,6 +70,17 @@ int load_nccl(rtr_ctx* ctx) {
             return rtr_set_error((ctx), RTR_E_COMM, "%s:%d %s -> %s", __FILE__, __LINE__, #call,     \
                                  g_nccl.GetErrorString ? g_nccl.GetErrorString(_e) : "nccl error"); \
     } while (0)
+
+// A rank that finds, before it joins a collective, that it cannot take part (the root has no BVH to send, ...) must not
+// just return: its peers have enqueued their side and would wait forever.  The communicator is aborted instead, which
+// makes every rank's pending and later calls on it fail (RTR_E_COMM) -- the ranks fail together.
+int comm_fail(rtr_ctx* ctx, int code, const char* what) {
+    if (ctx->nccl_comm && ctx->nranks > 1 && g_nccl.CommAbort) {
+        g_nccl.CommAbort(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return rtr_set_error(ctx, code, "%s (the communicator was aborted so that the other ranks do not wait)", what);
+}
 
 // Inside ncclGroupStart/End an error must not return before the group is closed (the thread would stay in group
 // mode): RTR_NCCL_G remembers the first failure and carries on, rtr_group_end closes the group and reports it.
@@ -138,8 +151,8 @@ int rtr_bvh_broadcast(rtr_ctx* ctx, rtr_bvh** bvh, int root) {
     if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: rtr_comm_init has not been called");
     if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: bad root %d", root);
     const bool is_root = ctx->rank == root;
-    if (is_root && (!*bvh || !(*bvh)->built)) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
-    if (is_root && (*bvh)->trav_only) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: the root holds traversal records only");
+    if (is_root && (!*bvh || !(*bvh)->built)) return comm_fail(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
+    if (is_root && (*bvh)->trav_only) return comm_fail(ctx, RTR_E_STATE, "bvh_broadcast: the root holds traversal records only");
     NcclComm comm = ctx->nccl_comm;
 
     // 1. header: triangle and mesh counts
@@ -226,7 +239,7 @@ int rtr_bvh_broadcast_traversal(rtr_ctx* ctx, rtr_bvh** bvh, int root, uint32_t 
     if (!ctx->nccl_comm) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: rtr_comm_init has not been called");
     if (root < 0 || root >= ctx->nranks) return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: bad root %d", root);
     const bool is_root = ctx->rank == root;
-    if (is_root && (!*bvh || !(*bvh)->built)) return rtr_set_error(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
+    if (is_root && (!*bvh || !(*bvh)->built)) return comm_fail(ctx, RTR_E_STATE, "bvh_broadcast: root has no built BVH");
     NcclComm comm = ctx->nccl_comm;
 
     // 1. header: triangle count -- unless every rank already knows it (a frame loop over one scene): then no
@@ -246,7 +259,7 @@ int rtr_bvh_broadcast_traversal(rtr_ctx* ctx, rtr_bvh** bvh, int root, uint32_t 
         n = h_hdr[0];
         if (n == 0) return rtr_set_error(ctx, RTR_E_COMM, "bvh_broadcast: empty header from root");
     } else if (is_root && (*bvh)->n != n) {
-        return rtr_set_error(ctx, RTR_E_INVALID, "bvh_broadcast: the BVH has %u triangles, the ranks expect %u", (*bvh)->n, n);
+        return comm_fail(ctx, RTR_E_INVALID, "bvh_broadcast: the root's BVH does not have the triangle count the ranks expect");
     }
     const size_t nc = 2 * (size_t)n - 1;
 

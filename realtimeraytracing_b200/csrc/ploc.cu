@@ -493,7 +493,8 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& genera
         __threadfence();
         atomicAdd(counter, 1u);
         const uint32_t target = gridDim.x * generation;
-        while (ld_acquire_u32(counter) < target) __nanosleep(32);
+        uint32_t pause = 32u;  // hundreds of CTAs poll one word: back off so that the late arrivals' atomics get through
+        while (ld_acquire_u32(counter) < target) { __nanosleep(pause); pause = pause < 256u ? pause * 2u : 256u; }
         __threadfence();
     }
     __syncthreads();
@@ -542,6 +543,10 @@ ploc_loop_kernel(uint32_t n_leaves, int radius, uint32_t* __restrict__ buf0, uin
                 __syncthreads();
             }
         } else {
+            // (Tried: a second staging buffer filled by cp.async -- ids during the first block of the search, boxes during
+            //  the rest -- so that the two dependent gathers of the next tile hide behind the current search.  55 KB of
+            //  shared memory per CTA, three small LDGSTS per slot instead of one 256-bit load: 473 us instead of 344 us
+            //  for the first iteration, the loop 3.28 ms instead of 2.55 ms.  Reverted.)
             while (true) {
                 // tiles are handed out in start order (dynamic: a few per cent faster than static rounds on the large
                 // iterations), so the look-back only ever waits on tiles of running CTAs
@@ -840,16 +845,28 @@ pack_pairs_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint32_t
                   uint4* __restrict__ pairs, TraceParams* __restrict__ tparams) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_nodes) return;
+    const uint32_t nb_tris = (nb_nodes + 1u) / 2u;
     const uint4* me = reinterpret_cast<const uint4*>(flat + i);
     const uint4 m0 = __ldg(me), m1 = __ldg(me + 1), links = __ldg(me + 2);
     const float4 nlo = make_float4(__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z), __uint_as_float(m1.x));
     const float4 nhi = make_float4(__uint_as_float(m1.y), __uint_as_float(m1.z), 0.f, 0.f);
     if (links.y == 0u && links.z == 0u) {
         const uint32_t slot = by_rank ? links.w : links.x;
+        if (slot >= nb_tris || links.x >= nb_tris) {  // a foreign array naming a triangle that does not exist: never followed
+            atomicAdd(&tparams->bad_layout, 1u);
+            store_leaf_record(pairs, i, make_float4(INFINITY, INFINITY, INFINITY, -INFINITY), make_float4(-INFINITY, -INFINITY, 0.f, 0.f), wtri, 0u);
+            return;
+        }
         store_leaf_record(pairs, i, nlo, nhi, wtri + 3 * (size_t)slot, links.x);
         return;
     }
-    if (links.y != i + 1u) atomicAdd(&tparams->bad_layout, 1u);  // not the DFS pre-order of scene.cpp:189-208
+    // not the DFS pre-order of scene.cpp:189-208, or links that leave the array: counted (the call fails with
+    // RTR_E_UNSUPPORTED) and never followed
+    if (links.y != i + 1u || links.y >= nb_nodes || links.z >= nb_nodes || links.z <= i) {
+        atomicAdd(&tparams->bad_layout, 1u);
+        store_inner_record(pairs, i, make_uint4(0u, 0u, 0u, 4u << 24), make_uint4(0u, 0u, 0u, i));
+        return;
+    }
     const uint4* l = reinterpret_cast<const uint4*>(flat + links.y);
     const uint4* r = reinterpret_cast<const uint4*>(flat + links.z);
     const uint4 l0 = __ldg(l), l1 = __ldg(l + 1), l2 = __ldg(l + 2);
@@ -873,6 +890,7 @@ pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* _
     const uint4* me = reinterpret_cast<const uint4*>(flat + i);
     const uint4 links = __ldg(me + 2);
     if (links.y == 0u && links.z == 0u) return;
+    if (links.y >= nb_nodes || links.z >= nb_nodes) return;  // flagged by pack_pairs_kernel
     const uint4 m0 = __ldg(me), m1 = __ldg(me + 1);
     const uint32_t child[2] = {links.y, links.z};
     float4 lo[4];
@@ -890,6 +908,7 @@ pack_quads_kernel(const rtr_node* __restrict__ flat, uint32_t nb_nodes, uint4* _
             leaf_bits |= 3u << (2 * k);
         } else {
             const uint32_t g[2] = {c2.y, c2.z};
+            if (g[0] >= nb_nodes || g[1] >= nb_nodes) return;  // flagged by pack_pairs_kernel at the child
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const uint4* q = reinterpret_cast<const uint4*>(flat + g[j]);

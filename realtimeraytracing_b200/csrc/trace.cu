@@ -582,7 +582,6 @@ struct JobDesc {
     float lx, ly, lz;
     float4* rgba;
     rtr_hit* hits;
-    uint32_t sbw, sbh;  // 8x4-pixel job tiles are dealt in super-blocks of sbw x sbh tiles (0: plain row-major order)
     // rays
     const rtr_ray* rays;
     const float* t_max;
@@ -743,17 +742,10 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     auto job_pixel = [&](uint32_t j, uint32_t& x, uint32_t& y, uint32_t& out_row) -> bool {
         const uint32_t tiles_x = (jd.width + 7u) / 8u;
         const uint32_t wg = j >> 5, ln = j & 31u;
-        uint32_t tx, ty;
-        if (jd.sbw == 0u) { tx = wg % tiles_x; ty = wg / tiles_x; }
-        else {  // super-blocks: the warps in flight at one time cover a compact part of the image (L2 locality)
-            const uint32_t per = jd.sbw * jd.sbh, blocks_x = (tiles_x + jd.sbw - 1u) / jd.sbw;
-            const uint32_t blk = wg / per, in = wg % per;
-            tx = (blk % blocks_x) * jd.sbw + in % jd.sbw;
-            ty = (blk / blocks_x) * jd.sbh + in / jd.sbw;
-            if (tx >= tiles_x) return false;
-        }
-        x = tx * 8u + (ln & 7u);
-        const uint32_t yl = ty * 4u + (ln >> 3);
+        // (dealing the tiles in compact super-blocks of 16..128 pixels instead of row-major order was measured: +1..2 %
+        //  slower at 4K -- the rows of tiles in flight already share the upper tree, profiles/exp_r02_1.sh)
+        x = (wg % tiles_x) * 8u + (ln & 7u);
+        const uint32_t yl = (wg / tiles_x) * 4u + (ln >> 3);
         return x < jd.width && yl < jd.rm.rows && map_row(jd.rm, yl, y, out_row);
     };
 
@@ -1173,14 +1165,7 @@ static JobDesc pixel_jobs(const rtr_camera& cam, uint32_t width, uint32_t denom_
     jd.bounces = bounces; jd.shadow = shadow;
     jd.lx = light ? light[0] : 0.f; jd.ly = light ? light[1] : 0.f; jd.lz = light ? light[2] : 0.f;
     jd.rgba = reinterpret_cast<float4*>(rgba); jd.hits = hits;
-    const uint32_t tiles_x = (width + 7) / 8, tiles_y = (rm.rows + 3) / 4;
-    jd.sbw = jd.sbh = 0u;
-    jd.total = tiles_x * tiles_y * 32u;
-    static const int sb = [] { const char* e = getenv("RTR_TILE_BLOCK"); return e ? atoi(e) : 0; }();  // experiment knob
-    if (sb > 0) {
-        jd.sbw = (uint32_t)sb; jd.sbh = (uint32_t)sb * 2u;   // sb x 2sb tiles = 8sb x 8sb pixels
-        jd.total = ((tiles_x + jd.sbw - 1) / jd.sbw) * ((tiles_y + jd.sbh - 1) / jd.sbh) * jd.sbw * jd.sbh * 32u;
-    }
+    jd.total = ((width + 7) / 8) * ((rm.rows + 3) / 4) * 32u;
     return jd;
 }
 

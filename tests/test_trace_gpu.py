@@ -417,3 +417,44 @@ def test_stack_overflow_is_never_silent(ctx, oracle):
         finally:
             bvh.close()
             ctx.dev_free(d_nodes); ctx.dev_free(d_tris); ctx.dev_free(d_meshes)
+
+
+def test_malformed_adopted_arrays_are_refused_without_a_device_fault(ctx, oracle):
+    """rtr_bvh_adopt_dev on a foreign node array: links that leave the array or triangle ids that do not exist are
+    counted and never followed -- RTR_E_UNSUPPORTED, and the context stays usable (no sticky CUDA error)."""
+    tris, meshes, L = scenes.soup(500)
+    good = capi.Bvh(ctx).build(tris, meshes)
+    flat = good.flat_nodes()
+    good.close()
+    d_tris, d_meshes = ctx.dev_alloc(tris.nbytes), ctx.dev_alloc(meshes.nbytes)
+    ctx.upload(d_tris, tris); ctx.upload(d_meshes, meshes)
+    try:
+        for what in ("right link beyond the array", "left link beyond the array", "triangle id beyond the array", "right link backwards"):
+            bad = flat.copy()
+            inner = np.nonzero((bad["left"] != 0) | (bad["right"] != 0))[0]
+            leaves = np.nonzero((bad["left"] == 0) & (bad["right"] == 0))[0]
+            if what.startswith("right link beyond"):
+                bad["right"][inner[7]] = 0x7FFFFFF0
+            elif what.startswith("left"):
+                bad["left"][inner[3]] = 2 * tris.size + 5
+            elif what.startswith("triangle"):
+                bad["tri"][leaves[11]] = 0xFFFFFF00
+            else:
+                bad["right"][inner[9]] = 1
+            d_nodes = ctx.dev_alloc(bad.nbytes)
+            ctx.upload(d_nodes, bad)
+            with pytest.raises(capi.RtrError) as e:
+                capi.Bvh(ctx).adopt_dev(d_nodes, tris.size, d_tris, d_meshes, meshes.size)
+            assert e.value.code == -5, (what, str(e.value))
+            ctx.dev_free(d_nodes)
+        # the context is still healthy: the unmodified array adopts and traces like the build it came from
+        d_nodes = ctx.dev_alloc(flat.nbytes)
+        ctx.upload(d_nodes, flat)
+        bvh = capi.Bvh(ctx).adopt_dev(d_nodes, tris.size, d_tris, d_meshes, meshes.size)
+        W, H = 64, 48
+        cam = synth.soup_camera(L, W, H)
+        assert_hits_equal(bvh.trace_primary(cam, W, H, W, H), oracle.trace_primary(flat, tris, meshes, cam, W, H, W, H), "adopted")
+        bvh.close()
+        ctx.dev_free(d_nodes)
+    finally:
+        ctx.dev_free(d_tris); ctx.dev_free(d_meshes)
