@@ -888,6 +888,15 @@ def main():
         if tr_ms:
             extras["trace_only"] = {"ms_per_frame": tr_ms / 3, "mrays_s": tr_rays / (tr_ms * 1e-3) / 1e6,
                                     "rays_per_frame": tr_rays // 3}
+            # warp execution efficiency and L2 hit rate of the traversal kernel (north_star): not measurable inside a
+            # timed run, so they come from the committed ncu --set full capture of the same kernel on the same workload
+            try:
+                ev = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("trace_persistent_kernel_evidence")
+                if ev and (n, W, H, bounces) == (10_000_000, 3840, 2160, 2):
+                    extras["trace_only"].update({"warp_exec_eff": ev["warp_exec_eff"], "threads_per_inst": ev["threads_per_inst"],
+                                                 "l2_hit_rate": ev["l2_hit_rate"], "evidence": ev["source"]})
+            except Exception:
+                pass
 
     cpu_baseline = cpu_stages = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
