@@ -2,7 +2,12 @@
 // drawOneFrame (srcOpenGL/application.cpp:16-20, 176-186, 225-245) written against include/rtr_scene.hpp.
 //
 //   render_obj <model.obj> <out.ppm> [--size W H] [--scale s] [--rotate x y z] [--eye x y z] [--wireframe]
-//              [--bvh-depth d] [--dump-camera file] [--dump-rgba file]
+//              [--bvh-depth d] [--dump-camera file] [--dump-rgba file] [--frames n [--rebuild]]
+//
+// --frames n runs the reference's main loop n times first (mainLoop -> render -> drawOneFrame, application.cpp:220-313:
+// dispatch the shader, _FPS.increment(), the statistics every 10 frames) with the camera stepping forward like a held
+// W key (Camera::processKeyboard); --rebuild also rebuilds the BVH every frame, the call the reference keeps
+// commented out at application.cpp:224.
 //
 // cr::Mesh::load -> cr::BVH (Morton, sort, PLOC, flatten on the GPU) -> tracePrimary (the compute shader's dispatch)
 // -> rtr_shade (getColor) -> 8-bit PPM.  Everything the reference does between reading the OBJ file and
@@ -23,8 +28,8 @@ int main(int argc, char** argv) {
                       "[--wireframe] [--bvh-depth d] [--dump-camera file] [--dump-rgba file]");
     uint32_t W = 1280, H = 720;  // ApplicationParameters defaults
     float scale = 1.f, rot[3] = {0.f, 0.f, 0.f}, eye[3] = {0.f, 0.f, -5.f};
-    bool wireframe = false;
-    int bvhDepth = -1;
+    bool wireframe = false, rebuild = false;
+    int bvhDepth = -1, frames = 0;
     const char* dumpCamera = nullptr;
     const char* dumpRgba = nullptr;
     for (int i = 3; i < argc; ++i) {
@@ -36,6 +41,8 @@ int main(int argc, char** argv) {
         else if (a == "--eye") { need(3); for (int k = 0; k < 3; ++k) eye[k] = (float)std::atof(argv[++i]); }
         else if (a == "--wireframe") wireframe = true;
         else if (a == "--bvh-depth") { need(1); bvhDepth = std::atoi(argv[++i]); }
+        else if (a == "--frames") { need(1); frames = std::atoi(argv[++i]); }
+        else if (a == "--rebuild") rebuild = true;
         else if (a == "--dump-camera") { need(1); dumpCamera = argv[++i]; }
         else if (a == "--dump-rgba") { need(1); dumpRgba = argv[++i]; }
         else die(("unknown option " + a).c_str());
@@ -65,6 +72,22 @@ int main(int argc, char** argv) {
 
     // Scene::bindSSBO builds the BVH (scene.cpp:148); drawOneFrame dispatches the shader
     cr::BVH bvh(static_cast<uint32_t>(triangles.size()), triangles, meshes, nullptr, /*fillInternalStruct=*/false);
+    if (frames > 0) {  // mainLoop: render() + _FPS.increment() + the statistics window (application.cpp:264-313)
+        glr::ApplicationFPS fps;
+        cr::Camera moving(eye, static_cast<float>(W) / static_cast<float>(H));
+        fps.increment();
+        for (int f = 0; f < frames; ++f) {
+            if (rebuild) {
+                cr::BVH again(static_cast<uint32_t>(triangles.size()), triangles, meshes, bvh.context(), /*fillInternalStruct=*/false);
+                (void)again.tracePrimary(moving.getGpuData(), W, H);
+            } else {
+                (void)bvh.tracePrimary(moving.getGpuData(), W, H);
+            }
+            moving.processKeyboard(cr::FORWARD, 0.016f);
+            fps.increment();
+            fps.display(stdout);
+        }
+    }
     const std::vector<cr::Hit> hits = bvh.tracePrimary(cameraGPU, W, H);
     std::vector<float> rgba(static_cast<size_t>(W) * H * 4), overlay;
     uint32_t flags = wireframe ? RTR_SHADE_WIREFRAME : 0u;

@@ -473,4 +473,66 @@ private:
 
 }  // namespace cr
 
+// ---------------------------------------------------------------------------------------------------------------
+// glr::ApplicationFPS (srcOpenGL/application.hpp:15-34, application.cpp:345-373): the frame-time statistics of the
+// reference's main loop (render() -> _FPS.increment(), then the "Statistics" window).  Same members, same float
+// arithmetic -- increment() accumulates the time since the last frame, every _NbFramesBetweenDisplay frames display()
+// turns the window's sum / longest / shortest frame into avg / min / max FPS and starts a new window -- with the two
+// bindings to the outside made explicit: the clock is a parameter (the reference reads glfwGetTime(): seconds since
+// start as a double, narrowed to float; increment() without argument reads a steady clock the same way) and display()
+// prints the three lines of the ImGui text to a FILE* (nullptr: statistics only).
+// ---------------------------------------------------------------------------------------------------------------
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+namespace glr {
+struct ApplicationFPS {
+public:
+    bool _DisplayFPS = true;
+    uint32_t _NbFramesBetweenDisplay = 10;
+    float _LastFrame = 0.f;
+
+private:
+    uint32_t _FrameCounter = 0;
+    float _SumOfTimes = 0.f;
+    float _MinTime = INFINITY;
+    float _MaxTime = 0.f;
+    float _AvgFPS = 0.f;
+    float _MinFPS = 0.f;
+    float _MaxFPS = 0.f;
+
+public:
+    void increment(double timeSeconds) {  // application.cpp:345-355, glfwGetTime() passed in
+        const float currentFrame = static_cast<float>(timeSeconds);
+        const float deltaTime = currentFrame - _LastFrame;
+        _LastFrame = currentFrame;
+        _SumOfTimes += deltaTime;
+        _FrameCounter++;
+        if (deltaTime > _MaxTime) _MaxTime = deltaTime;
+        if (deltaTime < _MinTime) _MinTime = deltaTime;
+    }
+    void increment() {
+        static const std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
+        increment(std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count());
+    }
+    void display(FILE* out = stdout) {  // application.cpp:357-373; returns after updating when out == nullptr
+        const bool fresh = _FrameCounter >= _NbFramesBetweenDisplay;
+        if (fresh) {
+            _AvgFPS = 1.f / (_SumOfTimes / static_cast<float>(_FrameCounter));
+            _MinFPS = 1.f / _MaxTime;
+            _MaxFPS = 1.f / _MinTime;
+            _FrameCounter = 0;
+            _SumOfTimes = 0.f;
+            _MinTime = INFINITY;
+            _MaxTime = 0.f;
+        }
+        if (out && _DisplayFPS && fresh)
+            std::fprintf(out, "avg FPS: %.2f\nmin FPS: %.2f\nmax FPS: %.2f\n\n", _AvgFPS, _MinFPS, _MaxFPS);
+    }
+    float avgFPS() const { return _AvgFPS; }
+    float minFPS() const { return _MinFPS; }
+    float maxFPS() const { return _MaxFPS; }
+};
+}  // namespace glr
+
 #endif  // RTR_SCENE_HPP

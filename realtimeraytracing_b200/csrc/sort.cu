@@ -196,6 +196,21 @@ __device__ __forceinline__ uint32_t lanemask_gt() {
     return m;
 }
 
+#ifdef RTR_SORT_PHASE_CLOCKS
+__device__ unsigned long long g_sort_phase_ns[8];   // diagnostics build only (profiles/sort_phases.py)
+#define RTR_PHASE(i)                                                              \
+    do {                                                                          \
+        if (threadIdx.x == 0) {                                                   \
+            unsigned long long _t;                                                \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                \
+            atomicAdd(&g_sort_phase_ns[i], _t - _phase_t);                        \
+            _phase_t = _t;                                                        \
+        }                                                                         \
+    } while (0)
+#else
+#define RTR_PHASE(i) do {} while (0)
+#endif
+
 template <typename KeyT, bool PAIRS, int BLOCK, int IPT, bool TMA>
 __global__ void __launch_bounds__(BLOCK, RTR_SORT_MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
@@ -214,6 +229,10 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#ifdef RTR_SORT_PHASE_CLOCKS
+    unsigned long long _phase_t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_phase_t));
+#endif
 
     // dynamic tile id: tiles start in issue order, so look-back never waits on an unscheduled CTA
     if (tid == 0) {
@@ -224,6 +243,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     if (tid < kRadix) s.cta_hist[tid] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
+    RTR_PHASE(0);  // ticket + barrier
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t valid = min((uint32_t)TILE, n - tile_base);
     const bool full = (valid == (uint32_t)TILE);
@@ -256,6 +276,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         }
     }
 
+    RTR_PHASE(1);  // tile load (TMA arrival, keys to registers)
     // ---- digit counts of the tile first (one shared-memory reduction per key): the aggregate other tiles
     //      look back at is published BEFORE the expensive ranking, and this tile's own look-back runs
     //      interleaved with the ranking instead of after it ----
@@ -304,6 +325,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     // ---- rank inside the warp.  peers = lanes with the same digit; the key's slot among the warp's keys of
     //      that digit = running count of the earlier items (shared memory, bumped by the highest peer lane)
     //      + peers below.  rank[k] ends as (digit << 16 | slot) ----
+    RTR_PHASE(2);  // tile histogram, aggregate published, first look-back loads
     uint32_t rank[IPT];
     uint32_t* wh = s.whist[warp];
     const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
@@ -359,7 +381,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
         if (lb_step) lb_consume();
     }
 #endif
+    RTR_PHASE(3);  // ranking (interleaved look-back steps)
     while (!lb_done) { lb_issue(); lb_consume(); }
+    RTR_PHASE(4);  // rest of the look-back
     __syncthreads();  // all keys are in registers; s.keys may be overwritten from here on
 
     // ---- per digit (threads 0..255): first tile-local slot of every (warp, digit) ----
@@ -373,6 +397,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     }
     __syncthreads();
 
+    RTR_PHASE(5);  // barrier + slots of (warp, digit)
     // ---- reorder keys (and payload) inside the tile through shared memory ----
     uint2* kv = reinterpret_cast<uint2*>(s.keys);
 #pragma unroll
@@ -387,6 +412,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     }
     __syncthreads();
 
+    RTR_PHASE(6);  // reorder through shared memory + barrier
     // ---- coalesced scatter: consecutive threads write runs of equal digits ----
     if (full) {
 #pragma unroll
@@ -423,6 +449,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
             }
         }
     }
+    RTR_PHASE(7);  // scatter issued
 }
 
 // ---------------------------------------------------------------------------------------
@@ -600,6 +627,14 @@ int rtr_sort_impl_u32(rtr_ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, 
 int rtr_sort_impl_u64(rtr_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n, int begin_bit, int end_bit) {
     return sort_impl<uint64_t>(ctx, keys, vals, n, begin_bit, end_bit);
 }
+
+#ifdef RTR_SORT_PHASE_CLOCKS
+extern "C" int rtr_debug_sort_phases(unsigned long long out[8], int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_sort_phase_ns, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_sort_phase_ns, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int rtr_bit_histogram32_launch(rtr_ctx* ctx, const uint32_t* keys, uint32_t n, uint32_t* out) {
     uint32_t blocks = (n + 2047) / 2048;  // the reference dispatches n/2048 work-groups of 2048 keys

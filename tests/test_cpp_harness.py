@@ -19,7 +19,7 @@ def executables():
     env.pop("CXX", None)
     out = subprocess.run(["make", "-C", HARNESS, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera", "testMesh"]}
+    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera", "testMesh", "testFps"]}
 
 
 def test_camera_mirror_is_bit_identical_to_the_reference(executables):
@@ -51,6 +51,14 @@ def test_mesh_mirror_is_bit_identical_to_the_reference(executables):
     assert "0 mismatches" in r.stdout and "%d cases" % (len(objs) + 4 + 2000) in r.stdout
 
 
+def test_fps_statistics_mirror(executables):
+    """glr::ApplicationFPS (application.cpp:345-373) in include/rtr_scene.hpp: 3000 replayed frames, three window
+    lengths, against the restated float arithmetic; a known-answer window and its printed text."""
+    r = subprocess.run([executables["testFps"]], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout
+
+
 def test_shim_compiles_with_glm_types(tmp_path):
     """RTR_SCENE_USE_GLM: cr::Mesh / cr::Triangle / cr::Material / cr::Camera with glm::vec / glm::mat members."""
     glm = "/root/reference/srcVulkan/dep/slang/external/glm"
@@ -69,7 +77,7 @@ def test_shim_compiles_with_glm_types(tmp_path):
 def test_cpp_harness_compiles_and_links(executables):
     for t, path in executables.items():
         assert os.path.exists(path), t
-        if t == "testCamera":
+        if t in ("testCamera", "testFps"):
             continue  # host-only: cr::Camera needs nothing from the library
         needed = subprocess.check_output(["readelf", "-d", path], text=True)
         assert "librtr_b200.so" in needed, t  # bound to the C ABI library, nothing else of ours
@@ -158,3 +166,24 @@ def test_render_obj_example_equals_the_python_pipeline(render_obj, ctx, tmp_path
     assert data.startswith(header) and len(data) == len(header) + 3 * W * H
     px = np.frombuffer(data[len(header):], dtype=np.uint8).reshape(-1, 3)
     assert np.array_equal(px, np.floor(np.clip(exp[:, :3], 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rebuild", [False, True])
+def test_render_obj_frame_loop_reports_fps(render_obj, tmp_path, rebuild):
+    """--frames: the reference's mainLoop (application.cpp:220-313) over the shim -- 25 frames give two statistics
+    windows of 10, and the final frame is the one the single-shot run writes."""
+    obj = os.path.join(ROOT, "tests", "golden", "obj", "random.obj")
+    base = [render_obj, obj, None, "--size", "320", "192", "--scale", "2e-5"]
+    outs = []
+    for extra in ([], ["--frames", "25"] + (["--rebuild"] if rebuild else [])):
+        ppm = str(tmp_path / ("f%d.ppm" % len(outs)))
+        cmd = list(base) + extra
+        cmd[2] = ppm
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((r.stdout, open(ppm, "rb").read()))
+    assert outs[0][0].count("avg FPS") == 0 and outs[1][0].count("avg FPS") == 2
+    fps = [float(l.split(":")[1]) for l in outs[1][0].splitlines() if l.startswith(("avg", "min", "max"))]
+    assert all(f > 0 for f in fps) and fps[1] <= fps[0] <= fps[2]
+    assert outs[0][1] == outs[1][1]
