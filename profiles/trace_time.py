@@ -30,3 +30,14 @@ img = np.zeros((H, W, 4), np.float32)
 ctx.download(img, d_rgba)
 print("rays ms: min %.3f median %.3f  overflow %d  digest %s" % (min(ms), float(np.median(ms)), bvh.stack_overflows(),
       hashlib.blake2b(img.view(np.uint8).tobytes(), digest_size=8).hexdigest()))
+# what a launch costs whatever it traces: 1/57 and 8/57 of the frame (a builder's / a worker's part at 8 GPUs), 4 bounces
+for lay_rank, label in ((0, "1/57"), (1, "8/57")):
+    t = []
+    for i in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        bvh.render_stripes_dev(cam, W, H, d_rgba, 16, [1] + [8] * 7, lay_rank, bounces=4)
+        e1.record(st)
+        ctx.sync()
+        t.append(e0.elapsed_time(e1))
+    print("%s of the frame, 4 bounces: min %.3f median %.3f ms" % (label, min(t[1:]), float(np.median(t[1:]))))

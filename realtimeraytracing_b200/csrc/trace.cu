@@ -565,6 +565,28 @@ constexpr int kWalkSteps = RTR_WALK_STEPS;
 constexpr uint32_t kBlockBatch = RTR_BLOCK_BATCH;  // ... or once this many lanes wait on a second leaf
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDry = 0xFFFFFFFFu;  // stack ran dry (also the state of an idle lane)
+// Drain: once the job pool is empty, idle lanes of a warp take stack entries off the lanes still walking (below).
+#ifndef RTR_STEAL
+#define RTR_STEAL 1
+#endif
+constexpr bool kSteal = RTR_STEAL != 0;
+#ifdef RTR_STEAL_STATS   // diagnostics build: lane occupancy of the walk before / after the pool ran empty (profiles/steal_stats.py)
+__device__ unsigned long long g_steal_stats[8];
+#define RTR_STAT(i, v) do { if (lane == 0u) atomicAdd(&g_steal_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define RTR_STAT(i, v) do { } while (0)
+#endif
+constexpr uint32_t kHelperBit = 0x80000u;      // st bit 19: this lane walks part of another lane's ray
+constexpr uint32_t kMasterShift = 20u;         // st bits 20-24: the lane that owns the ray
+#ifndef RTR_STEAL_MIN_IDLE
+#define RTR_STEAL_MIN_IDLE 4
+#endif
+constexpr uint32_t kStealMinIdle = RTR_STEAL_MIN_IDLE;   // stacks are split once this many lanes of the warp are idle
+// best hit of a ray as one word whose maximum is the closest hit: smaller t first (t >= 0: its bits order like the
+// value), then the larger leaf index -- the rule of the leaf step.  0: no hit.
+__device__ __forceinline__ unsigned long long pack_best(float t, uint32_t node) {
+    return ((unsigned long long)(~__float_as_uint(t)) << 32) | node;
+}
 #ifndef RTR_SMEM_STACK
 #define RTR_SMEM_STACK 20
 #endif
@@ -651,7 +673,15 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     // a divergent local-memory access would cost one L1 wavefront per lane instead.
     __shared__ uint32_t s_stack[2][kSmemStack][kTraceBlock];
     __shared__ float s_pb[2];                   // pruning bound constants k, k*Emax (negative k: disabled)
-    __shared__ float s_stash[6][kTraceBlock];   // normal + incoming direction while a shadow ray is out
+    // Six words per lane with two uses that never overlap in time: while the lane's SHADOW ray is out, the normal and the
+    // incoming direction of the bounce (words 0-5); while its CLOSEST-HIT ray is shared with helper lanes (drain, below),
+    // the best hit they have published (words 0-1 as one 64-bit word) and the number of helpers still out (word 2).
+    // Any-hit rays are never shared and a ray only ends once its helpers are back, so the second use finds its
+    // words 0-2 zero: set here and again when the stash is read.  (A separate array would push the CTA's shared memory
+    // past the 196 KB carve-out for 8 CTAs per SM and shrink the L1: measured, the frame takes 27.8 ms instead of 24.2.)
+    __shared__ __align__(8) uint32_t s_lane[kTraceBlock][6];
+    auto lane_best = [&](uint32_t t) -> unsigned long long* { return reinterpret_cast<unsigned long long*>(&s_lane[t][0]); };
+    s_lane[threadIdx.x][0] = 0u; s_lane[threadIdx.x][1] = 0u; s_lane[threadIdx.x][2] = 0u;
     if (threadIdx.x == 0) {
         const PruneBound pb = make_prune_bound(tp, true);
         s_pb[0] = pb.enabled ? pb.k : -1.f;
@@ -674,7 +704,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
     uint32_t pend_node = RTR_NONE;  // parked leaf
     int sp = 0;
     uint32_t st = 0u;               // bits 0-15 bounce index, bit 16 any-hit ray, bit 17 stack overflow seen,
-                                    // bit 18 ray with a (nearly) zero direction component
+                                    // bit 18 ray with a (nearly) zero direction component, bits 19-24 drain (kHelperBit ...)
     float L = 0.f;
     float stack_t[kStack - kSmemStack];   // entries the shared-memory part has no room for
     uint32_t stack_a[kStack - kSmemStack];
@@ -789,6 +819,82 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             }
             pool_next += min(avail, (uint32_t)__popc(idle));
             idle = __ballot_sync(0xffffffffu, job == RTR_NONE);
+        }
+        // ---- drain: the pool is empty and lanes fall idle while the last rays are still being walked -- the end of every
+        //      launch, about 2 ms of a 4-bounce frame however few pixels it has (a 10 M-triangle soup: hundreds of
+        //      dependent steps per ray, up to five rays per path).  Idle lanes pair up with walking lanes and take EVERY
+        //      OTHER entry of their stacks (read straight from the donor's column of the shared-memory stack), together
+        //      with a copy of the ray and of its best hit so far, and walk them as helpers; all pairs of a warp split
+        //      at once.  The lanes of a ray publish their best hit in the owner's shared-memory word -- the closest hit is the
+        //      maximum of a total order (smaller t, then larger leaf index: the rule of the leaf step) -- prune with
+        //      it, and the owner takes it when its own stack is dry and no helper is out.  The leaves met are those of
+        //      the one-lane walk or a superset, so the record is the same bits.  Any-hit rays stop at their first hit
+        //      and are not shared. ----
+        if (kSteal && exhausted && idle != 0xffffffffu && (uint32_t)__popc(idle) >= kStealMinIdle) {
+            const bool can_give = job != RTR_NONE && (st & 0x10000u) == 0u && sp >= 2 && sp <= kSmemStack;
+            const uint32_t m_give = __ballot_sync(0xffffffffu, can_give);
+            const uint32_t pairs = min((uint32_t)__popc(m_give), (uint32_t)__popc(idle));
+            RTR_STAT(0, 1); RTR_STAT(1, __popc(idle)); RTR_STAT(2, __popc(m_give)); RTR_STAT(3, pairs);
+            if (pairs != 0u) {
+                const uint32_t below = lanemask_lt();
+                const bool thief = job == RTR_NONE && (uint32_t)__popc(idle & below) < pairs;
+                const bool donor = can_give && (uint32_t)__popc(m_give & below) < pairs;
+                uint32_t partner = lane;   // i-th idle lane <-> i-th donor
+                if (thief) partner = __fns(m_give, 0u, __popc(idle & below) + 1);
+                // the thief's lane state is replaced value by value (no block of temporaries: the walk's registers are
+                // all live here); every lane takes part in the shuffles, the others read themselves
+                {
+                    const uint32_t g_st = __shfl_sync(0xffffffffu, st, partner);
+                    const uint32_t g_job = __shfl_sync(0xffffffffu, job, partner);
+                    if (thief) {
+                        const uint32_t owner = (g_st & kHelperBit) ? ((g_st >> kMasterShift) & 31u) : partner;
+                        atomicAdd(&s_lane[(threadIdx.x & ~31u) + owner][2], 1u);
+                        job = g_job;   // not RTR_NONE: the lane is busy; the owner's lane writes the results
+                        st = (g_st & 0x4FFFFu) | kHelperBit | (owner << kMasterShift);   // bounce index and bit 18 carry over
+                        pend_node = RTR_NONE; L = 0.f;
+                    }
+                }
+                float v;
+                v = __shfl_sync(0xffffffffu, r.ox, partner); if (thief) r.ox = v;
+                v = __shfl_sync(0xffffffffu, r.oy, partner); if (thief) r.oy = v;
+                v = __shfl_sync(0xffffffffu, r.oz, partner); if (thief) r.oz = v;
+                v = __shfl_sync(0xffffffffu, r.dx, partner); if (thief) r.dx = v;
+                v = __shfl_sync(0xffffffffu, r.dy, partner); if (thief) r.dy = v;
+                v = __shfl_sync(0xffffffffu, r.dz, partner); if (thief) r.dz = v;
+                v = __shfl_sync(0xffffffffu, r.ix, partner); if (thief) r.ix = v;   // (the owner's 1/d, as computed by make_ray)
+                v = __shfl_sync(0xffffffffu, r.iy, partner); if (thief) r.iy = v;
+                v = __shfl_sync(0xffffffffu, r.iz, partner); if (thief) r.iz = v;
+                v = __shfl_sync(0xffffffffu, best_t, partner); if (thief) best_t = v;
+                v = __shfl_sync(0xffffffffu, limit, partner); if (thief) limit = v;
+                {
+                    const uint32_t g_bn = __shfl_sync(0xffffffffu, best_node, partner);
+                    if (thief) best_node = g_bn;
+                }
+                const int g_sp = __shfl_sync(0xffffffffu, sp, partner);
+                if (thief) {
+                    const uint32_t col = (threadIdx.x & ~31u) + partner;
+                    int m = 0;
+#pragma unroll 1
+                    for (int i = 0; i < g_sp; i += 2) {   // entries 0, 2, 4 ... in order; dead ones are dropped on the way
+                        const uint32_t tb = s_stack[0][i][col], w = s_stack[1][i][col];
+                        if (!(__uint_as_float(tb) > limit)) { s_stack[0][m][threadIdx.x] = tb; s_stack[1][m][threadIdx.x] = w; ++m; }
+                    }
+                    sp = m;
+                }
+                __syncwarp();
+                if (donor) {
+                    int m = 0;
+#pragma unroll 1
+                    for (int i = 1; i < sp; i += 2) {     // entries 1, 3, 5 ... stay
+                        const uint32_t tb = s_stack[0][i][threadIdx.x], w = s_stack[1][i][threadIdx.x];
+                        if (!(__uint_as_float(tb) > limit)) { s_stack[0][m][threadIdx.x] = tb; s_stack[1][m][threadIdx.x] = w; ++m; }
+                    }
+                    sp = m;
+                }
+                __syncwarp();
+                if (thief) pop_next();   // (a lane whose entries were all dead is dry: it reports back at once)
+                idle = __ballot_sync(0xffffffffu, job == RTR_NONE);
+            }
         }
         if (idle == 0xffffffffu) break;
 
@@ -907,6 +1013,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
             const uint32_t m_walk = __ballot_sync(0xffffffffu, a != kDry);
             const uint32_t m_dry = __ballot_sync(0xffffffffu, busy && a == kDry);
             const uint32_t movable = m_walk & ~m_blocked;
+            RTR_STAT(exhausted ? 4 : 6, 1); RTR_STAT(exhausted ? 5 : 7, __popc(m_walk));
             const bool want_fin = m_dry != 0u && ((uint32_t)__popc(m_dry) >= kFinBatch || (uint32_t)__popc(m_walk) < 16u);
             if ((uint32_t)__popc(m_blocked) >= kBlockBatch || (uint32_t)__popc(m_pend) >= kLeafBatch || movable == 0u || (want_fin && (m_dry & m_pend) != 0u)) {
                 // ---- leaf step: every parked leaf of the warp.  The reference's own two tests, on the exact
@@ -942,10 +1049,42 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                 }
             }
             if (want_fin || (movable == 0u && m_blocked == 0u)) break;
+            if (kSteal && exhausted && m_walk != 0xffffffffu) break;   // drain: lanes are free to take over stacked entries
         }
 
         // ---- rays whose stack ran dry: shade, continue the path or retire the job ----
-        const bool fin = job != RTR_NONE && a == kDry && pend_node == RTR_NONE;
+        if (kSteal && exhausted) {
+            const bool helper = (st & kHelperBit) != 0u;
+            const uint32_t own = helper ? ((threadIdx.x & ~31u) + ((st >> kMasterShift) & 31u)) : threadIdx.x;
+            const bool shared = job != RTR_NONE && (st & 0x10000u) == 0u && (helper || s_lane[threadIdx.x][2] != 0u);
+            if (__any_sync(0xffffffffu, shared)) {
+                // the lanes of a ray publish their best hit and prune with the best any of them has found
+                if (shared && best_node != RTR_NONE) atomicMax(lane_best(own), pack_best(best_t, best_node));
+                __syncwarp();
+                if (shared) {
+                    const unsigned long long p = *lane_best(own);
+                    if (p != 0ull) limit = fminf(limit, limit_of(__uint_as_float(~(uint32_t)(p >> 32))));
+                }
+                // a helper whose stack ran dry has published what it found: it falls idle
+                if (helper && a == kDry && pend_node == RTR_NONE) {
+                    if (st & 0x20000u) atomicAdd(&tp->stack_overflows, 1u);
+                    atomicSub(&s_lane[own][2], 1u);
+                    job = RTR_NONE; st = 0u;
+                }
+                __syncwarp();
+            }
+        }
+        const bool fin = job != RTR_NONE && a == kDry && pend_node == RTR_NONE && (st & kHelperBit) == 0u &&
+                         (!kSteal || !exhausted || (st & 0x10000u) != 0u || s_lane[threadIdx.x][2] == 0u);   // (any-hit: the words are the stash)
+        if (kSteal && exhausted && fin && (st & 0x10000u) == 0u) {   // what the helpers of this ray found
+            const unsigned long long p = *lane_best(threadIdx.x);
+            if (p != 0ull) {
+                const float h_t = __uint_as_float(~(uint32_t)(p >> 32));
+                const uint32_t h_n = (uint32_t)p;
+                if (best_node == RTR_NONE || h_t < best_t || (h_t == best_t && h_n > best_node)) { best_t = h_t; best_node = h_n; }
+                *lane_best(threadIdx.x) = 0ull;
+            }
+        }
         traced += __popc(__ballot_sync(0xffffffffu, fin));
         if (fin) {
             const bool any_mode = (st & 0x10000u) != 0u;
@@ -986,8 +1125,8 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         if (jd.shadow) {
                             const float sx = __fsub_rn(jd.lx, ox), sy = __fsub_rn(jd.ly, oy), sz = __fsub_rn(jd.lz, oz);
                             const float len = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
-                            s_stash[0][threadIdx.x] = nx; s_stash[1][threadIdx.x] = ny; s_stash[2][threadIdx.x] = nz;
-                            s_stash[3][threadIdx.x] = dx; s_stash[4][threadIdx.x] = dy; s_stash[5][threadIdx.x] = dz;
+                            s_lane[threadIdx.x][0] = __float_as_uint(nx); s_lane[threadIdx.x][1] = __float_as_uint(ny); s_lane[threadIdx.x][2] = __float_as_uint(nz);
+                            s_lane[threadIdx.x][3] = __float_as_uint(dx); s_lane[threadIdx.x][4] = __float_as_uint(dy); s_lane[threadIdx.x][5] = __float_as_uint(dz);
                             r = make_ray(ox, oy, oz, __fdiv_rn(sx, len), __fdiv_rn(sy, len), __fdiv_rn(sz, len));
                             start_ray(true, len);
                         } else {
@@ -996,8 +1135,9 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                         }
                     }
                 } else {  // shadow ray finished; its origin is the bounce origin
-                    nx = s_stash[0][threadIdx.x]; ny = s_stash[1][threadIdx.x]; nz = s_stash[2][threadIdx.x];
-                    dx = s_stash[3][threadIdx.x]; dy = s_stash[4][threadIdx.x]; dz = s_stash[5][threadIdx.x];
+                    nx = __uint_as_float(s_lane[threadIdx.x][0]); ny = __uint_as_float(s_lane[threadIdx.x][1]); nz = __uint_as_float(s_lane[threadIdx.x][2]);
+                    dx = __uint_as_float(s_lane[threadIdx.x][3]); dy = __uint_as_float(s_lane[threadIdx.x][4]); dz = __uint_as_float(s_lane[threadIdx.x][5]);
+                    s_lane[threadIdx.x][0] = 0u; s_lane[threadIdx.x][1] = 0u; s_lane[threadIdx.x][2] = 0u;   // free for the drain's use
                     const float ndl = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
                     c = best.did_hit ? 0.f : fmaxf(0.f, ndl);
                     shade = true;
@@ -1150,6 +1290,14 @@ int launch_persistent(rtr_ctx* ctx, const rtr_bvh* b, const JobDesc& jd, uint64_
 }
 
 }  // namespace
+
+#ifdef RTR_STEAL_STATS
+extern "C" int rtr_debug_steal_stats(unsigned long long out[8], int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_steal_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_steal_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 static void resolve_denoms(uint32_t width, uint32_t height, uint32_t& dw, uint32_t& dh) {
     if (dw == 0) dw = (width / 16) * 16;   // application.cpp:225-226 + raytracer.glsl:304-305 (Q5)

@@ -130,6 +130,26 @@ def builder_share_for(build_ms: float, render_ms: float, world: int) -> float:
     return max(0.0, min(1.0, mine / others))
 
 
+def stripe_layout_for(build_ms: float, render_ms: float, launch_ms: float, world: int, stripes_per_rank: int = 8) -> List[int]:
+    """stripe_layout with the builder's stripes chosen by a model that knows what a launch costs whatever it traces
+    (`launch_ms`: the frame's longest paths, walked by a few lanes): a rank with k of V stripes takes
+    launch_ms + k / V * (render_ms - launch_ms), the builder `build_ms` on top -- and nothing at all with k == 0.  The
+    k with the shortest frame wins (ties: the larger k).  At 8 GPUs that is 0: one stripe would cost the builder a
+    whole launch."""
+    if world <= 1:
+        return [1]
+    bulk = max(0.0, render_ms - launch_ms)
+    best_k, best_t = 0, float("inf")
+    for k in range(stripes_per_rank + 1):
+        total = k + stripes_per_rank * (world - 1)
+        builder = build_ms + ((launch_ms + k / total * bulk) if k else 0.0)
+        worker = launch_ms + stripes_per_rank / total * bulk
+        t = max(builder, worker)
+        if t <= best_t + 1e-9:
+            best_k, best_t = k, t
+    return [best_k] + [stripes_per_rank] * (world - 1)
+
+
 def gather_rows_striped(image, height: int, layout: List[int], rows_per_block: int = DEFAULT_ROWS_PER_BLOCK, group=None):
     """gather_rows for a stripe layout (same schedule as rtr_allgather_stripes)."""
     import torch.distributed as dist

@@ -236,3 +236,20 @@ def test_sharded_upload_and_download_over_gloo(tmp_path, world, layout):
     port = _free_port()
     mp.spawn(_sharded_worker, args=(world, port, 1001, height, width, 8, layout, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def test_stripe_layout_for_knows_what_a_launch_costs():
+    """The builder's stripes minimise the modelled frame time; with a launch floor a single stripe is never worth a
+    launch of its own at 8 ranks, and the 2 / 4 rank layouts keep the shares that balance rebuild and rays."""
+    from realtimeraytracing_b200 import parallel
+    assert parallel.stripe_layout_for(4.9, 37.9, 2.0, 1) == [1]
+    assert parallel.stripe_layout_for(4.9, 35.8, 1.0, 2) == [6, 8]
+    assert parallel.stripe_layout_for(4.9, 37.8, 1.0, 4)[0] in (3, 4) and parallel.stripe_layout_for(4.9, 37.8, 1.0, 4)[1:] == [8, 8, 8]
+    assert parallel.stripe_layout_for(4.9, 37.9, 2.0, 8) == [0] + [8] * 7
+    assert parallel.stripe_layout_for(0.0, 40.0, 0.0, 4) == [8, 8, 8, 8]           # nothing to rebuild: plain dealing
+    assert parallel.stripe_layout_for(100.0, 40.0, 1.0, 2) == [0, 8]              # the rebuild dominates: the builder only builds
+    for world in (2, 3, 4, 8):
+        lay = parallel.stripe_layout_for(4.9, 37.9, 2.0, world)
+        assert len(lay) == world and all(0 <= k <= 8 for k in lay) and sum(lay) > 0
+        owners = parallel.stripe_owners(lay)
+        assert sorted(set(owners)) == [r for r in range(world) if lay[r] > 0]
