@@ -413,9 +413,9 @@ def main():
     pipelined = world > 1 and not args.no_pipeline
     layout = [1] * world
     if pipelined:
-        NB = 4   # BVHs in rotation: traced (f, and f+1 on the second ray stream), received (f+1), travelling / rebuilt (f+2)
+        NB = 3
         stream_a = torch.cuda.Stream(device=dev)
-        stream_b = torch.cuda.Stream(device=dev, priority=-1)   # NCCL's kernels get SMs as soon as some are free
+        stream_b = torch.cuda.Stream(device=dev)
         stream_r = stream
         bvhs = [bvh] + [capi.Bvh(ctx) for _ in range(NB - 1)]
         built = [torch.cuda.Event() for _ in range(NB)]       # rank 0: BVH k rebuilt (not yet sent)
@@ -423,7 +423,6 @@ def main():
         released = [torch.cuda.Event() for _ in range(NB)]    # the rays of the frame that used BVH k are done
         sent = [torch.cuda.Event() for _ in range(NB)]        # rank 0: BVH k has left (it may be rebuilt)
         last_built = [None]
-        last_rays = [None]                                    # rank 0: its rays submitted last (the next rebuild waits for them)
 
         # e2e arm, host traffic SHARDED over the ranks' own PCIe links: every rank uploads its slice of the frame's
         # triangles (rtr_dev_upload_async), the slices are assembled on rank 0 over NVLink (rtr_gather_slices), and every
@@ -470,8 +469,9 @@ def main():
                 e.record(st)
                 marks.append((what, f, e))
 
-        def submit_h2d(f):
-            """e2e, every rank: its slice of frame f's host triangles goes up its own PCIe link."""
+        def submit_upload(f):
+            """e2e, every rank: its slice of frame f's host triangles goes up its own PCIe link, then the slices are
+            assembled on rank 0 over NVLink (an NCCL point: issued by all ranks at the same place of the schedule)."""
             j = f % 2
             ctx.switch_stream(x_in.cuda_stream)
             x_in.wait_event(x_slice_free[j])
@@ -480,11 +480,6 @@ def main():
             if rank == 0:
                 ctx.upload_async(d_meshes.data_ptr(), x_meshes_pinned.numpy())
             x_up_done[j].record(x_in)
-
-        def submit_slices(f):
-            """e2e, every rank: the slices of frame f are assembled on rank 0 over NVLink (an NCCL point: issued by all
-            ranks at the same place of the schedule)."""
-            j = f % 2
             ctx.switch_stream(stream_b.cuda_stream)
             stream_b.wait_event(x_up_done[j])
             if rank == 0:
@@ -503,8 +498,6 @@ def main():
             ctx.switch_stream(stream_a.cuda_stream)
             stream_a.wait_event(released[k])   # own rays of the frame that used this BVH
             stream_a.wait_event(sent[k])       # and its broadcast
-            if last_rays[0] is not None:
-                stream_a.wait_event(last_rays[0])   # a rebuild beside the persistent traversal kernel crawls (and stalls it)
             if e2e:
                 j = f % 2
                 stream_a.wait_event(x_tris_ready[j])
@@ -538,9 +531,7 @@ def main():
             ctx.switch_stream(sr.cuda_stream)
             sr.wait_event(ready[k])
             sr.wait_event(x_img_done[j])          # frame f-2 has left this image buffer
-            if layout[rank] == 0:
-                pass    # no rows for this rank (the rebuilding rank at 8 GPUs): nothing to launch
-            elif rank == 0 and last_built[0] is not None:
+            if rank == 0 and layout[0] > 0 and last_built[0] is not None:
                 # the persistent traversal kernel would hold the SMs a rebuild needs: on the building rank the rays
                 # start once the rebuild submitted last is through
                 sr.wait_event(last_built[0])
@@ -548,12 +539,9 @@ def main():
             img = x_rgba[j]
             if e2e:
                 sr.wait_event(x_img_free[j])   # the download of the frame that used this image buffer is through
-            if layout[rank] > 0:
-                bvhs[k].render_stripes_dev(cam, W, H, img.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
-                                           bounces=bounces, flags=flags)
+            bvhs[k].render_stripes_dev(cam, W, H, img.data_ptr(), rpb, layout, rank, rays_dev=d_rays.data_ptr(),
+                                       bounces=bounces, flags=flags)
             released[k].record(sr)
-            if layout[rank] > 0:
-                last_rays[0] = released[k]
             mark("rays1", f, sr)
             if e2e:
                 # every rank sends the rows it traced to the shared host image over its own PCIe link
@@ -564,9 +552,9 @@ def main():
                 ctx.download_stripes_async(x_host_img[j].ctypes.data, img.data_ptr(), W, H, 16, rpb, layout)
                 x_img_free[j].record(x_out)
                 ctx.switch_stream(sr.cuda_stream)
-            else:
-                # the frame is gathered on rank 0 by the communicator's stream (NCCL kernels do not belong into the rays'
-                # stream: the next frame's rays follow at once), issued by every rank at the same place of the schedule
+            elif args.partition:
+                # NCCL kernels do not belong into the rays' partition: the frame is gathered on rank 0 by the
+                # communicator's stream, issued by every rank at the same place of the schedule (after exchange(f+1))
                 x_frame_done[j].record(sr)
                 ctx.switch_stream(stream_b.cuda_stream)
                 stream_b.wait_event(x_frame_done[j])
@@ -574,35 +562,33 @@ def main():
                 x_img_done[j].record(stream_b)
                 mark("gather", f, stream_b)
                 ctx.switch_stream(sr.cuda_stream)
+            else:
+                ctx.gather_stripes(img.data_ptr(), W, H, 16, rpb, layout, 0)
+                x_img_done[j].record(sr)
+                mark("gather", f, sr)
 
         def run_pipelined(steps, e2e):
-            # Every rank issues its NCCL calls in the same order:
-            #   value: exchange(0), exchange(1), [gather(f), exchange(f+2)] ...     e2e: ... [slices(f+2), exchange(f+2)] ...
-            # On rank 0's SMs: B0 B1 R0 B2 R1 B3 ... -- the BVH of frame f+2 is rebuilt after the rays of f and travels beside
-            # the rays of f+1, on every rank.  (Round 2 first issued exchange(f+1) behind gather(f-1) on the communicator:
-            # the broadcast then waited for every rank's rays of f-1 and ran beside rank 0's NEXT rebuild, RTR_BENCH_TRACE:
-            # rebuild 9 ms, broadcast 6.7 ms where 4.9 and 4.3 are due.)
+            # every rank issues its NCCL calls in the same order:
+            #   value: exchange(f+1), gather(f), exchange(f+2), ...     e2e: slices(f+2), exchange(f+1), slices(f+3), ...
+            # (the slices of f+2 go BEFORE the exchange of f+1 on the communicator's stream: they only wait for host
+            #  uploads, whereas the exchange waits for the rebuild of f+1 -- so rank 0 can rebuild f+2 beside it)
             last_built[0] = None
-            last_rays[0] = None
             if e2e:
-                for f in range(min(2, steps)):
-                    submit_h2d(f)
-            for f in range(min(2, steps)):
-                if e2e:
-                    submit_slices(f)
-                submit_build(f, e2e)
-                submit_exchange(f)
-            if e2e and steps > 2:
-                submit_h2d(2)      # (after slices(0) was issued: both use the events of buffer 0)
+                submit_upload(0)
+                if steps > 1:
+                    submit_upload(1)
+            submit_build(0, e2e)
+            submit_exchange(0)
+            if steps > 1:
+                submit_build(1, e2e)
             for f in range(steps):
-                submit_rays(f, e2e)
-                if e2e and f + 3 < steps:
-                    submit_h2d(f + 3)
+                if e2e and f + 2 < steps:
+                    submit_upload(f + 2)
+                if f + 1 < steps:
+                    submit_exchange(f + 1)
                 if f + 2 < steps:
-                    if e2e:
-                        submit_slices(f + 2)
                     submit_build(f + 2, e2e)
-                    submit_exchange(f + 2)
+                submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
             barrier(); stream_a.synchronize(); stream_b.synchronize(); streams_r[0].synchronize(); streams_r[1].synchronize()
@@ -633,7 +619,7 @@ def main():
             frame_device()
         ctx.gather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, [1] * world, 0)   # first use connects the send/recv channels
         barrier()
-        t0, t1, t2, t3, t4, t5 = (torch.cuda.Event(enable_timing=True) for _ in range(6))
+        t0, t1, t2, t3, t4 = (torch.cuda.Event(enable_timing=True) for _ in range(5))
         t0.record(stream)
         if rank == 0:
             bvh.build_dev(d_tris.data_ptr(), n, n, d_meshes.data_ptr(), 1)
@@ -644,18 +630,14 @@ def main():
         t3.record(stream)
         ctx.gather_stripes(d_rgba.data_ptr(), W, H, 16, rpb, [1] * world, 0)
         t4.record(stream)
-        # one stripe of 57: what a launch costs whatever it traces (the longest paths of the frame, walked by a few lanes)
-        bvh.render_stripes_dev(cam, W, H, d_rgba.data_ptr(), rpb, [1] + [8] * 7, 0, bounces=bounces, flags=flags)
-        t5.record(stream)
         barrier()
-        tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2), t2.elapsed_time(t3), t3.elapsed_time(t4), t4.elapsed_time(t5)],
+        tt = torch.tensor([t0.elapsed_time(t1), t1.elapsed_time(t2), t2.elapsed_time(t3), t3.elapsed_time(t4)],
                           dtype=torch.float64, device=dev)
         dist.broadcast(tt, src=0)
-        serial_ms, bcast_ms, render_ms, gather_ms, small_ms = (float(x) for x in tt.tolist())
-        launch_ms = max(0.0, (small_ms - render_ms / 57.0) / (1.0 - 1.0 / 57.0))
-        layout = parallel.stripe_layout_for(serial_ms, render_ms, launch_ms, world)
+        serial_ms, bcast_ms, render_ms, gather_ms = (float(x) for x in tt.tolist())
+        layout = parallel.stripe_layout(world, parallel.builder_share_for(serial_ms, render_ms, world))
         phases = {"rebuild_ms": serial_ms, "broadcast_ms": bcast_ms, "full_frame_rays_ms_one_gpu": render_ms,
-                  "gather_ms": gather_ms, "launch_floor_ms": launch_ms, "stripes_of_rank": layout}
+                  "gather_ms": gather_ms, "stripes_of_rank": layout}
         barrier()
         if args.partition:
             # First launch inside the green context, with nothing else in flight: loading the kernel into a new context

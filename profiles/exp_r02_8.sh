@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 export NCCL_DEBUG=WARN
 i=0
-for extra in "" "--partition"; do
+for extra in ""; do
 i=$((i+1))
 tag=n${N}_v$i
 RTR_BENCH_WATCHDOG=240 RTR_BENCH_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+i)) bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-cpu-baseline $extra > gpurun_out/pipe_$tag.log 2> gpurun_out/pipe_$tag.err

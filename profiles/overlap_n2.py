@@ -109,7 +109,26 @@ if rank == 0:
 else:
     span([(sa, None)])
 
-for layout, r, label in (([1] + [8] * 7, 1, "8/57 of the frame"), ([1] + [8] * 7, 0, "1/57 of the frame"), ([6, 8], 1, "8/14 of the frame")):
+
+def delayed(fn, st, us):
+    def go():
+        with torch.cuda.stream(st):
+            torch.cuda._sleep(int(us * 1.9e3))   # spin, ~1.9 GHz
+        fn()
+    return go
+
+
+# who goes first matters: an NCCL kernel that becomes due while a rebuild is running
+for us in (0, 100, 1000, 3000):
+    t = span([(sa, (lambda: build(A)) if rank == 0 else None), (sb, delayed(lambda: bcast(B), sb, us))])
+    say("rebuild first, broadcast %4d us later      rebuild %.2f  bcast %.2f (from the start of the span)" % (us, t[0], t[1]))
+for us in (100, 500):
+    t = span([(sb, lambda: bcast(B)), (sa, delayed((lambda: build(A)) if rank == 0 else (lambda: None), sa, us))])
+    say("broadcast first, rebuild %4d us later      bcast %.2f  rebuild %.2f" % (us, t[0], t[1]))
+t = span([(sa, (lambda: (build(A), build(A))) if rank == 0 else None), (sb, delayed(lambda: bcast(B), sb, 1000))])
+say("two rebuilds back to back, broadcast 1000 us after the start: rebuilds %.2f  bcast %.2f" % (t[0], t[1]))
+
+for layout, r, label in (([1] + [8] * 7, 1, "8/57 of the frame"),):
     t = span([(main, lambda: rays(A, layout, r))])
     say("rays alone, %s        %.2f ms" % (label, t[0]))
     t = span([(sb, lambda: bcast(B)), (main, lambda: rays(A, layout, r))])
