@@ -412,6 +412,7 @@ def main():
     #      fewer of them (parallel.stripe_layout), and the frame is gathered on rank 0 (the rank that hands it on). ----
     pipelined = world > 1 and not args.no_pipeline
     layout = [1] * world
+    rank_zero_defers = False
     if pipelined:
         NB = 3
         stream_a = torch.cuda.Stream(device=dev)
@@ -509,12 +510,14 @@ def main():
             last_built[0] = built[k]
             mark("built", f, stream_a)
 
-        def submit_exchange(f):
+        def submit_exchange(f, after=None):
             """stage B, every rank: BVH f % NB travels from rank 0 (64 B*(2n-1), enqueue only)."""
             k = f % NB
             ctx.switch_stream(stream_b.cuda_stream)
             if rank == 0:
                 stream_b.wait_event(built[k])
+                if after is not None:
+                    stream_b.wait_event(after)
             else:
                 stream_b.wait_event(released[k])   # the rays of the frame that used this receive buffer
             bvhs[k].broadcast(0, traversal_only=not args.reference_order, expected_triangles=n)
@@ -552,9 +555,11 @@ def main():
                 ctx.download_stripes_async(x_host_img[j].ctypes.data, img.data_ptr(), W, H, 16, rpb, layout)
                 x_img_free[j].record(x_out)
                 ctx.switch_stream(sr.cuda_stream)
-            elif args.partition:
-                # NCCL kernels do not belong into the rays' partition: the frame is gathered on rank 0 by the
-                # communicator's stream, issued by every rank at the same place of the schedule (after exchange(f+1))
+            elif args.partition or (rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER")):
+                # the frame is gathered on rank 0 by the communicator's stream, issued by every rank at the same place of
+                # the schedule (after exchange(f+1)): the next frame's rays follow at once instead of waiting for rank 0 to
+                # receive (RTR_BENCH_TRACE at 2 GPUs: 1.1 ms of every 23.5 ms frame of rank 1).  Not at 8 GPUs: measured
+                # there, the broadcasts queued behind these gathers take 8 ms instead of 3.6 (2359 against 2694 Mrays/s).
                 x_frame_done[j].record(sr)
                 ctx.switch_stream(stream_b.cuda_stream)
                 stream_b.wait_event(x_frame_done[j])
@@ -581,13 +586,20 @@ def main():
             submit_exchange(0)
             if steps > 1:
                 submit_build(1, e2e)
+            # Where rank 0 traces a good part of the frame itself (2 and 4 GPUs), its broadcast of f+1 is held back until
+            # its rebuild of f+2 is through: it then travels beside rank 0's rays of f, which make room for NCCL, instead of
+            # beside the rebuild -- RTR_BENCH_TRACE at 2 GPUs: rebuild 9 ms and broadcast 6.7 ms side by side, 4.9 and 4.3
+            # apart.  At 8 GPUs rank 0 hardly traces and the workers would wait for the later broadcast: not done there.
+            defer = rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER")
             for f in range(steps):
                 if e2e and f + 2 < steps:
                     submit_upload(f + 2)
-                if f + 1 < steps:
+                if f + 1 < steps and not (defer and f + 2 < steps):
                     submit_exchange(f + 1)
                 if f + 2 < steps:
                     submit_build(f + 2, e2e)
+                    if defer:
+                        submit_exchange(f + 1, after=last_built[0])
                 submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
@@ -636,8 +648,10 @@ def main():
         dist.broadcast(tt, src=0)
         serial_ms, bcast_ms, render_ms, gather_ms = (float(x) for x in tt.tolist())
         layout = parallel.stripe_layout(world, parallel.builder_share_for(serial_ms, render_ms, world))
+        rank_zero_defers = 2 * layout[0] >= max(layout)
         phases = {"rebuild_ms": serial_ms, "broadcast_ms": bcast_ms, "full_frame_rays_ms_one_gpu": render_ms,
-                  "gather_ms": gather_ms, "stripes_of_rank": layout}
+                  "gather_ms": gather_ms, "stripes_of_rank": layout,
+                  "broadcast_held_until_next_rebuild_done": bool(rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER"))}
         barrier()
         if args.partition:
             # First launch inside the green context, with nothing else in flight: loading the kernel into a new context
