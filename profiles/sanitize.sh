@@ -33,6 +33,6 @@ with capi.Context(0) as ctx:
 print("driver ok")
 PY
 for tool in ${TOOLS:-memcheck racecheck}; do
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout ${SAN_TIMEOUT:-1200} compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|driver ok|Error|hazard" gpurun_out/sanitizer_$tool.log | head -12
 done

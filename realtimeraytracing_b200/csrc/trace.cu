@@ -871,6 +871,7 @@ trace_persistent_kernel(const Accel A, TraceParams* __restrict__ tp, const JobDe
                     if (thief) best_node = g_bn;
                 }
                 const int g_sp = __shfl_sync(0xffffffffu, sp, partner);
+                __syncwarp();   // the donors' stack entries, written lanes apart, are read by other lanes below
                 if (thief) {
                     const uint32_t col = (threadIdx.x & ~31u) + partner;
                     int m = 0;

@@ -143,6 +143,44 @@ def test_multi_bounce_render(ctx, oracle, shadow):
         bvh.close()
 
 
+@pytest.mark.parametrize("shadow", [False, True])
+def test_shared_walks_of_the_drain_keep_the_records(ctx, oracle, shadow):
+    """Once the job pool of the persistent kernel is empty, idle lanes take over half of a walking lane's stack and the
+    ray's closest hit is assembled from what its lanes found (trace.cu, drain).  A small frame of long paths on a big
+    scene is almost all drain: one job tile per warp, the pool empty from the start.  The frame, the primary records and
+    the ray count equal the shader's order (one lane per pixel, no sharing) and, for the smaller scene, the oracle."""
+    for n, W, H, bounces, against_oracle in ((20000, 64, 48, 5, True), (400_000, 256, 160, 6, False)):
+        tris, meshes, L = scenes.soup(n)
+        if against_oracle:
+            bvh, flat = build_pair(ctx, oracle, tris, meshes)
+        else:
+            bvh = capi.Bvh(ctx).build(tris, meshes)
+        try:
+            cam = synth.soup_camera(L, W, H)
+            light = (0.3 * L, 0.8 * L, -1.2 * L)
+            a = bvh.render(cam, W, H, W, H, bounces=bounces, shadow=shadow, light=light, flags=capi.TRACE_DEFAULT)
+            b = bvh.render(cam, W, H, W, H, bounces=bounces, shadow=shadow, light=light, flags=capi.TRACE_REFERENCE_ORDER)
+            assert a[2] == b[2] and a[2] > 1.3 * W * H                    # rays traced: paths do bounce
+            assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)), "frame"
+            assert np.array_equal(a[1].view(np.uint8), b[1].view(np.uint8)), "primary records"
+            if against_oracle:
+                ergba, ehits, enrays = oracle.render(flat, tris, meshes, cam, W, H, W, H, bounces=bounces, shadow=shadow, light=light)
+                assert a[2] == enrays and np.array_equal(a[0], ergba)
+                assert_hits_equal(a[1], ehits, "drain primary")
+            # explicit closest-hit rays (the other job kind), a batch small enough to be all drain
+            rng = np.random.RandomState(11)
+            m = 3000
+            rays = np.zeros(m, dtype=RAY)
+            rays["o"][:, :3] = rng.uniform(-L, L, size=(m, 3)); rays["o"][:, 3] = 1.0
+            d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            rays["d"][:, :3] = d
+            x = bvh.trace_rays(rays, flags=capi.TRACE_DEFAULT)
+            y = bvh.trace_rays(rays, flags=capi.TRACE_REFERENCE_ORDER)
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)) and x["did_hit"].sum() > 100
+        finally:
+            bvh.close()
+
+
 def test_row_ranges_tile_the_frame(ctx):
     """Rows [row0,row1) rendered separately equal the full frame (what the multi-GPU sharding relies on)."""
     tris, meshes, L = scenes.soup(10000)
