@@ -590,6 +590,10 @@ def main():
             # its rebuild of f+2 is through: it then travels beside rank 0's rays of f, which make room for NCCL, instead of
             # beside the rebuild -- RTR_BENCH_TRACE at 2 GPUs: rebuild 9 ms and broadcast 6.7 ms side by side, 4.9 and 4.3
             # apart.  At 8 GPUs rank 0 hardly traces and the workers would wait for the later broadcast: not done there.
+            # (Holding it back in the e2e arm of 8 GPUs as well -- there the broadcast starts with rank 0's next rebuild and
+            # takes 8.8 ms beside it -- was measured: the broadcast drops to 3.5 ms, but the slices of the frame after next
+            # then queue behind it on the communicator and the rebuild behind them: 2 046 against 2 252 Mrays/s.  It needs the
+            # slices issued one frame earlier; not done, no GPU time left to validate it.)
             defer = rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER")
             for f in range(steps):
                 if e2e and f + 2 < steps:
