@@ -750,11 +750,13 @@ def main():
             up_done[k].record(s_in)
 
         def e2e_frame(f):
+            # (starting the upload of f+1 with the rays of f instead of beside its rebuild was measured: 30.42 against
+            #  30.39 ms per step, profiles/exp_r02_19.sh -- the copy does not disturb the rebuild)
             k = f % 2
             ctx.switch_stream(stream.cuda_stream)
             stream.wait_event(up_done[k])
-            stream.wait_event(img_free[k])
             bvh.build_dev(d_tris2[k].data_ptr(), n, n, d_meshes.data_ptr(), 1)
+            stream.wait_event(img_free[k])      # only the rays need the image buffer back
             bvh.render_sharded_dev(cam, W, H, d_rgba2[k].data_ptr(), rpb, 0, 1, rays_dev=d_rays.data_ptr(),
                                    bounces=bounces, flags=flags)
             frame_done[k].record(stream)
