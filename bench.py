@@ -578,14 +578,6 @@ def main():
             # (the slices of f+2 go BEFORE the exchange of f+1 on the communicator's stream: they only wait for host
             #  uploads, whereas the exchange waits for the rebuild of f+1 -- so rank 0 can rebuild f+2 beside it)
             last_built[0] = None
-            if e2e:
-                submit_upload(0)
-                if steps > 1:
-                    submit_upload(1)
-            submit_build(0, e2e)
-            submit_exchange(0)
-            if steps > 1:
-                submit_build(1, e2e)
             # Where rank 0 traces a good part of the frame itself (2 and 4 GPUs), its broadcast of f+1 is held back until
             # its rebuild of f+2 is through: it then travels beside rank 0's rays of f, which make room for NCCL, instead of
             # beside the rebuild -- RTR_BENCH_TRACE at 2 GPUs: rebuild 9 ms and broadcast 6.7 ms side by side, 4.9 and 4.3
@@ -594,17 +586,18 @@ def main():
             # takes 8.8 ms beside it -- was measured: the broadcast drops to 3.5 ms, but the slices of the frame after next
             # then queue behind it on the communicator and the rebuild behind them: 2 046 against 2 252 Mrays/s.  It needs the
             # slices issued one frame earlier; not done, no GPU time left to validate it.)
-            defer = rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER")
-            for f in range(steps):
-                if e2e and f + 2 < steps:
-                    submit_upload(f + 2)
-                if f + 1 < steps and not (defer and f + 2 < steps):
-                    submit_exchange(f + 1)
-                if f + 2 < steps:
-                    submit_build(f + 2, e2e)
-                    if defer:
-                        submit_exchange(f + 1, after=last_built[0])
-                submit_rays(f, e2e)
+            hold = bool(rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER"))
+            for op, f in parallel.frame_schedule(steps, e2e, hold):   # the issue order, with its invariants: parallel.py
+                if op == "upload":
+                    submit_upload(f)
+                elif op == "build":
+                    submit_build(f, e2e)
+                elif op == "exchange":
+                    submit_exchange(f)
+                elif op == "exchange_after_build":
+                    submit_exchange(f, after=last_built[0])
+                else:
+                    submit_rays(f, e2e)
 
         def timed_pipelined(steps, e2e):
             barrier(); stream_a.synchronize(); stream_b.synchronize(); streams_r[0].synchronize(); streams_r[1].synchronize()

@@ -150,6 +150,43 @@ def stripe_layout_for(build_ms: float, render_ms: float, launch_ms: float, world
     return [best_k] + [stripes_per_rank] * (world - 1)
 
 
+def frame_schedule(steps: int, e2e: bool, hold_broadcast: bool) -> List[Tuple[str, int]]:
+    """Issue order of the pipelined frames of `bench.py` (N > 1), the same on every rank -- which is what keeps the NCCL
+    calls of the ranks in step.  Operations: ("upload", f) this rank's slice of frame f's triangles goes up and the slices
+    are assembled on rank 0 (e2e arm only), ("build", f) rank 0 rebuilds BVH f, ("exchange", f) BVH f travels from rank 0,
+    ("exchange_after_build", f) the same, held back on rank 0 until the rebuild issued just before it (f + 1) is through,
+    ("rays", f) every rank traces its stripes of frame f (and the frame is gathered / downloaded).
+
+    Steady state, per frame f:  upload(f+2) | exchange(f+1) | build(f+2) | rays(f)   -- or, with hold_broadcast (ranks 0
+    that trace a good part of the frame themselves), upload(f+2) | build(f+2) | exchange_after_build(f+1) | rays(f): the
+    broadcast then travels beside rank 0's rays of f instead of beside its rebuild of f+2.  The buffers behind it:
+    three BVHs (f % 3), two upload / triangle / image buffers (f % 2); tests/test_parallel_cpu.py checks that no slot is
+    re-used before the operation that frees it has been issued."""
+    ops: List[Tuple[str, int]] = []
+    if steps <= 0:
+        return ops
+    if e2e:
+        ops.append(("upload", 0))
+        if steps > 1:
+            ops.append(("upload", 1))
+    ops.append(("build", 0))
+    ops.append(("exchange", 0))
+    if steps > 1:
+        ops.append(("build", 1))
+    for f in range(steps):
+        if e2e and f + 2 < steps:
+            ops.append(("upload", f + 2))
+        held = hold_broadcast and f + 2 < steps
+        if f + 1 < steps and not held:
+            ops.append(("exchange", f + 1))
+        if f + 2 < steps:
+            ops.append(("build", f + 2))
+            if held:
+                ops.append(("exchange_after_build", f + 1))
+        ops.append(("rays", f))
+    return ops
+
+
 def gather_rows_striped(image, height: int, layout: List[int], rows_per_block: int = DEFAULT_ROWS_PER_BLOCK, group=None):
     """gather_rows for a stripe layout (same schedule as rtr_allgather_stripes)."""
     import torch.distributed as dist

@@ -253,3 +253,68 @@ def test_stripe_layout_for_knows_what_a_launch_costs():
         assert len(lay) == world and all(0 <= k <= 8 for k in lay) and sum(lay) > 0
         owners = parallel.stripe_owners(lay)
         assert sorted(set(owners)) == [r for r in range(world) if lay[r] > 0]
+
+
+def _old_inline_loop(steps, e2e, defer):
+    """the loop bench.py ran before the schedule moved into parallel.frame_schedule (the one the multi-GPU numbers of
+    DESIGN.md §7 were measured with), transcribed: the two must stay identical"""
+    ops = []
+    if e2e:
+        ops.append(("upload", 0))
+        if steps > 1:
+            ops.append(("upload", 1))
+    ops.append(("build", 0))
+    ops.append(("exchange", 0))
+    if steps > 1:
+        ops.append(("build", 1))
+    for f in range(steps):
+        if e2e and f + 2 < steps:
+            ops.append(("upload", f + 2))
+        if f + 1 < steps and not (defer and f + 2 < steps):
+            ops.append(("exchange", f + 1))
+        if f + 2 < steps:
+            ops.append(("build", f + 2))
+            if defer:
+                ops.append(("exchange_after_build", f + 1))
+        ops.append(("rays", f))
+    return ops
+
+
+@pytest.mark.parametrize("e2e", [False, True])
+@pytest.mark.parametrize("hold", [False, True])
+def test_frame_schedule_invariants(e2e, hold):
+    """What the pipelined frames rely on, for every length: each operation once per frame; upload < build < exchange <
+    rays within a frame; a receiver posts the exchange of f+1 before it launches the rays of f; and no buffer slot --
+    three BVHs, two upload / triangle buffers -- is handed to a new frame before the operation that frees it has been
+    issued (an event waited for before it is recorded again names the OLD record: the hazard the first re-ordering hit)."""
+    from realtimeraytracing_b200 import parallel
+    assert parallel.frame_schedule(0, e2e, hold) == []
+    for steps in range(1, 14):
+        ops = parallel.frame_schedule(steps, e2e, hold)
+        assert ops == _old_inline_loop(steps, e2e, hold)
+        at = {}
+        for i, (op, f) in enumerate(ops):
+            key = ("exchange" if op.startswith("exchange") else op, f)
+            assert key not in at, "issued twice: %r" % (key,)
+            at[key] = i
+            assert 0 <= f < steps
+        for f in range(steps):
+            assert ("build", f) in at and ("exchange", f) in at and ("rays", f) in at
+            assert (("upload", f) in at) == e2e
+            if e2e:
+                assert at[("upload", f)] < at[("build", f)]
+            assert at[("build", f)] < at[("exchange", f)] < at[("rays", f)]
+            if f + 1 < steps:
+                assert at[("exchange", f + 1)] < at[("rays", f)]          # posted before the host turns to the rays
+            if f + 3 < steps:                                             # BVH slot f % 3: rays and broadcast of f issued
+                assert at[("build", f + 3)] > at[("rays", f)] and at[("build", f + 3)] > at[("exchange", f)]
+                assert at[("exchange", f + 3)] > at[("rays", f)]          # receivers: the buffer is released by then
+            if e2e and f + 2 < steps:                                     # triangle / slice slot f % 2: rebuilt from first
+                assert at[("upload", f + 2)] > at[("build", f)]
+            if f + 2 < steps:                                             # image slot f % 2
+                assert at[("rays", f + 2)] > at[("rays", f)]
+        for i, (op, f) in enumerate(ops):
+            if op == "exchange_after_build":
+                assert hold and ops[i - 1] == ("build", f + 1)
+        if not hold:
+            assert all(op != "exchange_after_build" for op, _ in ops)
