@@ -28,6 +28,7 @@
 #ifndef RTR_SCENE_HPP
 #define RTR_SCENE_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -472,6 +473,149 @@ private:
 };
 
 }  // namespace cr
+
+// ---------------------------------------------------------------------------------------------------------------
+// glr::Scene (srcOpenGL/scene/scene.hpp:22-62, scene.cpp): the container the reference's application fills and hands
+// to the shader -- materials (always one default one), meshes, the three *ToGPUData views, the DFS flatten of the BVH
+// (getBVH_NodesToGPUData) and sendDataToGpu.  Same members and method names.  What the reference does with GL there
+// (createSSBO / bindSSBO / the three uniforms) is the build of the cr::BVH from the views (scene.cpp:148) and keeping the
+// arrays for the rays and the shading; `referencePadding` reproduces the fixed-size SSBO views of the reference --
+// vectors of MAX_NB_* records, extra input dropped (65 536 triangles, 64 meshes) -- without it the views have the
+// size of their content and nothing is dropped.
+// ---------------------------------------------------------------------------------------------------------------
+namespace glr {
+class Scene;
+using ScenePtr = std::shared_ptr<Scene>;
+
+class Scene {
+private:
+    std::vector<cr::Material> _Materials = {cr::Material()};  // always one default material (scene.hpp:24)
+    std::vector<cr::MeshPtr> _Meshes = {};
+    uint32_t _NbTriangles = 0;
+    uint32_t _NbMaterials = 1;  // the default one
+    uint32_t _NbMeshes = 0;
+    cr::BVH_Ptr _BVH = nullptr;
+    rtr_ctx* _ctx = nullptr;
+    bool _referencePadding = false;
+    // what bindSSBO sent (scene.cpp:112-176), kept for the shading of the hit records
+    std::vector<cr::TriangleGPU> _TrianglesSent;
+    std::vector<cr::MeshModelGPU> _ModelsSent;
+    std::vector<cr::MaterialGPU> _MaterialsSent;
+
+public:
+    explicit Scene(rtr_ctx* ctx = nullptr, bool referencePadding = false) : _ctx(ctx), _referencePadding(referencePadding) {}
+
+    std::vector<cr::TriangleGPU> getTriangleToGPUData() const {  // scene.cpp:26-40
+        std::vector<cr::TriangleGPU> trianglesGPU;
+        if (_referencePadding) {
+            cr::TriangleGPU zero;
+            std::memset(static_cast<void*>(&zero), 0, sizeof(zero));
+            trianglesGPU.assign(cr::Triangle::MAX_NB_TRIANGLES, zero);
+        }
+        size_t i = 0;
+        for (const cr::MeshPtr& mesh : _Meshes)
+            for (const cr::Triangle& triangle : mesh->_Triangles) {
+                if (_referencePadding) {
+                    if (i == cr::Triangle::MAX_NB_TRIANGLES) break;
+                    trianglesGPU[i] = triangle._InternalStruct;
+                } else {
+                    trianglesGPU.push_back(triangle._InternalStruct);
+                }
+                i++;
+            }
+        return trianglesGPU;
+    }
+    std::vector<cr::MaterialGPU> getMaterialToGPUData() const {  // scene.cpp:42-48
+        const size_t n = _referencePadding ? std::min(_Materials.size(), cr::Material::MAX_NB_MATERIALS) : _Materials.size();
+        std::vector<cr::MaterialGPU> materialGPU(_referencePadding ? cr::Material::MAX_NB_MATERIALS : n);
+        for (size_t i = 0; i < n; i++) materialGPU[i] = _Materials[i]._InternalStruct;
+        return materialGPU;
+    }
+    std::vector<cr::MeshModelGPU> getMeshModelToGPUData() const {  // scene.cpp:17-23
+        const size_t n = _referencePadding ? std::min(_Meshes.size(), cr::Mesh::MAX_NB_MESHES) : _Meshes.size();
+        std::vector<cr::MeshModelGPU> modelsGPU(_referencePadding ? cr::Mesh::MAX_NB_MESHES : n);
+        for (size_t i = 0; i < n; i++) modelsGPU[i] = _Meshes[i]->_InternalStruct;
+        return modelsGPU;
+    }
+    // scene.cpp:203-208: the DFS pre-order array the shader walks, root first.  Computed by the library's flatten
+    // kernels; flattenTopDown below is the reference's own recursion over _InternalStruct, for comparison.
+    std::vector<cr::BVH_NodeGPU> getBVH_NodesToGPUData(cr::BVH_Ptr bvh) const { return bvh->getFlatNodes(); }
+
+    // recursiveTopDownTraversalBVH (scene.cpp:189-201) over the by-cluster-id view, with an explicit stack instead of
+    // the recursion (a 10 M-leaf PLOC tree is deep enough to matter): a node is appended when it is first met, its
+    // _LeftChild / _RightChild become the positions its children are appended at; leaves keep the 0 / 0 links.
+    static std::vector<cr::BVH_NodeGPU> flattenTopDown(const cr::BVH_Params& params, uint32_t nbTriangles) {
+        std::vector<cr::BVH_NodeGPU> out;
+        if (nbTriangles == 0) return out;
+        out.reserve(2 * static_cast<size_t>(nbTriangles) - 1);
+        struct Pending { uint32_t node; uint32_t parentPosition; bool isRight; };
+        std::vector<Pending> stack;
+        stack.push_back({2 * nbTriangles - 2, 0xFFFFFFFFu, false});  // rootId (scene.cpp:205)
+        while (!stack.empty()) {
+            const Pending cur = stack.back();
+            stack.pop_back();
+            const uint32_t position = static_cast<uint32_t>(out.size());
+            out.push_back(params._Clusters[cur.node].value());
+            if (cur.parentPosition != 0xFFFFFFFFu) {
+                if (cur.isRight) out[cur.parentPosition]._RightChild = position;
+                else out[cur.parentPosition]._LeftChild = position;
+            }
+            if (!params._IsLeaf[cur.node]) {  // has_value(): set for leaves only (scene.cpp:193)
+                stack.push_back({params._RightChild[cur.node].value(), position, true});   // popped second: after the whole
+                stack.push_back({params._LeftChild[cur.node].value(), position, false});   // left subtree, as in the recursion
+            }
+        }
+        return out;
+    }
+
+    void addMesh(cr::MeshPtr mesh) {  // scene.cpp:50-55
+        if (_referencePadding && _Meshes.size() == cr::Mesh::MAX_NB_MESHES) return;
+        _Meshes.push_back(mesh);
+        _NbMeshes++;
+        _NbTriangles += static_cast<uint32_t>(_referencePadding ? std::min(mesh->_Triangles.size(), cr::Triangle::MAX_NB_TRIANGLES)
+                                                                : mesh->_Triangles.size());
+    }
+    void addMaterial(const cr::vec4& color) {  // scene.cpp:57-61
+        if (_Materials.size() == cr::Material::MAX_NB_MATERIALS) return;
+        _Materials.emplace_back(color);
+        _NbMaterials++;
+    }
+    void addRandomMaterial() {  // scene.cpp:63-67
+        if (_Materials.size() == cr::Material::MAX_NB_MATERIALS) return;
+        _Materials.emplace_back();
+        _NbMaterials++;
+    }
+
+    // scene.cpp:210-222 + bindSSBO (:112-176): the views are taken, the BVH is built from them; the three uniforms
+    // (uNbTriangles / uNbMaterials / uNbModels) are the getNb* accessors below
+    void sendDataToGpu() {
+        _MaterialsSent = getMaterialToGPUData();
+        _TrianglesSent = getTriangleToGPUData();
+        _ModelsSent = getMeshModelToGPUData();
+        _BVH = cr::BVH_Ptr(new cr::BVH(_NbTriangles, _TrianglesSent, _ModelsSent, _ctx));
+    }
+
+    // one dispatch of raytracer.glsl over the scene that was sent (application.cpp:225-245): closest hits, then
+    // getColor (raytracer.glsl:159-179,299-331) -- the rgba32f image, 4 floats per pixel
+    std::vector<float> drawOneFrame(const cr::CameraGPU& camera, uint32_t width, uint32_t height, bool wireframe = false) const {
+        std::vector<float> rgba(static_cast<size_t>(width) * height * 4, 0.f);
+        if (!_BVH) return rgba;
+        const std::vector<cr::Hit> hits = _BVH->tracePrimary(camera, width, height);
+        RTR_SCENE_CHECK(_BVH->context(),
+                        rtr_shade(_BVH->context(), reinterpret_cast<const rtr_hit*>(hits.data()), hits.size(),
+                                  reinterpret_cast<const rtr_triangle*>(_TrianglesSent.data()), _NbTriangles,
+                                  reinterpret_cast<const rtr_mesh*>(_ModelsSent.data()), _NbMeshes,
+                                  reinterpret_cast<const rtr_material*>(_MaterialsSent.data()), _NbMaterials,
+                                  wireframe ? RTR_SHADE_WIREFRAME : 0u, nullptr, rgba.data()));
+        return rgba;
+    }
+
+    cr::BVH_Ptr getBVH() const { return _BVH; }
+    uint32_t getNbTriangles() const { return _NbTriangles; }
+    uint32_t getNbMaterials() const { return _NbMaterials; }
+    uint32_t getNbMeshes() const { return _NbMeshes; }
+};
+}  // namespace glr
 
 // ---------------------------------------------------------------------------------------------------------------
 // glr::ApplicationFPS (srcOpenGL/application.hpp:15-34, application.cpp:345-373): the frame-time statistics of the

@@ -19,7 +19,7 @@ def executables():
     env.pop("CXX", None)
     out = subprocess.run(["make", "-C", HARNESS, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera", "testMesh", "testFps"]}
+    return {t: os.path.join(HARNESS, "build", t) for t in TESTS + ["testCamera", "testMesh", "testFps", "testScene"]}
 
 
 def test_camera_mirror_is_bit_identical_to_the_reference(executables):
@@ -57,6 +57,19 @@ def test_fps_statistics_mirror(executables):
     r = subprocess.run([executables["testFps"]], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+def test_scene_mirror_container_and_flatten(executables):
+    """glr::Scene of include/rtr_scene.hpp (scene.hpp:22-62, scene.cpp): counters, caps and the fixed-size views of the
+    reference, and its recursiveTopDownTraversalBVH restated over `_InternalStruct` against the oracle's flatten on PLOC
+    trees of 1 ... 20 000 triangles (the oracle's flatten is pinned to the reference's fixtures)."""
+    from oracle import bindings as ob
+    ob.Oracle()     # builds oracle/librtr_oracle.so if it is not there
+    lib = os.path.join(ROOT, "oracle", "librtr_oracle.so")
+    assert os.path.exists(lib)
+    r = subprocess.run([executables["testScene"], lib], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "9 cases, 0 mismatches" in r.stdout
 
 
 def test_shim_compiles_with_glm_types(tmp_path):

@@ -78,5 +78,45 @@ int main() {
         if (h._DidHit) { ++nbHits; assert(h._TriangleId < n && h._Coords.w > 0.f); }
     std::fprintf(stderr, "%zu of %zu primary rays hit\n", nbHits, hits.size());
     assert(nbHits > hits.size() / 20);
+
+    // glr::Scene (scene.cpp): the same triangles as the one mesh of a scene -> sendDataToGpu (the reference's bindSSBO
+    // builds the BVH there, scene.cpp:148) -> the same tree through getBVH_NodesToGPUData and through the reference's
+    // own top-down walk of _InternalStruct, and the frame of drawOneFrame = getColor over the primary hits
+    {
+        glr::ScenePtr scene(new glr::Scene());
+        scene->addMaterial(cr::vec4{0.2f, 0.3f, 0.1f, 1.f});
+        cr::MeshPtr mesh(new cr::Mesh());
+        for (const cr::TriangleGPU& t : tris) mesh->_Triangles.emplace_back(t);
+        mesh->setMaterial(1);
+        scene->addMesh(mesh);
+        assert(scene->getNbTriangles() == n && scene->getNbMeshes() == 1 && scene->getNbMaterials() == 2);
+        scene->sendDataToGpu();
+        const std::vector<cr::BVH_NodeGPU> sent = scene->getBVH_NodesToGPUData(scene->getBVH());
+        const std::vector<cr::BVH_NodeGPU> walked = glr::Scene::flattenTopDown(scene->getBVH()->_InternalStruct, n);
+        assert(sent.size() == flat.size() && walked.size() == flat.size());
+        for (size_t i = 0; i < flat.size(); ++i) {
+            assert(std::memcmp(&sent[i]._BoundingBox._Min, &flat[i]._BoundingBox._Min, 12) == 0 &&
+                   std::memcmp(&sent[i]._BoundingBox._Max, &flat[i]._BoundingBox._Max, 12) == 0 &&
+                   sent[i]._TriangleId == flat[i]._TriangleId && sent[i]._LeftChild == flat[i]._LeftChild &&
+                   sent[i]._RightChild == flat[i]._RightChild);
+            assert(std::memcmp(&walked[i]._BoundingBox._Min, &flat[i]._BoundingBox._Min, 12) == 0 &&
+                   std::memcmp(&walked[i]._BoundingBox._Max, &flat[i]._BoundingBox._Max, 12) == 0 &&
+                   walked[i]._TriangleId == flat[i]._TriangleId && walked[i]._LeftChild == flat[i]._LeftChild &&
+                   walked[i]._RightChild == flat[i]._RightChild);
+        }
+        const std::vector<float> frame = scene->drawOneFrame(cam, W, H);
+        const std::vector<cr::MaterialGPU> materials = scene->getMaterialToGPUData();
+        const std::vector<cr::MeshModelGPU> models = scene->getMeshModelToGPUData();
+        std::vector<float> expect(frame.size(), 0.f);
+        HARNESS_CHECK(bvh->context(), rtr_shade(bvh->context(), reinterpret_cast<const rtr_hit*>(hits.data()), hits.size(),
+                                                reinterpret_cast<const rtr_triangle*>(tris.data()), n,
+                                                reinterpret_cast<const rtr_mesh*>(models.data()), 1,
+                                                reinterpret_cast<const rtr_material*>(materials.data()), 2, 0u, nullptr, expect.data()));
+        assert(frame.size() == static_cast<size_t>(W) * H * 4 && std::memcmp(frame.data(), expect.data(), frame.size() * 4) == 0);
+        size_t lit = 0;
+        for (size_t px = 0; px < frame.size(); px += 4) lit += frame[px] != 0.f || frame[px + 1] != 0.f || frame[px + 2] != 0.f;
+        assert(lit > hits.size() / 20);
+        std::fprintf(stderr, "glr::Scene: same %zu nodes, frame of %zu lit pixels equals getColor over the hits\n", sent.size(), lit);
+    }
     return EXIT_SUCCESS;
 }
