@@ -650,7 +650,7 @@ def main():
         # kernels do not -- and with back-to-back rebuilds only the broadcasts starve (measured with the re-ordered
         # schedule: 2 169...2 305 Mrays/s without rows on rank 0, 2 694 with one stripe).
         layout[0] = max(1, layout[0])
-        rank_zero_defers = 2 * layout[0] >= max(layout)
+        rank_zero_defers = 3 * layout[0] >= max(layout)   # 6 of 8 stripes at 2 GPUs, 4 (or 3) at 4: yes; 1 at 8: no
         phases = {"rebuild_ms": serial_ms, "broadcast_ms": bcast_ms, "full_frame_rays_ms_one_gpu": render_ms,
                   "gather_ms": gather_ms, "stripes_of_rank": layout,
                   "broadcast_held_until_next_rebuild_done": bool(rank_zero_defers and not os.environ.get("RTR_BENCH_NO_DEFER"))}
